@@ -1,0 +1,1439 @@
+// lexls_oracle.hpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A plain C++17, Eigen-free restatement of the reference's LexLSE / LexLSI algorithm
+// (jrl-umi3218/lexls v1.0.0, header-only; cited below as <file>:<line> relative to the
+// reference's include/lexls/).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may include, link or execute this file; the product (lexls_b200/) never
+// does.
+//
+// The reference cannot be built in this environment (its only dependency, Eigen >= 3.2, is neither
+// installed nor vendored), so this is a restatement; it is pinned against the reference's own
+// fixtures in tests/test_oracle_*.py (tests/test_01.dat #Solution, the Escande multiplier KAT,
+// the pinv identity, fixed-variables == equality re-posing, LexLSI-final-set == LexLSE).
+//
+// Arithmetic contract ("canonical order").  Eigen's summation order is packet/alignment dependent
+// (the reference says so itself, tests/test_numerical_error.cpp:5-22), so no order is "the"
+// reference order.  This oracle fixes one, chosen so that a warp-per-problem GPU kernel can
+// reproduce it bit for bit:
+//   (S) "sequential": one accumulator, explicit fused multiply-add, ascending index.  Used whenever
+//       many independent outputs exist (per-column dots of a Householder application, the Gauss /
+//       Schur update, gemv rows, initial column norms).
+//   (T) "tree32": the terms are dealt round-robin to 32 partial accumulators (term i -> slot i%32,
+//       fma, ascending i), which are then combined by an xor-butterfly of width
+//       min(32, nextpow2(count)).  Used for reductions that produce ONE scalar (pivot column norm,
+//       Householder tail norm, Householder-sequence dots on a single vector).
+// No other floating-point contraction is allowed: compile with -ffp-contract=off.
+#pragma once
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace lexls_oracle
+{
+typedef unsigned int Index;
+
+// typedefs.h:49-55
+enum TerminationStatus
+{
+    TERMINATION_STATUS_UNKNOWN            = -1,
+    PROBLEM_SOLVED                        = 0,
+    PROBLEM_SOLVED_CYCLING_HANDLING       = 1,
+    MAX_NUMBER_OF_FACTORIZATIONS_EXCEEDED = 2
+};
+// typedefs.h:60-64
+enum ObjectiveType
+{
+    GENERAL_OBJECTIVE       = 0,
+    SIMPLE_BOUNDS_OBJECTIVE = 1
+};
+// typedefs.h:69-76
+enum ConstraintActivationType
+{
+    CTR_INACTIVE           = 0,
+    CTR_ACTIVE_LB          = 1,
+    CTR_ACTIVE_UB          = 2,
+    CTR_ACTIVE_EQ          = 3,
+    CORRECT_SIGN_OF_LAMBDA = 4
+};
+// typedefs.h:537-542
+enum OperationType
+{
+    OPERATION_UNDEFINED = 0,
+    OPERATION_ADD       = 1,
+    OPERATION_REMOVE    = 2
+};
+
+// typedefs.h:127-295 (defaults :268-294).  Regularization is out of scope.
+struct Parameters
+{
+    Index max_number_of_factorizations  = 200;
+    double tol_linear_dependence        = 1e-12;
+    double tol_wrong_sign_lambda        = 1e-08;
+    double tol_correct_sign_lambda      = 1e-12;
+    double tol_feasibility              = 1e-13;
+    bool cycling_handling_enabled       = false;
+    Index cycling_max_counter           = 50;
+    double cycling_relax_step           = 1e-08;
+    bool modify_x_guess_enabled         = false;
+    bool modify_type_active_enabled     = false;
+    bool modify_type_inactive_enabled   = false;
+    bool set_min_init_ctr_violation     = true;
+    bool use_phase1_v0                  = false;
+    bool log_working_set_enabled        = false;
+    bool deactivate_first_wrong_sign    = false;
+};
+
+struct Exception : public std::runtime_error
+{
+    explicit Exception(const char *m) : std::runtime_error(m) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// canonical arithmetic
+// ---------------------------------------------------------------------------------------------
+static inline double fmad(double a, double b, double c)
+{
+    return __builtin_fma(a, b, c);
+}
+
+// (T) tree32 dot product of a[i*sa] and b[i*sb], i = 0..count-1
+static inline double tree32_dot(Index count, const double *a, long sa, const double *b, long sb)
+{
+    double p[32];
+    for (int l = 0; l < 32; l++) p[l] = 0.0;
+    for (Index i = 0; i < count; i++) p[i & 31] = fmad(a[(long)i * sa], b[(long)i * sb], p[i & 31]);
+    Index width = 1;
+    while (width < count && width < 32) width <<= 1;
+    for (Index off = width >> 1; off >= 1; off >>= 1)
+    {
+        double q[32];
+        for (Index l = 0; l < width; l++) q[l] = p[l] + p[l ^ off];
+        for (Index l = 0; l < width; l++) p[l] = q[l];
+    }
+    return p[0];
+}
+
+// utility.h:48-51
+static inline bool isEqual(double a, double b, double tol = 1e-15)
+{
+    return std::fabs(a - b) < tol;
+}
+
+// typedefs.h:621-670
+struct ObjectiveInfo
+{
+    Index dim = 0, rank = 0, first_row_index = 0, first_col_index = 0;
+};
+
+// typedefs.h:380-432
+struct WorkingSetLogEntry
+{
+    Index obj_index;
+    Index ctr_index;
+    int ctr_type;
+    double alpha_or_lambda;
+    Index rank;
+    bool cycling_detected;
+};
+
+// =============================================================================================
+// LexLSE (lexlse.h)
+// =============================================================================================
+class LexLSE
+{
+public:
+    LexLSE() {}
+    LexLSE(Index nVar_, Index nObj_, const Index *ObjDim_)
+    {
+        resize(nVar_, nObj_, ObjDim_);
+        setObjDim(ObjDim_);
+    }
+
+    // lexlse.h:67-103
+    void resize(Index nVar_, Index nObj_, const Index *maxObjDim)
+    {
+        nVar = nVar_;
+        nObj = nObj_;
+        obj_info.assign(nObj, ObjectiveInfo());
+        x.assign(nVar, 0.0); // the reference leaves x uninitialised here; initialize() zeroes the tail
+        maxCtr = 0;
+        for (Index k = 0; k < nObj; k++) maxCtr += maxObjDim[k];
+        ld = maxCtr > 0 ? maxCtr : 1;
+        hh_scalars.assign(maxCtr, 0.0);
+        ctr_type.assign(maxCtr, CTR_INACTIVE);
+        LOD.assign((size_t)ld * (nVar + 1), 0.0);
+        PROBLEM_DATA.assign((size_t)ld * (nVar + 1), 0.0);
+        Index dim = std::max(maxCtr, nVar);
+        dWorkspace.assign(2 * dim + nVar + 1 + 2 * nVar, 0.0);
+        column_permutations.assign(nVar, 0);
+        ColNorms.assign(nVar, 0.0);
+        nVarFixed = nVarFixedInit = 0;
+        fixed_var_index.clear();
+        fixed_var_type.clear();
+        nCtr = 0;
+    }
+
+    // lexlse.h:1426-1442 (+ initialize :1672-1693)
+    void setObjDim(const Index *ObjDim_)
+    {
+        nCtr = 0;
+        for (Index k = 0; k < nObj; k++)
+        {
+            nCtr += ObjDim_[k];
+            obj_info[k].dim = ObjDim_[k];
+            if (k > 0) obj_info[k].first_row_index = obj_info[k - 1].first_row_index + obj_info[k - 1].dim;
+        }
+        if (nCtr > maxCtr) throw Exception("setObjDim: more constraints than allocated");
+        initialize();
+    }
+
+    // lexlse.h:1449-1462
+    void setFixedVariablesCount(Index nVarFixed_)
+    {
+        if (nVarFixed_ > nVar) throw Exception("Cannot fix more than nVar variables");
+        nVarFixed = nVarFixed_;
+        fixed_var_index.resize(nVarFixed);
+        fixed_var_type.resize(nVarFixed);
+    }
+
+    // lexlse.h:1381-1388
+    void fixVariable(Index VarIndex, double VarValue, int type = CTR_ACTIVE_UB)
+    {
+        fixed_var_index[nVarFixedInit] = VarIndex;
+        x[nVarFixedInit]               = VarValue;
+        fixed_var_type[nVarFixedInit]  = type;
+        nVarFixedInit++;
+    }
+
+    void setTolLinearDependence(double t)
+    {
+        tol_linear_dependence = t;
+    }
+
+    // lexlse.h:1522-1530; data is column-major dim x (nVar+1) with leading dimension ldd
+    void setData(Index ObjIndex, const double *data, Index ldd)
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        Index r0 = obj_info[ObjIndex].first_row_index, m = obj_info[ObjIndex].dim;
+        for (Index c = 0; c <= nVar; c++)
+            for (Index i = 0; i < m; i++) L(r0 + i, c) = data[(size_t)c * ldd + i];
+    }
+
+    // lexlse.h:1539-1543; row has nVar entries spaced `stride` apart
+    void setCtr(Index CtrIndex, const double *row, size_t stride, double rhs)
+    {
+        for (Index c = 0; c < nVar; c++) L(CtrIndex, c) = row[c * stride];
+        L(CtrIndex, nVar) = rhs;
+    }
+
+    // lexlse.h:1548-1552
+    void setCtrType(Index ObjIndex, Index CtrIndex, int type)
+    {
+        ctr_type[obj_info[ObjIndex].first_row_index + CtrIndex] = type;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // lexlse.h:117-506 with REGULARIZATION_NONE
+    // -----------------------------------------------------------------------------------------
+    void factorize()
+    {
+        PROBLEM_DATA = LOD; // lexlse.h:119 (kept: get_data() is part of the surface)
+
+        // fixed variables, lexlse.h:132-156
+        if (nVarFixed > 0)
+        {
+            for (Index k = 0; k < nVarFixed; k++)
+            {
+                Index coeff            = fixed_var_index[k];
+                column_permutations[k] = coeff;
+                if (k != coeff)
+                    for (Index r = 0; r < nCtr; r++) std::swap(L(r, k), L(r, coeff));
+                for (Index i = k + 1; i < nVarFixed; i++)
+                    if (fixed_var_index[i] == k)
+                    {
+                        fixed_var_index[i] = coeff;
+                        break;
+                    }
+            }
+            // RHS -= LOD[:,0:nFixed] * x[0:nFixed]   (S): per row, ascending fixed index
+            for (Index r = 0; r < nCtr; r++)
+            {
+                double acc = L(r, nVar);
+                for (Index f = 0; f < nVarFixed; f++) acc = fmad(-L(r, f), x[f], acc);
+                L(r, nVar) = acc;
+            }
+        }
+
+        Index ColIndex         = nVarFixed;
+        Index RemainingColumns = nVar - nVarFixed;
+        if (ColIndex >= nVar) // lexlse.h:164-175
+        {
+            TotalRank = nVarFixed;
+            return;
+        }
+
+        for (Index ObjIndex = 0; ObjIndex < nObj; ObjIndex++)
+        {
+            const Index FirstRowIndex = obj_info[ObjIndex].first_row_index;
+            const Index FirstColIndex = obj_info[ObjIndex].first_col_index = ColIndex;
+            const Index ObjDim                                            = obj_info[ObjIndex].dim;
+
+            // initial squared column norms over this level's rows, lexlse.h:193-196  (S)
+            for (Index k = ColIndex; k < nVar; k++)
+            {
+                double acc = 0.0;
+                for (Index i = 0; i < ObjDim; i++) acc = fmad(L(FirstRowIndex + i, k), L(FirstRowIndex + i, k), acc);
+                ColNorms[k] = acc;
+            }
+
+            for (Index counter = 0; counter < ObjDim; counter++) // lexlse.h:199
+            {
+                const Index RowIndex      = FirstRowIndex + counter;
+                const Index RemainingRows = ObjDim - counter;
+
+                // pivot: first maximum of the (down-dated) norms, lexlse.h:205-206
+                Index maxColNormIndex = ColIndex;
+                double best = ColNorms[ColIndex], second = -1.0;
+                for (Index k = ColIndex + 1; k < nVar; k++)
+                {
+                    if (ColNorms[k] > best)
+                    {
+                        second          = best;
+                        best            = ColNorms[k];
+                        maxColNormIndex = k;
+                    }
+                    else if (ColNorms[k] > second)
+                        second = ColNorms[k];
+                }
+                if (second >= 0.0 && best > 0.0) min_pivot_gap = std::min(min_pivot_gap, (best - second) / best);
+
+                // exact recomputation of the chosen column's norm, lexlse.h:210-211  (T)
+                double maxColNormValue =
+                    tree32_dot(RemainingRows, &L(RowIndex, maxColNormIndex), 1, &L(RowIndex, maxColNormIndex), 1);
+                ColNorms[maxColNormIndex] = maxColNormValue;
+
+                if (maxColNormValue > 0.0)
+                    min_rank_margin = std::min(
+                        min_rank_margin, std::fabs(std::log10(maxColNormValue) - std::log10(tol_linear_dependence)));
+
+                if (maxColNormValue < tol_linear_dependence) break; // lexlse.h:214-217
+
+                // column swap over ALL nCtr rows, lexlse.h:222-232
+                column_permutations[ColIndex] = maxColNormIndex;
+                if (ColIndex != maxColNormIndex)
+                {
+                    for (Index r = 0; r < nCtr; r++) std::swap(L(r, ColIndex), L(r, maxColNormIndex));
+                    std::swap(ColNorms[ColIndex], ColNorms[maxColNormIndex]);
+                }
+
+                // Householder, lexlse.h:239-248 (Eigen primitives restated from
+                // interfaces/matlab-octave/tests/implementation/lexqr/eigen_like_syntax/
+                //   makeHouseholderInPlace.m:33-58, applyHouseholderOnTheLeft.m:11-20)
+                if (RemainingRows > 1)
+                {
+                    double *col       = &L(RowIndex, ColIndex);
+                    double tailSqNorm = tree32_dot(RemainingRows - 1, col + 1, 1, col + 1, 1); // (T)
+                    double c0         = col[0];
+                    double tau, beta;
+                    if (tailSqNorm <= DBL_MIN) // Eigen >= 3.3 (the .m file, Eigen 3.2 style, has == 0)
+                    {
+                        tau  = 0.0;
+                        beta = c0;
+                        for (Index i = 1; i < RemainingRows; i++) col[i] = 0.0;
+                    }
+                    else
+                    {
+                        beta = std::sqrt(fmad(c0, c0, tailSqNorm));
+                        if (c0 >= 0.0) beta = -beta;
+                        double den = c0 - beta;
+                        for (Index i = 1; i < RemainingRows; i++) col[i] = col[i] / den;
+                        tau = (beta - c0) / beta;
+                    }
+                    col[0] = beta;
+                    if (tau != 0.0)
+                    {
+                        // block rows RowIndex.., columns ColIndex+1 .. nVar (RHS included)
+                        for (Index j = ColIndex + 1; j <= nVar; j++)
+                        {
+                            double *a  = &L(RowIndex, j);
+                            double acc = 0.0;
+                            for (Index i = 1; i < RemainingRows; i++) acc = fmad(col[i], a[i], acc); // (S)
+                            double tmp = acc + a[0];
+                            double w   = tau * tmp;
+                            a[0]       = a[0] - w;
+                            for (Index i = 1; i < RemainingRows; i++) a[i] = fmad(-col[i], w, a[i]);
+                        }
+                    }
+                    hh_scalars[FirstRowIndex + counter] = tau;
+                }
+
+                ColIndex++;
+                RemainingColumns = nVar - ColIndex;
+                if (RemainingColumns == 0) break; // lexlse.h:255-258
+
+                // norm down-date, lexlse.h:262-266
+                for (Index j = ColIndex; j < nVar; j++) ColNorms[j] = fmad(-L(RowIndex, j), L(RowIndex, j), ColNorms[j]);
+            }
+
+            const Index ObjRank = obj_info[ObjIndex].rank = ColIndex - FirstColIndex; // lexlse.h:272
+
+            // Gauss step, lexlse.h:431-471
+            if (ObjIndex + 1 < nObj && ObjRank > 0)
+            {
+                const Index FirstRowNext = FirstRowIndex + ObjDim;
+                const Index Rows         = nCtr - FirstRowNext;
+                // Left := Left * inv(R)  (R = upper-triangular ObjRank x ObjRank), column by column.
+                for (Index c = 0; c < ObjRank; c++)
+                {
+                    const double inv = 1.0 / L(FirstRowIndex + c, FirstColIndex + c);
+                    for (Index r = 0; r < Rows; r++)
+                    {
+                        double acc = L(FirstRowNext + r, FirstColIndex + c);
+                        for (Index k = 0; k < c; k++)
+                            acc = fmad(-L(FirstRowNext + r, FirstColIndex + k), L(FirstRowIndex + k, FirstColIndex + c), acc);
+                        L(FirstRowNext + r, FirstColIndex + c) = acc * inv;
+                    }
+                }
+                // Trailing -= Left * Up  (columns ColIndex .. nVar, RHS included)
+                for (Index j = ColIndex; j <= nVar; j++)
+                    for (Index r = 0; r < Rows; r++)
+                    {
+                        double acc = L(FirstRowNext + r, j);
+                        for (Index k = 0; k < ObjRank; k++)
+                            acc = fmad(-L(FirstRowNext + r, FirstColIndex + k), L(FirstRowIndex + k, j), acc);
+                        L(FirstRowNext + r, j) = acc;
+                    }
+            }
+
+            if (RemainingColumns == 0) // lexlse.h:475-490
+            {
+                for (Index k = ObjIndex + 1; k < nObj; k++)
+                    obj_info[k].first_col_index = obj_info[k - 1].first_col_index + obj_info[k - 1].rank;
+                break;
+            }
+        }
+
+        TotalRank = nVarFixed;
+        for (Index k = 0; k < nObj; k++) TotalRank += obj_info[k].rank; // lexlse.h:494-498
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // lexlse.h:1015-1045
+    // -----------------------------------------------------------------------------------------
+    void solve()
+    {
+        Index AccumulatedRanks = 0;
+        for (Index k = nObj; k--;)
+        {
+            const Index ObjRank = obj_info[k].rank;
+            if (ObjRank == 0) continue;
+            const Index fr = obj_info[k].first_row_index, fc = obj_info[k].first_col_index;
+            double *xk = &x[fc];
+            for (Index i = 0; i < ObjRank; i++)
+            {
+                double acc = L(fr + i, nVar);
+                if (AccumulatedRanks > 0)
+                {
+                    const Index fc1 = obj_info[k + 1].first_col_index;
+                    for (Index j = 0; j < AccumulatedRanks; j++) acc = fmad(-L(fr + i, fc1 + j), x[fc1 + j], acc); // (S)
+                }
+                xk[i] = acc;
+            }
+            // upper-triangular solve, column oriented
+            for (Index j = ObjRank; j--;)
+            {
+                xk[j] = xk[j] / L(fr + j, fc + j);
+                for (Index i = 0; i < j; i++) xk[i] = fmad(-L(fr + i, fc + j), xk[j], xk[i]);
+            }
+            AccumulatedRanks += ObjRank;
+        }
+        // x = P*x with P = T_0 T_1 ... T_{TotalRank-1}  (lexlse.h:501-504, :1044, equivalence :1869-1884)
+        for (Index k = TotalRank; k--;) std::swap(x[k], x[column_permutations[k]]);
+    }
+
+    // Q_k * y for level k; y has obj_info[k].dim entries.  householderSequence(...).applyOnTheLeft,
+    // eigen_like_syntax/applyOnTheLeft.m:11-14, householderSequence.m:11-15.
+    void applyQ(Index k, double *y) const
+    {
+        const Index fr = obj_info[k].first_row_index, fc = obj_info[k].first_col_index;
+        const Index dim = obj_info[k].dim, rank = obj_info[k].rank;
+        for (Index i = rank; i--;)
+        {
+            const Index len = dim - i;
+            const double tau = hh_scalars[fr + i];
+            if (len == 1 || tau == 0.0) continue; // 1-row block scales by (1 - tau) with tau == 0
+            const double *ess = &Lc(fr + i + 1, fc + i);
+            double acc = tree32_dot(len - 1, ess, 1, y + i + 1, 1); // (T)
+            double tmp = acc + y[i];
+            double w   = tau * tmp;
+            y[i]       = y[i] - w;
+            for (Index r = 1; r < len; r++) y[i + r] = fmad(-ess[r - 1], w, y[i + r]);
+        }
+    }
+
+    // lexlse.h:1560-1582; returns a pointer to nCtr residuals (v = A x - b restricted to the factorization)
+    const double *get_v()
+    {
+        double *v = &dWorkspace[0];
+        for (Index k = 0; k < nObj; k++)
+        {
+            const Index fr = obj_info[k].first_row_index, dim = obj_info[k].dim, rank = obj_info[k].rank;
+            for (Index i = 0; i < rank; i++) v[fr + i] = 0.0;
+            for (Index i = rank; i < dim; i++) v[fr + i] = -Lc(fr + i, nVar);
+            applyQ(k, v + fr);
+        }
+        return v;
+    }
+
+    // lexlse.h:935-987
+    bool findDescentDirection(int FirstRowIndex,
+                              Index ObjDim,
+                              double &maxAbsValue,
+                              Index &CtrIndex,
+                              const double *lambda,
+                              double tol_wrong_sign_lambda,
+                              double tol_correct_sign_lambda)
+    {
+        bool found = false;
+        for (Index k = 0; k < ObjDim; k++)
+        {
+            Index ind;
+            int *aCtrType;
+            if (FirstRowIndex < 0)
+            {
+                ind      = k;
+                aCtrType = &fixed_var_type[ind];
+            }
+            else
+            {
+                ind      = FirstRowIndex + k;
+                aCtrType = &ctr_type[ind];
+            }
+            if (*aCtrType != CTR_ACTIVE_EQ && *aCtrType != CORRECT_SIGN_OF_LAMBDA)
+            {
+                double aLambda = lambda[ind];
+                if (*aCtrType == CTR_ACTIVE_LB) aLambda = -aLambda;
+                if (aLambda > tol_correct_sign_lambda)
+                    *aCtrType = CORRECT_SIGN_OF_LAMBDA;
+                else if (aLambda < -tol_wrong_sign_lambda)
+                {
+                    if (aLambda < maxAbsValue)
+                    {
+                        if (maxAbsValue < 0.0) min_lambda_gap = std::min(min_lambda_gap, maxAbsValue - aLambda);
+                        found       = true;
+                        maxAbsValue = aLambda;
+                        CtrIndex    = k;
+                    }
+                    else
+                        min_lambda_gap = std::min(min_lambda_gap, aLambda - maxAbsValue);
+                }
+            }
+        }
+        return found;
+    }
+
+    // lexlse.h:611-762.  On exit dWorkspace = [LambdaFixed (nVarFixed) | Lambda (nLambda) | rhs].
+    bool ObjectiveSensitivity(Index ObjIndex,
+                              Index &CtrIndex2Remove,
+                              int &ObjIndex2Remove,
+                              double tol_wrong_sign_lambda,
+                              double tol_correct_sign_lambda,
+                              double &maxAbsValue)
+    {
+        maxAbsValue = 0.0;
+        bool found  = false;
+        Index nLambda = 0, nRank = 0;
+        for (Index k = 0; k < ObjIndex; k++)
+        {
+            nLambda += obj_info[k].dim;
+            nRank += obj_info[k].rank;
+        }
+        nLambda += obj_info[ObjIndex].dim;
+
+        const Index total = nVarFixed + nLambda + nRank + nVarFixed;
+        for (Index i = 0; i < total; i++) dWorkspace[i] = 0.0;
+        double *LambdaFixed = &dWorkspace[0];
+        double *Lambda      = &dWorkspace[nVarFixed];
+        double *rhs         = &dWorkspace[nVarFixed + nLambda];
+
+        Index fr = obj_info[ObjIndex].first_row_index, fc = obj_info[ObjIndex].first_col_index;
+        Index dim = obj_info[ObjIndex].dim, rank = obj_info[ObjIndex].rank;
+
+        for (Index i = rank; i < dim; i++) Lambda[fr + i] = -L(fr + i, nVar); // lexlse.h:658-659
+        applyQ(ObjIndex, Lambda + fr);                                         // :662-664
+
+        found = findDescentDirection((int)fr, dim, maxAbsValue, CtrIndex2Remove, Lambda, tol_wrong_sign_lambda,
+                                     tol_correct_sign_lambda);
+        if (found) ObjIndex2Remove = (int)ObjIndex;
+
+        if (ObjIndex > 0)
+        {
+            subtractTransposeProduct(rhs, fc, fr, dim, Lambda); // :706-707
+            for (Index k = ObjIndex; k--;)
+            {
+                fr   = obj_info[k].first_row_index;
+                fc   = obj_info[k].first_col_index;
+                dim  = obj_info[k].dim;
+                rank = obj_info[k].rank;
+                for (Index i = 0; i < rank; i++) Lambda[fr + i] = rhs[fc + i]; // :719
+                applyQ(k, Lambda + fr);                                          // :722-725
+                subtractTransposeProduct(rhs, fc, fr, dim, Lambda);              // :727-728
+                bool t = findDescentDirection((int)fr, dim, maxAbsValue, CtrIndex2Remove, Lambda,
+                                              tol_wrong_sign_lambda, tol_correct_sign_lambda);
+                if (t) ObjIndex2Remove = (int)k;
+                found = found || t;
+            }
+        }
+
+        if (nVarFixed > 0) // :742-758
+        {
+            for (Index f = 0; f < nVarFixed; f++)
+            {
+                double acc = 0.0;
+                for (Index i = 0; i < nLambda; i++) acc = fmad(L(i, f), Lambda[i], acc); // (S)
+                LambdaFixed[f] = -acc;
+            }
+            bool t = findDescentDirection(-1, nVarFixed, maxAbsValue, CtrIndex2Remove, LambdaFixed,
+                                          tol_wrong_sign_lambda, tol_correct_sign_lambda);
+            if (t) ObjIndex2Remove = -1;
+            found = found || t;
+        }
+        return found;
+    }
+
+    // getters ------------------------------------------------------------------------------
+    const std::vector<double> &get_x() const { return x; }
+    Index getDim(Index k) const { return obj_info[k].dim; }
+    Index getRank(Index k) const { return obj_info[k].rank; }
+    Index getTotalRank() const { return TotalRank; }
+    Index getFixedVariablesCount() const { return nVarFixed; }
+    Index get_nCtr() const { return nCtr; }
+    Index get_ld() const { return ld; }
+    const std::vector<double> &get_lexqr() const { return LOD; }
+    const std::vector<double> &get_data() const { return PROBLEM_DATA; }
+    const std::vector<double> &getWorkspace() const { return dWorkspace; }
+    const std::vector<Index> &getColumnPermutations() const { return column_permutations; }
+    const std::vector<double> &getHouseholderScalars() const { return hh_scalars; }
+    const ObjectiveInfo &getObjInfo(Index k) const { return obj_info[k]; }
+
+    // near-tie diagnostics (not part of the reference): smallest relative gap between the two largest
+    // candidate pivot norms, smallest |log10(norm/tol)| at a rank decision, smallest gap between
+    // competing wrong-sign multipliers.
+    double min_pivot_gap   = 1e300;
+    double min_rank_margin = 1e300;
+    double min_lambda_gap  = 1e300;
+
+private:
+    double &L(Index r, Index c) { return LOD[(size_t)c * ld + r]; }
+    const double &Lc(Index r, Index c) const { return LOD[(size_t)c * ld + r]; }
+
+    // rhs[0:ColDim] -= LOD(rows fr..fr+dim, 0:ColDim)^T * Lambda[fr..fr+dim]   (S) per column
+    void subtractTransposeProduct(double *rhs, Index ColDim, Index fr, Index dim, const double *Lambda)
+    {
+        for (Index c = 0; c < ColDim; c++)
+        {
+            double acc = rhs[c];
+            for (Index i = 0; i < dim; i++) acc = fmad(-L(fr + i, c), Lambda[fr + i], acc);
+            rhs[c] = acc;
+        }
+    }
+
+    // lexlse.h:1672-1693
+    void initialize()
+    {
+        nVarFixedInit = 0;
+        TotalRank     = 0;
+        for (Index k = 0; k < nObj; k++)
+        {
+            obj_info[k].rank            = 0;
+            obj_info[k].first_col_index = 0;
+        }
+        std::fill(hh_scalars.begin(), hh_scalars.end(), 0.0);
+        // NB (reference quirk, replicated): nVarFixed is still the PREVIOUS problem's count here, so
+        // entries [new nVarFixed, old nVarFixed) keep whatever the last solve left in them.
+        for (Index i = nVarFixed; i < nVar; i++) x[i] = 0.0;
+    }
+
+    Index nVar = 0, nObj = 0, nCtr = 0, maxCtr = 0, ld = 1;
+    Index nVarFixed = 0, nVarFixedInit = 0, TotalRank = 0;
+    double tol_linear_dependence = 1e-12;
+    std::vector<ObjectiveInfo> obj_info;
+    std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms;
+    std::vector<int> ctr_type, fixed_var_type;
+    std::vector<Index> fixed_var_index, column_permutations;
+};
+
+// =============================================================================================
+// WorkingSet (workingset.h)
+// =============================================================================================
+class WorkingSet
+{
+public:
+    void resize(Index dim) // :26-33
+    {
+        all_type.resize(dim);
+        reset();
+    }
+    void reset() // :38-47
+    {
+        std::fill(all_type.begin(), all_type.end(), (int)CTR_INACTIVE);
+        active.clear();
+        active_ctr_type.clear();
+        inactive.resize(all_type.size());
+        for (Index i = 0; i < inactive.size(); i++) inactive[i] = i;
+    }
+    void activate(Index CtrIndex, int type) // :57-78
+    {
+        if (all_type[CtrIndex] != CTR_INACTIVE) throw Exception("Cannot activate an active constraint");
+        Index ind     = getCtrIndex(CtrIndex);
+        inactive[ind] = inactive.back();
+        inactive.pop_back();
+        all_type[CtrIndex] = type;
+        active.push_back(CtrIndex);
+        active_ctr_type.push_back(type);
+    }
+    void deactivate(Index CtrIndexActive) // :91-115
+    {
+        Index CtrIndex = active[CtrIndexActive];
+        if (all_type[CtrIndex] == CTR_INACTIVE) throw Exception("Cannot deactivate an inactive constraint");
+        active.erase(active.begin() + CtrIndexActive);
+        active_ctr_type.erase(active_ctr_type.begin() + CtrIndexActive);
+        all_type[CtrIndex] = CTR_INACTIVE;
+        inactive.push_back(CtrIndex);
+    }
+    Index getCtrIndex(Index k) const // :154-168
+    {
+        const std::vector<Index> &v = isActive(k) ? active : inactive;
+        return (Index)(std::find(v.begin(), v.end(), k) - v.begin());
+    }
+    bool isActive(Index k) const { return all_type[k] != CTR_INACTIVE; }
+
+    std::vector<Index> active, inactive;
+    std::vector<int> active_ctr_type, all_type;
+};
+
+// =============================================================================================
+// Objective (objective.h)
+// =============================================================================================
+class Objective
+{
+public:
+    void resize(Index nCtr_, Index nVar_, int obj_type_) // :36-71
+    {
+        obj_type = obj_type_;
+        nCtr     = nCtr_;
+        nVar     = nVar_;
+        ws.resize(nCtr);
+        v.assign(nCtr, 0.0);
+        dv.assign(nCtr, 0.0);
+        Ax.assign(nCtr, 0.0);
+        Adx.assign(nCtr, 0.0);
+        if (obj_type == GENERAL_OBJECTIVE)
+        {
+            data.assign((size_t)nCtr * (nVar + 2), 0.0);
+            lb_index = nVar;
+            ub_index = nVar + 1;
+        }
+        else if (obj_type == SIMPLE_BOUNDS_OBJECTIVE)
+        {
+            data.assign((size_t)nCtr * 2, 0.0);
+            var_index.assign(nCtr, 0);
+            lb_index = 0;
+            ub_index = 1;
+        }
+        else
+            throw Exception("Unknown objective type");
+        v0_is_specified = false;
+    }
+
+    double &D(Index r, Index c) { return data[(size_t)c * nCtr + r]; }
+    const double &D(Index r, Index c) const { return data[(size_t)c * nCtr + r]; }
+
+    // :73-103
+    void ensureZeroCtrViolationForSimpleBounds(std::vector<double> &x)
+    {
+        if (obj_type != SIMPLE_BOUNDS_OBJECTIVE) return;
+        for (Index i = 0; i < nCtr; i++)
+        {
+            Index VarIndex = var_index[i];
+            int t          = ws.all_type[i];
+            if (t == CTR_INACTIVE)
+                x[VarIndex] = 0.5 * (D(i, lb_index) + D(i, ub_index));
+            else if (t == CTR_ACTIVE_EQ || t == CTR_ACTIVE_UB)
+                x[VarIndex] = D(i, ub_index);
+            else if (t == CTR_ACTIVE_LB)
+                x[VarIndex] = D(i, lb_index);
+        }
+    }
+
+    // :115-172
+    void formInitialWorkingSet(std::vector<double> &x, bool modify_type_active, bool modify_type_inactive, bool modify_x_guess)
+    {
+        if (modify_type_active || modify_type_inactive)
+        {
+            for (Index i = 0; i < nCtr; i++)
+            {
+                if (!ws.isActive(i) && modify_type_inactive)
+                {
+                    if (Ax[i] <= D(i, lb_index))
+                        ws.activate(i, CTR_ACTIVE_LB);
+                    else if (Ax[i] >= D(i, ub_index))
+                        ws.activate(i, CTR_ACTIVE_UB);
+                }
+                else if (ws.all_type[i] == CTR_ACTIVE_LB && modify_type_active)
+                {
+                    if (Ax[i] > D(i, lb_index))
+                    {
+                        ws.deactivate(ws.getCtrIndex(i));
+                        if (Ax[i] >= D(i, ub_index)) ws.activate(i, CTR_ACTIVE_UB);
+                    }
+                }
+                else if (ws.all_type[i] == CTR_ACTIVE_UB && modify_type_active)
+                {
+                    if (Ax[i] < D(i, ub_index))
+                    {
+                        ws.deactivate(ws.getCtrIndex(i));
+                        if (Ax[i] <= D(i, lb_index)) ws.activate(i, CTR_ACTIVE_LB);
+                    }
+                }
+            }
+        }
+        if (obj_type == SIMPLE_BOUNDS_OBJECTIVE && modify_x_guess)
+        {
+            ensureZeroCtrViolationForSimpleBounds(x);
+            initialize_Ax(x);
+        }
+    }
+
+    // :183-237
+    void initialize_v0(double tol_feasibility, bool set_min_init_ctr_violation)
+    {
+        for (Index i = 0; i < nCtr; i++) v[i] = Ax[i] - 0.5 * (D(i, lb_index) + D(i, ub_index));
+        for (Index a = 0; a < ws.active.size(); a++)
+        {
+            Index i = ws.active[a];
+            int t   = ws.active_ctr_type[a];
+            if (t == CTR_ACTIVE_LB)
+                v[i] = Ax[i] - D(i, lb_index);
+            else if (t == CTR_ACTIVE_UB)
+                v[i] = Ax[i] - D(i, ub_index);
+        }
+        for (Index i = 0; i < nCtr; i++)
+        {
+            if (ws.isActive(i)) continue;
+            if (set_min_init_ctr_violation)
+            {
+                if (Ax[i] <= D(i, lb_index))
+                    v[i] = Ax[i] - D(i, lb_index);
+                else if (Ax[i] >= D(i, ub_index))
+                    v[i] = Ax[i] - D(i, ub_index);
+                else
+                    v[i] = 0.0;
+            }
+            else if (Ax[i] >= (D(i, lb_index) - tol_feasibility) && Ax[i] <= (D(i, ub_index) + tol_feasibility))
+                v[i] = 0.0;
+        }
+    }
+
+    // out = A * vec (general) or a gather (simple bounds); :242-273   (S) per row, ascending column
+    void multiply(const std::vector<double> &vec, std::vector<double> &out) const
+    {
+        if (obj_type == GENERAL_OBJECTIVE)
+            for (Index i = 0; i < nCtr; i++)
+            {
+                double acc = 0.0;
+                for (Index c = 0; c < nVar; c++) acc = fmad(D(i, c), vec[c], acc);
+                out[i] = acc;
+            }
+        else
+            for (Index i = 0; i < nCtr; i++) out[i] = vec[var_index[i]];
+    }
+    void initialize_Ax(const std::vector<double> &x) { multiply(x, Ax); }
+
+    // :288-338
+    void formStep(const std::vector<double> &dx)
+    {
+        multiply(dx, Adx);
+        for (Index i = 0; i < nCtr; i++) dv[i] = -v[i];
+        for (Index a = 0; a < ws.active.size(); a++)
+        {
+            Index i    = ws.active[a];
+            int t      = ws.active_ctr_type[a];
+            double rhs = (t == CTR_ACTIVE_LB) ? D(i, lb_index) : D(i, ub_index);
+            dv[i]      = dv[i] + ((Ax[i] + Adx[i]) - rhs);
+        }
+    }
+
+    // :353-374
+    void phase1(std::vector<double> &x,
+                bool x_guess_is_specified,
+                bool modify_type_active,
+                bool modify_type_inactive,
+                bool modify_x_guess,
+                bool set_min_init_ctr_violation,
+                double tol_feasibility)
+    {
+        initialize_Ax(x);
+        if (!v0_is_specified)
+        {
+            if (x_guess_is_specified) formInitialWorkingSet(x, modify_type_active, modify_type_inactive, modify_x_guess);
+            initialize_v0(tol_feasibility, set_min_init_ctr_violation);
+        }
+    }
+
+    // :434-494
+    void formLexLSE(LexLSE &lexlse, Index &counter, Index ObjIndex)
+    {
+        if (obj_type == SIMPLE_BOUNDS_OBJECTIVE)
+        {
+            lexlse.setFixedVariablesCount((Index)ws.active.size());
+            for (Index a = 0; a < ws.active.size(); a++)
+            {
+                Index i = ws.active[a];
+                int t   = ws.active_ctr_type[a];
+                if (t == CTR_ACTIVE_LB)
+                    lexlse.fixVariable(var_index[i], D(i, 0), CTR_ACTIVE_LB);
+                else if (t == CTR_ACTIVE_UB)
+                    lexlse.fixVariable(var_index[i], D(i, 1), CTR_ACTIVE_UB);
+                else if (t == CTR_ACTIVE_EQ)
+                    lexlse.fixVariable(var_index[i], D(i, 1), CTR_ACTIVE_EQ);
+            }
+        }
+        else
+        {
+            for (Index a = 0; a < ws.active.size(); a++)
+            {
+                Index i    = ws.active[a];
+                int t      = ws.active_ctr_type[a];
+                double rhs = (t == CTR_ACTIVE_LB) ? D(i, nVar) : D(i, nVar + 1);
+                lexlse.setCtrType(ObjIndex, a, t);
+                lexlse.setCtr(counter, &data[i], nCtr, rhs);
+                counter++;
+            }
+        }
+    }
+
+    // :521-578
+    bool checkBlockingConstraints(Index &CtrIndexBlocking, int &CtrTypeBlocking, double &alpha, double tol_feasibility,
+                                  double &min_alpha_gap) const
+    {
+        const double alpha_input = alpha;
+        for (Index q = 0; q < ws.inactive.size(); q++)
+        {
+            Index i    = ws.inactive[q];
+            double den = Adx[i] - dv[i];
+            int t;
+            double rhs;
+            if (den < -tol_feasibility)
+            {
+                t   = CTR_ACTIVE_LB;
+                rhs = D(i, lb_index);
+            }
+            else if (den > tol_feasibility)
+            {
+                t   = CTR_ACTIVE_UB;
+                rhs = D(i, ub_index);
+            }
+            else
+                continue;
+            double num   = (rhs - Ax[i]) + v[i];
+            double ratio = num / den;
+            if (ratio < 0) ratio = 0;
+            if (ratio < alpha)
+            {
+                if (alpha < 1.0) min_alpha_gap = std::min(min_alpha_gap, alpha - ratio);
+                alpha            = ratio;
+                CtrIndexBlocking = i;
+                CtrTypeBlocking  = t;
+            }
+            else if (ratio < 1.0)
+                min_alpha_gap = std::min(min_alpha_gap, ratio - alpha);
+        }
+        return alpha < alpha_input;
+    }
+
+    // :585-589
+    void step(double alpha)
+    {
+        for (Index i = 0; i < nCtr; i++)
+        {
+            v[i]  = fmad(alpha, dv[i], v[i]);
+            Ax[i] = fmad(alpha, Adx[i], Ax[i]);
+        }
+    }
+
+    // :611-630
+    void getConstraintViolation(std::vector<double> &out) const
+    {
+        out.resize(nCtr);
+        for (Index i = 0; i < nCtr; i++)
+        {
+            if (Ax[i] <= D(i, lb_index))
+                out[i] = Ax[i] - D(i, lb_index);
+            else if (Ax[i] >= D(i, ub_index))
+                out[i] = Ax[i] - D(i, ub_index);
+            else
+                out[i] = 0.0;
+        }
+    }
+
+    // :774-788
+    void relax_bounds(Index CtrIndex, int CtrType, double p)
+    {
+        if (CtrType == CTR_ACTIVE_LB)
+            D(CtrIndex, lb_index) -= p;
+        else if (CtrType == CTR_ACTIVE_UB)
+            D(CtrIndex, ub_index) += p;
+        else
+            throw Exception("Should not be here");
+    }
+
+    // :845-857
+    bool isZeroNormal(Index CtrIndex) const
+    {
+        if (obj_type != GENERAL_OBJECTIVE) return false;
+        double s = 0.0;
+        for (Index c = 0; c < nVar; c++) s = fmad(D(CtrIndex, c), D(CtrIndex, c), s);
+        return s == 0;
+    }
+
+    Index nVar = 0, nCtr = 0, lb_index = 0, ub_index = 0;
+    int obj_type = GENERAL_OBJECTIVE;
+    std::vector<Index> var_index;
+    std::vector<double> data; // column-major nCtr x (nVar+2)  or  nCtr x 2
+    WorkingSet ws;
+    std::vector<double> v, dv, Ax, Adx;
+    bool v0_is_specified = false;
+};
+
+// =============================================================================================
+// LexLSI (lexlsi.h) + CyclingHandler (cycling.h)
+// =============================================================================================
+class LexLSI
+{
+public:
+    LexLSI() {}
+    LexLSI(Index nVar_, Index nObj_, const Index *ObjDim_, const int *ObjType_) { resize(nVar_, nObj_, ObjDim_, ObjType_); }
+
+    // lexlsi.h:77-83, :923-946
+    void resize(Index nVar_, Index nObj_, const Index *ObjDim_, const int *ObjType_)
+    {
+        nVar       = nVar_;
+        nObj       = nObj_;
+        nObjOffset = (ObjType_[0] == SIMPLE_BOUNDS_OBJECTIVE) ? 1 : 0;
+        lexlse.resize(nVar, nObj - nObjOffset, ObjDim_ + nObjOffset);
+        lexlse.setTolLinearDependence(parameters.tol_linear_dependence);
+        nActive.assign(nObj, 0);
+        objectives.assign(nObj, Objective());
+        for (Index k = 0; k < nObj; k++) objectives[k].resize(ObjDim_[k], nVar, ObjType_[k]);
+        x.assign(nVar, 0.0);
+        dx.assign(nVar, 0.0);
+        nIterations = nActivations = nDeactivations = nFactorizations = lexlse_rank = 0;
+        x_guess_is_specified = false;
+        status               = TERMINATION_STATUS_UNKNOWN;
+        cyc_counter          = 0;
+        cyc_prev_op          = OPERATION_UNDEFINED;
+        cyc_prev_obj = cyc_prev_ctr = 0;
+        cyc_prev_type               = CTR_INACTIVE;
+        working_set_log.clear();
+        WS.clear();
+    }
+
+    // lexlsi.h:325-342
+    void setParameters(const Parameters &p)
+    {
+        parameters = p;
+        lexlse.setTolLinearDependence(p.tol_linear_dependence);
+    }
+
+    // lexlsi.h:350-435; data column-major dim x (nVar+2) with leading dimension ldd
+    void setData(Index ObjIndex, const double *data, Index ldd)
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        Objective &o = objectives[ObjIndex];
+        if (o.obj_type != GENERAL_OBJECTIVE) throw Exception("ObjType = GENERAL_OBJECTIVE is assumed");
+        for (Index i = 0; i < o.nCtr; i++)
+        {
+            double bl = data[(size_t)nVar * ldd + i], bu = data[(size_t)(nVar + 1) * ldd + i];
+            if (isEqual(bl, bu))
+            {
+                double s = 0.0;
+                for (Index c = 0; c < nVar; c++) s = fmad(data[(size_t)c * ldd + i], data[(size_t)c * ldd + i], s);
+                if (s > 0) activate(ObjIndex, i, CTR_ACTIVE_EQ, false);
+            }
+            else if (bl > bu)
+                throw Exception("(general) Lower bound is greater than upper bound.");
+        }
+        for (Index c = 0; c < nVar + 2; c++)
+            for (Index i = 0; i < o.nCtr; i++) o.D(i, c) = data[(size_t)c * ldd + i];
+    }
+
+    // lexlsi.h:444-491; data column-major dim x 2
+    void setData(Index ObjIndex, const Index *VarIndex, const double *data, Index ldd)
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        Objective &o = objectives[ObjIndex];
+        if (o.obj_type != SIMPLE_BOUNDS_OBJECTIVE) throw Exception("ObjType = SIMPLE_BOUNDS_OBJECTIVE is assumed");
+        for (Index i = 0; i < o.nCtr; i++)
+        {
+            double bl = data[i], bu = data[(size_t)ldd + i];
+            if (isEqual(bl, bu))
+                activate(ObjIndex, i, CTR_ACTIVE_EQ, false);
+            else if (bl > bu)
+                throw Exception("(simple) Lower bound is greater than upper bound.");
+        }
+        for (Index k = 0; k < o.nCtr; k++)
+            for (Index j = 0; j < o.nCtr; j++)
+                if (VarIndex[k] == VarIndex[j] && j != k) throw Exception("Elements of VarIndex are not unique.");
+        for (Index i = 0; i < o.nCtr; i++)
+        {
+            o.var_index[i] = VarIndex[i];
+            o.D(i, 0)      = data[i];
+            o.D(i, 1)      = data[(size_t)ldd + i];
+        }
+    }
+
+    // lexlsi.h:120-136
+    void api_activate(Index ObjIndex, Index CtrIndex, int type)
+    {
+        if (!objectives[ObjIndex].ws.isActive(CtrIndex))
+            if (type == CTR_ACTIVE_LB || type == CTR_ACTIVE_UB) activate(ObjIndex, CtrIndex, type, false);
+    }
+
+    // lexlsi.h:306-320
+    void set_x0(const double *x0)
+    {
+        for (Index i = 0; i < nVar; i++) x[i] = x0[i];
+        x_guess_is_specified = true;
+    }
+    void set_v0(Index ObjIndex, const double *v0)
+    {
+        Objective &o = objectives[ObjIndex];
+        for (Index i = 0; i < o.nCtr; i++) o.v[i] = v0[i];
+        o.v0_is_specified = true;
+    }
+
+    // lexlsi.h:205-246
+    TerminationStatus solve()
+    {
+        if (parameters.use_phase1_v0)
+            phase1_v0();
+        else
+            phase1();
+        while (1)
+        {
+            verifyWorkingSet();
+            if (status == PROBLEM_SOLVED || status == PROBLEM_SOLVED_CYCLING_HANDLING) break;
+            if (nFactorizations >= parameters.max_number_of_factorizations)
+            {
+                status = MAX_NUMBER_OF_FACTORIZATIONS_EXCEEDED;
+                break;
+            }
+        }
+        return status;
+    }
+
+    // getters -------------------------------------------------------------------------------
+    const std::vector<double> &get_x() const { return x; }
+    const std::vector<double> &get_v(Index k) const { return objectives[k].v; }
+    void getConstraintViolation(Index k, std::vector<double> &out) const { objectives[k].getConstraintViolation(out); }
+    void getActiveCtr(Index k, std::vector<int> &ctr_type) const // lexlsi.h:688-698
+    {
+        const Objective &o = objectives[k];
+        ctr_type.assign(o.nCtr, CTR_INACTIVE);
+        for (Index a = 0; a < o.ws.active.size(); a++) ctr_type[o.ws.active[a]] = o.ws.active_ctr_type[a];
+    }
+    const WorkingSet &getWorkingSet(Index k) const { return objectives[k].ws; }
+    Index getFactorizationsCount() const { return nFactorizations; }
+    Index getActivationsCount() const { return nActivations; }
+    Index getDeactivationsCount() const { return nDeactivations; }
+    Index getIterationsCount() const { return nIterations; }
+    Index getCyclingCounter() const { return cyc_counter; }
+    Index getActiveCtrCount(Index k) const { return (Index)objectives[k].ws.active.size(); }
+    Index getTotalRank() const { return lexlse.getTotalRank(); }
+    TerminationStatus getStatus() const { return status; }
+    LexLSE &getLexLSE() { return lexlse; }
+    Objective &getObjective(Index k) { return objectives[k]; }
+    const std::vector<WorkingSetLogEntry> &getWorkingSetLog() const { return working_set_log; }
+
+    // lexlsi.h:519-526
+    const std::vector<double> &get_xStar()
+    {
+        formLexLSE();
+        lexlse.factorize();
+        lexlse.solve();
+        return lexlse.get_x();
+    }
+
+    // lexlsi.h:552-605: vec_lambda[k] is dim_k x nObj, column-major
+    void getLambda(std::vector<std::vector<double>> &vec_lambda)
+    {
+        Index nActiveCtr = 0;
+        vec_lambda.resize(nObj);
+        for (Index k = 0; k < nObj; k++)
+        {
+            nActiveCtr += getActiveCtrCount(k);
+            vec_lambda[k].assign((size_t)objectives[k].nCtr * nObj, 0.0);
+        }
+        if (status != PROBLEM_SOLVED)
+        {
+            formLexLSE();
+            lexlse.factorize();
+        }
+        std::vector<double> L_active((size_t)nActiveCtr * nObj, 0.0);
+        Index nMeaningful = lexlse.getFixedVariablesCount();
+        Index ctr;
+        int obj;
+        double maxAbs;
+        for (Index k = 0; k < nObj - nObjOffset; k++)
+        {
+            lexlse.ObjectiveSensitivity(k, ctr, obj, parameters.tol_wrong_sign_lambda, parameters.tol_correct_sign_lambda, maxAbs);
+            nMeaningful += lexlse.getDim(k);
+            for (Index i = 0; i < nMeaningful; i++) L_active[(size_t)(nObjOffset + k) * nActiveCtr + i] = lexlse.getWorkspace()[i];
+        }
+        Index acc = 0;
+        for (Index k = 0; k < nObj; k++)
+        {
+            for (Index a = 0; a < getActiveCtrCount(k); a++)
+            {
+                Index ind = objectives[k].ws.active[a];
+                for (Index j = 0; j < nObj; j++)
+                    vec_lambda[k][(size_t)j * objectives[k].nCtr + ind] = L_active[(size_t)j * nActiveCtr + acc + a];
+            }
+            acc += getActiveCtrCount(k);
+        }
+    }
+
+    double min_alpha_gap = 1e300; // near-tie diagnostic for the ratio test (not in the reference)
+
+private:
+    // lexlsi.h:148-173
+    void activate(Index ObjIndex, Index CtrIndex, int type, bool CountActivation = true)
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        if (CtrIndex >= objectives[ObjIndex].nCtr) throw Exception("CtrIndex >= nCtr");
+        WS.push_back(std::make_pair(ObjIndex, CtrIndex));
+        objectives[ObjIndex].ws.activate(CtrIndex, type);
+        if (CountActivation) nActivations++;
+    }
+    // lexlsi.h:181-198
+    void deactivate(Index ObjIndex, Index CtrIndexActive)
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        std::pair<Index, Index> key(ObjIndex, objectives[ObjIndex].ws.active[CtrIndexActive]);
+        WS.erase(std::find(WS.begin(), WS.end(), key));
+        objectives[ObjIndex].ws.deactivate(CtrIndexActive);
+        nDeactivations++;
+    }
+
+    // lexlsi.h:758-793
+    void hot_start_related_tests()
+    {
+        bool partial   = false;
+        bool attempted = objectives[0].v0_is_specified;
+        for (Index k = 1; k < nObj; k++)
+            if (objectives[k].v0_is_specified != attempted)
+            {
+                attempted = true;
+                partial   = true;
+                break;
+            }
+        bool forgot_x = (!x_guess_is_specified) && attempted;
+        if (partial || forgot_x)
+            for (Index k = 0; k < nObj; k++) objectives[k].v0_is_specified = false;
+    }
+
+    // lexlsi.h:816-869
+    void phase1()
+    {
+        hot_start_related_tests();
+        if (!x_guess_is_specified)
+        {
+            formLexLSE();
+            lexlse.factorize();
+            lexlse.solve();
+            lexlse_rank = lexlse.getTotalRank();
+            x           = lexlse.get_x();
+        }
+        for (Index k = 0; k < nObj; k++)
+            objectives[k].phase1(x, x_guess_is_specified, parameters.modify_type_active_enabled,
+                                 parameters.modify_type_inactive_enabled, parameters.modify_x_guess_enabled,
+                                 parameters.set_min_init_ctr_violation, parameters.tol_feasibility);
+        if (x_guess_is_specified)
+        {
+            formLexLSE();
+            lexlse.factorize();
+            lexlse.solve();
+            lexlse_rank = lexlse.getTotalRank();
+            for (Index i = 0; i < nVar; i++) dx[i] = lexlse.get_x()[i] - x[i];
+        }
+        for (Index k = 0; k < nObj; k++) objectives[k].formStep(dx);
+        nFactorizations++;
+    }
+
+    // lexlsi.h:880-915
+    void phase1_v0()
+    {
+        if (!x_guess_is_specified) throw Exception("when use_phase1_v0 = true, x_guess has to be specified");
+        hot_start_related_tests();
+        for (Index k = 0; k < nObj; k++)
+            objectives[k].phase1(x, x_guess_is_specified, parameters.modify_type_active_enabled,
+                                 parameters.modify_type_inactive_enabled, parameters.modify_x_guess_enabled,
+                                 parameters.set_min_init_ctr_violation, parameters.tol_feasibility);
+        for (Index k = 0; k < nObj; k++) objectives[k].formStep(dx);
+    }
+
+    // lexlsi.h:968-982
+    void formLexLSE()
+    {
+        for (Index k = 0; k < nObj; k++) nActive[k] = getActiveCtrCount(k);
+        lexlse.setObjDim(&nActive[0] + nObjOffset);
+        Index counter = 0;
+        for (Index k = 0; k < nObj; k++) objectives[k].formLexLSE(lexlse, counter, k - nObjOffset);
+    }
+
+    // lexlsi.h:1115-1139
+    bool findActiveCtr2Remove_largest(Index &ObjIndex2Remove, Index &CtrIndex2Remove, double &lambda_wrong_sign)
+    {
+        bool found  = false;
+        int obj_int = 0;
+        for (Index k = 0; k < nObj - nObjOffset; k++)
+        {
+            found = lexlse.ObjectiveSensitivity(k, CtrIndex2Remove, obj_int, parameters.tol_wrong_sign_lambda,
+                                                parameters.tol_correct_sign_lambda, lambda_wrong_sign);
+            if (found) break;
+        }
+        ObjIndex2Remove = (Index)(obj_int + (int)nObjOffset);
+        return found;
+    }
+
+    // lexlsi.h:1144-1265
+    OperationType verifyWorkingSet()
+    {
+        Index ObjIndex2Manipulate = 0, CtrIndex2Manipulate = 0;
+        int CtrType2Manipulate  = CTR_INACTIVE;
+        bool normalIteration    = true;
+        OperationType operation = OPERATION_UNDEFINED;
+        Index id_obj = 0, id_ctr = 0;
+        int id_type = CTR_INACTIVE;
+        double alpha;
+
+        if (nIterations != 0)
+        {
+            formLexLSE();
+            lexlse.factorize();
+            lexlse.solve();
+            lexlse_rank = lexlse.getTotalRank();
+            for (Index i = 0; i < nVar; i++) dx[i] = lexlse.get_x()[i] - x[i]; // formStep :987-994
+            for (Index k = 0; k < nObj; k++) objectives[k].formStep(dx);
+            nFactorizations++;
+        }
+        else if (parameters.use_phase1_v0)
+            normalIteration = false;
+
+        // checkBlockingConstraints, lexlsi.h:1006-1029
+        alpha         = 1;
+        bool blocking = false;
+        for (Index k = 0; k < nObj; k++)
+            if (objectives[k].checkBlockingConstraints(CtrIndex2Manipulate, CtrType2Manipulate, alpha,
+                                                       parameters.tol_feasibility, min_alpha_gap))
+                ObjIndex2Manipulate = k;
+        blocking = alpha < 1;
+
+        if (blocking)
+        {
+            id_obj  = ObjIndex2Manipulate;
+            id_ctr  = CtrIndex2Manipulate;
+            id_type = CtrType2Manipulate;
+            if (parameters.log_working_set_enabled)
+                working_set_log.push_back({ObjIndex2Manipulate, CtrIndex2Manipulate, CtrType2Manipulate, alpha, lexlse_rank, false});
+            operation = OPERATION_ADD;
+            activate(ObjIndex2Manipulate, CtrIndex2Manipulate, CtrType2Manipulate);
+        }
+        else if (normalIteration)
+        {
+            double lambda_wrong_sign;
+            if (parameters.deactivate_first_wrong_sign)
+                throw Exception("deactivate_first_wrong_sign is not restated in the oracle");
+            if (findActiveCtr2Remove_largest(ObjIndex2Manipulate, CtrIndex2Manipulate, lambda_wrong_sign))
+            {
+                const WorkingSet &w = objectives[ObjIndex2Manipulate].ws;
+                id_obj              = ObjIndex2Manipulate;
+                id_ctr              = w.active[CtrIndex2Manipulate];
+                id_type             = w.active_ctr_type[CtrIndex2Manipulate];
+                if (parameters.log_working_set_enabled)
+                    working_set_log.push_back({ObjIndex2Manipulate, id_ctr, CTR_INACTIVE, lambda_wrong_sign, lexlse_rank, false});
+                operation = OPERATION_REMOVE;
+                deactivate(ObjIndex2Manipulate, CtrIndex2Manipulate);
+            }
+            else
+                status = PROBLEM_SOLVED;
+        }
+
+        if (alpha > 0)
+        {
+            for (Index i = 0; i < nVar; i++) x[i] = fmad(alpha, dx[i], x[i]);
+            for (Index k = 0; k < nObj; k++) objectives[k].step(alpha);
+        }
+
+        // cycling.h:32-65
+        if (parameters.cycling_handling_enabled && operation != OPERATION_UNDEFINED)
+        {
+            bool cycling_detected = false;
+            TerminationStatus ret = TERMINATION_STATUS_UNKNOWN;
+            bool early            = false;
+            if (operation == OPERATION_ADD && cyc_prev_op == OPERATION_REMOVE && id_obj == cyc_prev_obj &&
+                id_ctr == cyc_prev_ctr && id_type == cyc_prev_type)
+            {
+                if (cyc_counter >= parameters.cycling_max_counter)
+                {
+                    ret   = PROBLEM_SOLVED_CYCLING_HANDLING;
+                    early = true;
+                }
+                else
+                {
+                    objectives[cyc_prev_obj].relax_bounds(cyc_prev_ctr, cyc_prev_type, parameters.cycling_relax_step);
+                    cyc_counter++;
+                    cycling_detected = true;
+                }
+            }
+            if (!early)
+            {
+                cyc_prev_op   = operation;
+                cyc_prev_obj  = id_obj;
+                cyc_prev_ctr  = id_ctr;
+                cyc_prev_type = id_type;
+            }
+            status = ret;
+            if (parameters.log_working_set_enabled) working_set_log.back().cycling_detected = cycling_detected;
+        }
+
+        nIterations++;
+        return operation;
+    }
+
+    Index nVar = 0, nObj = 0, nObjOffset = 0;
+    Index nActivations = 0, nDeactivations = 0, nFactorizations = 0, nIterations = 0, lexlse_rank = 0;
+    bool x_guess_is_specified = false;
+    std::vector<double> x, dx;
+    std::vector<Index> nActive;
+    TerminationStatus status = TERMINATION_STATUS_UNKNOWN;
+    LexLSE lexlse;
+    std::vector<Objective> objectives;
+    std::vector<WorkingSetLogEntry> working_set_log;
+    Parameters parameters;
+    std::vector<std::pair<Index, Index>> WS;
+    // CyclingHandler state (cycling.h:85-109)
+    Index cyc_counter = 0;
+    int cyc_prev_op   = OPERATION_UNDEFINED;
+    Index cyc_prev_obj = 0, cyc_prev_ctr = 0;
+    int cyc_prev_type = CTR_INACTIVE;
+};
+
+} // namespace lexls_oracle
