@@ -1,0 +1,981 @@
+// lexls_b200.cu — C-ABI of the batched LexLSE / LexLSI solver (include/lexls_b200.h) and its kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/lexls_b200.h"
+#include "lexls_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lexls_dev;
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                                        \
+    do                                                                                                                  \
+    {                                                                                                                   \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess)                                                                                          \
+            return fail(LEXLS_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------------
+struct lexls_b200_batch
+{
+    int kind = 0, device = 0;
+    uint64_t batch = 0;
+    Shape sh{};
+    Params pr{};
+    lexls_b200_params_t user_params{};
+    SmemMap sm{};
+    int W = 1;
+    bool DS = false, LG = false;
+    unsigned grid = 0, smem = 0, per_sm = 0;
+    std::string kname;
+    bool planned = false;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+
+    // device buffers
+    double *rec = nullptr, *obj = nullptr, *sb = nullptr, *fval = nullptr, *x0 = nullptr, *v0 = nullptr;
+    unsigned *sbidx = nullptr, *fidx = nullptr;
+    unsigned char *ftype = nullptr, *guess = nullptr;
+    uint64_t rec_stride = 0, obj_stride = 0, sbidx_stride = 0;
+    bool have_x0 = false, have_guess = false;
+    std::vector<char> have_v0;
+    std::vector<char> data_set;
+    double *x = nullptr, *v = nullptr, *viol = nullptr, *lod_scratch = nullptr;
+    unsigned char *act = nullptr;
+    unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
+    int *status = nullptr, *flag = nullptr;
+    unsigned long long *queue = nullptr;
+    uint64_t lod_stride = 0;
+    // staging for host inputs
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+};
+
+static int ensure_stage(lexls_b200_batch *h, size_t bytes)
+{
+    if (h->stage_bytes >= bytes) return 0;
+    if (h->stage) cudaFree(h->stage);
+    h->stage       = nullptr;
+    h->stage_bytes = 0;
+    CK(cudaMalloc(&h->stage, bytes));
+    h->stage_bytes = bytes;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// repack kernels: caller layout -> device records
+// ---------------------------------------------------------------------------------------------------------------
+// dst[p*dstride + c*dld + roff + i] = src[p*sstride + c*sld + i], i < m, c < cols.  flag |= 1 when col lbcol > col ubcol.
+__global__ void repack_level_kernel(double *dst, unsigned long long dstride, int dld, int roff, const double *src,
+                                    unsigned long long sstride, int sld, int m, int cols, unsigned long long batch, int lbcol,
+                                    int ubcol, int *flag)
+{
+    const unsigned long long per = (unsigned long long)m * cols;
+    const unsigned long long tot = per * batch;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < tot;
+         e += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long p = e / per;
+        const unsigned r           = (unsigned)(e - p * per);
+        const int c = r / m, i = r - c * m;
+        const double val = src[p * sstride + (unsigned long long)c * sld + i];
+        dst[p * dstride + (unsigned long long)c * dld + roff + i] = val;
+        if (lbcol >= 0 && c == ubcol)
+        {
+            const double lb = src[p * sstride + (unsigned long long)lbcol * sld + i];
+            if (lb > val) atomicOr(flag, 1);
+        }
+    }
+}
+
+__global__ void check_unique_kernel(const unsigned *idx, unsigned long long stride, int m, unsigned nVar, unsigned long long count,
+                                    int *flag)
+{
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < count;
+         p += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned *v = idx + p * stride;
+        for (int a = 0; a < m; a++)
+        {
+            if (v[a] >= nVar) atomicOr(flag, 4);
+            for (int b = a + 1; b < m; b++)
+                if (v[a] == v[b]) atomicOr(flag, 2);
+        }
+    }
+}
+
+// gather one level of a [B][Mall] result array into a dense [B][m] array
+template <typename T>
+__global__ void slice_level_kernel(T *dst, const T *src, int Mall, int off, int m, unsigned long long batch)
+{
+    const unsigned long long tot = (unsigned long long)m * batch;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < tot;
+         e += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long p = e / m;
+        const int i                = (int)(e - p * m);
+        dst[e]                     = src[p * Mall + off + i];
+    }
+}
+template <typename T>
+__global__ void scatter_level_kernel(T *dst, const T *src, int Mall, int off, int m, unsigned long long batch)
+{
+    const unsigned long long tot = (unsigned long long)m * batch;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < tot;
+         e += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long p = e / m;
+        const int i                = (int)(e - p * m);
+        dst[p * Mall + off + i]    = src[e];
+    }
+}
+
+static unsigned blocks_for(unsigned long long work)
+{
+    unsigned long long b = (work + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148ull * 16) b = 148ull * 16;
+    return (unsigned)b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// planning: shared-memory map and kernel variant
+// ---------------------------------------------------------------------------------------------------------------
+static unsigned align_up(unsigned v, unsigned a)
+{
+    return (v + a - 1) / a * a;
+}
+
+static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
+{
+    SmemMap m{};
+    unsigned o = 0;
+    auto take  = [&](unsigned bytes, unsigned al) {
+        o           = align_up(o, al);
+        unsigned at = o;
+        o += bytes;
+        return at;
+    };
+    const unsigned n = sh.n, M = sh.M, Mall = sh.Mall, m0 = sh.m0, G = sh.G, P = sh.P;
+    // LOD first: it is the target of a TMA bulk copy (LSE) -> 128-byte alignment; size rounded to 16 bytes
+    m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16), 128);
+    m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, 128);
+    m.sb  = take((lsi && DS) ? 2 * m0 * 8 + 16 : 16, 16);
+    m.x = take(n * 8, 8);
+    m.dx = take(n * 8, 8);
+    m.lx = take(n * 8, 8);
+    m.lxo = take(n * 8, 8);
+    m.colnorm = take(n * 8, 8);
+    m.invd = take(n * 8, 8);
+    m.hh = take((M + 1) * 8, 8);
+    m.wsp = take((2 * m0 + M + n + 2) * 8, 8);
+    const unsigned vecs = lsi ? Mall + 1 : 1;
+    m.v = take(vecs * 8, 8);
+    m.dv = take(vecs * 8, 8);
+    m.Ax = take(vecs * 8, 8);
+    m.Adx = take(vecs * 8, 8);
+    m.active = take((Mall + 1) * 2, 4);
+    m.inactive = take((Mall + 1) * 2, 4);
+    m.fidx = take((std::max(m0, (unsigned)sh.nfix) + 1) * 2, 4);
+    m.colperm = take((n + 1) * 2, 4);
+    m.varofcol = take((n + 1) * 2, 4);
+    m.sbidx = take((m0 + 1) * 2, 4);
+    m.atype = take(Mall + 1, 4);
+    m.alltype = take(Mall + 1, 4);
+    m.ctype = take(M + 1, 4);
+    m.ftype = take(std::max(m0, (unsigned)sh.nfix) + 1, 4);
+    m.ldim = take((G + 1) * 4, 4);
+    m.frow = take((G + 1) * 4, 4);
+    m.fcol = take((G + 1) * 4, 4);
+    m.rank = take((G + 1) * 4, 4);
+    m.nact = take((P + 1) * 4, 4);
+    m.ninact = take((P + 1) * 4, 4);
+    m.scal = take(8 * 4, 8);
+    m.mbar = take(8, 8);
+    m.total = align_up(o, 128);
+    return m;
+}
+
+template <typename K> static int occupancy_of(K kernel, int threads, unsigned smem, int *per_sm)
+{
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kernel, threads, smem));
+    return 0;
+}
+
+typedef void (*kernel_fn)(const Shape, const Params, const SmemMap, const Buffers);
+
+static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &name)
+{
+    char buf[64];
+    if (kind == LEXLS_B200_LSE)
+    {
+        snprintf(buf, sizeof buf, "lse_w%d%s", W, LG ? "_lodglobal" : "");
+        name = buf;
+        if (LG) return (kernel_fn)lse_kernel<16, true>;
+        switch (W)
+        {
+        case 1: return (kernel_fn)lse_kernel<1, false>;
+        case 2: return (kernel_fn)lse_kernel<2, false>;
+        case 4: return (kernel_fn)lse_kernel<4, false>;
+        default: return (kernel_fn)lse_kernel<8, false>;
+        }
+    }
+    snprintf(buf, sizeof buf, "lsi_w%d%s", W, LG ? "_lodglobal" : (DS ? "_smemdata" : "_l2data"));
+    name = buf;
+    if (LG) return (kernel_fn)lsi_kernel<16, false, true>;
+    if (DS) switch (W)
+        {
+        case 1: return (kernel_fn)lsi_kernel<1, true, false>;
+        case 2: return (kernel_fn)lsi_kernel<2, true, false>;
+        case 4: return (kernel_fn)lsi_kernel<4, true, false>;
+        default: return (kernel_fn)lsi_kernel<8, true, false>;
+        }
+    switch (W)
+    {
+    case 1: return (kernel_fn)lsi_kernel<1, false, false>;
+    case 2: return (kernel_fn)lsi_kernel<2, false, false>;
+    case 4: return (kernel_fn)lsi_kernel<4, false, false>;
+    default: return (kernel_fn)lsi_kernel<8, false, false>;
+    }
+}
+
+static int plan(lexls_b200_batch *h)
+{
+    if (h->planned) return 0;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const unsigned max_smem = (unsigned)prop.sharedMemPerBlockOptin;
+    const bool lsi          = h->kind == LEXLS_B200_LSI;
+    const int cols          = h->sh.n + 1;
+
+    int W = cols <= 64 ? 1 : (cols <= 128 ? 2 : (cols <= 256 ? 4 : 8));
+    if (const char *e = getenv("LEXLS_B200_WARPS"))
+    {
+        int w = atoi(e);
+        if (w == 1 || w == 2 || w == 4 || w == 8) W = w;
+    }
+    bool DS = lsi, LG = false;
+    if (const char *e = getenv("LEXLS_B200_DATA"))
+    {
+        if (!strcmp(e, "l2")) DS = false;
+    }
+    SmemMap m = build_map(h->sh, lsi, DS, LG);
+    // keep the objective data in shared memory only while at least 3 problems stay resident per SM
+    if (lsi && DS && m.total * 3 > max_smem)
+    {
+        DS = false;
+        m  = build_map(h->sh, lsi, DS, LG);
+    }
+    if (m.total > max_smem || getenv("LEXLS_B200_FORCE_LODGLOBAL"))
+    {
+        LG = true;
+        DS = false;
+        W  = 16;
+        m  = build_map(h->sh, lsi, DS, LG);
+        if (m.total > max_smem) return fail(LEXLS_B200_ECAPACITY, "problem shape exceeds the shared memory of every kernel variant");
+    }
+    h->W  = W;
+    h->DS = DS;
+    h->LG = LG;
+    h->sm = m;
+    h->smem = m.total;
+    kernel_fn k = pick_kernel(h->kind, W, DS, LG, h->kname);
+    int per_sm  = 0;
+    if (int rc = occupancy_of(k, 32 * W, h->smem, &per_sm)) return rc;
+    if (per_sm < 1) return fail(LEXLS_B200_ECAPACITY, "kernel does not fit on an SM");
+    h->per_sm = per_sm;
+    unsigned long long g = (unsigned long long)prop.multiProcessorCount * per_sm;
+    if (g > h->batch) g = h->batch;
+    if (g < 1) g = 1;
+    h->grid = (unsigned)g;
+    if (LG)
+    {
+        h->lod_stride = (uint64_t)h->sh.ld * (h->sh.n + 1);
+        if (h->lod_scratch) cudaFree(h->lod_scratch);
+        CK(cudaMalloc(&h->lod_scratch, sizeof(double) * h->lod_stride * h->grid));
+    }
+    h->planned = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lexls_b200_abi_version(void)
+{
+    return LEXLS_B200_ABI_VERSION;
+}
+const char *lexls_b200_last_error(void)
+{
+    return g_err.c_str();
+}
+void lexls_b200_default_params(lexls_b200_params_t *p)
+{
+    p->max_number_of_factorizations = 200;
+    p->tol_linear_dependence        = 1e-12;
+    p->tol_wrong_sign_lambda        = 1e-08;
+    p->tol_correct_sign_lambda      = 1e-12;
+    p->tol_feasibility              = 1e-13;
+    p->cycling_handling_enabled     = 0;
+    p->cycling_max_counter          = 50;
+    p->cycling_relax_step           = 1e-08;
+    p->regularization_type          = 0;
+    p->modify_x_guess_enabled       = 0;
+    p->modify_type_active_enabled   = 0;
+    p->modify_type_inactive_enabled = 0;
+    p->set_min_init_ctr_violation   = 1;
+    p->use_phase1_v0                = 0;
+    p->log_working_set_enabled      = 0;
+    p->deactivate_first_wrong_sign  = 0;
+}
+int lexls_b200_device_count(int *count)
+{
+    int c         = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess)
+    {
+        *count = 0;
+        return fail(LEXLS_B200_ECUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    return 0;
+}
+
+static void to_dev_params(const lexls_b200_params_t &u, Params &p)
+{
+    p.max_fact     = u.max_number_of_factorizations;
+    p.tol_lindep   = u.tol_linear_dependence;
+    p.tol_wrong    = u.tol_wrong_sign_lambda;
+    p.tol_correct  = u.tol_correct_sign_lambda;
+    p.tol_feas     = u.tol_feasibility;
+    p.cycling      = u.cycling_handling_enabled;
+    p.cyc_max      = u.cycling_max_counter;
+    p.cyc_step     = u.cycling_relax_step;
+    p.mod_x        = u.modify_x_guess_enabled;
+    p.mod_active   = u.modify_type_active_enabled;
+    p.mod_inactive = u.modify_type_inactive_enabled;
+    p.min_viol     = u.set_min_init_ctr_violation;
+    p.phase1_v0    = u.use_phase1_v0;
+}
+
+int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
+                            int device, lexls_b200_batch_t **out)
+{
+    if (!out) return fail(LEXLS_B200_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (kind != LEXLS_B200_LSE && kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "unknown solver kind");
+    if (nVar == 0 || nObj == 0 || !ObjDim) return fail(LEXLS_B200_EINVAL, "nVar, nObj and ObjDim are required");
+    if (nObj > LX_MAX_LEVELS) return fail(LEXLS_B200_ECAPACITY, "more than 16 levels");
+    if (batch == 0) return fail(LEXLS_B200_EINVAL, "empty batch");
+    if (nVar > 60000) return fail(LEXLS_B200_ECAPACITY, "nVar too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LEXLS_B200_ECUDA, "no CUDA device available: lexls_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(LEXLS_B200_EINVAL, "bad device ordinal");
+    for (uint32_t k = 0; k < nObj; k++)
+    {
+        int t = ObjType ? ObjType[k] : 0;
+        if (t != 0 && t != 1) return fail(LEXLS_B200_EINVAL, "Unknown objective type");
+        if (t == 1 && k != 0) return fail(LEXLS_B200_EINVAL, "only the first objective may be SIMPLE_BOUNDS");
+        if (t == 1 && kind == LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "LexLSE has no simple-bounds objective; use set_fixed_variables");
+    }
+    CK(cudaSetDevice(device));
+    lexls_b200_batch *h = new lexls_b200_batch();
+    h->kind   = kind;
+    h->device = device;
+    h->batch  = batch;
+    Shape &s  = h->sh;
+    s.kind    = kind;
+    s.n       = (int)nVar;
+    s.P       = (int)nObj;
+    s.off     = (ObjType && ObjType[0] == 1) ? 1 : 0;
+    s.G       = s.P - s.off;
+    s.m0      = s.off ? (int)ObjDim[0] : 0;
+    s.M       = 0;
+    s.uoff[0] = 0;
+    for (int k = 0; k < s.P; k++)
+    {
+        s.dim[k]      = (int)ObjDim[k];
+        s.uoff[k + 1] = s.uoff[k] + s.dim[k];
+    }
+    s.goff[0] = 0;
+    for (int g = 0; g < s.G; g++) s.goff[g + 1] = s.goff[g] + s.dim[g + s.off];
+    s.M    = s.goff[s.G];
+    s.Mall = s.m0 + s.M;
+    if (s.Mall > 60000) { delete h; return fail(LEXLS_B200_ECAPACITY, "too many constraints"); }
+    if (s.off && s.G == 0) { delete h; return fail(LEXLS_B200_EINVAL, "a problem of one simple-bounds level is not supported"); }
+    s.ld   = std::max(s.M, 1) | 1; // odd
+    s.nfix = 0;
+    if (kind == LEXLS_B200_LSE)
+    {
+        s.ldo         = s.ld;
+        h->rec_stride = ((uint64_t)s.ld * (nVar + 1) + 1) & ~1ull; // whole doubles, 16-byte multiple
+    }
+    else
+    {
+        s.ldo         = std::max(s.M, 1);
+        h->obj_stride = ((uint64_t)s.ldo * (nVar + 2) + 1) & ~1ull;
+    }
+    lexls_b200_default_params(&h->user_params);
+    to_dev_params(h->user_params, h->pr);
+    h->have_v0.assign(s.P, 0);
+    h->data_set.assign(s.P, 0);
+
+    auto bail = [&](int rc) {
+        lexls_b200_destroy(h);
+        return rc;
+    };
+#define CKB(call)                                                                                                       \
+    do                                                                                                                  \
+    {                                                                                                                   \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess) return bail(fail(LEXLS_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    CKB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CKB(cudaEventCreate(&h->ev0));
+    CKB(cudaEventCreate(&h->ev1));
+    const uint64_t B = batch;
+    if (kind == LEXLS_B200_LSE)
+    {
+        CKB(cudaMalloc(&h->rec, sizeof(double) * h->rec_stride * B));
+        CKB(cudaMemsetAsync(h->rec, 0, sizeof(double) * h->rec_stride * B, h->stream));
+        CKB(cudaMalloc(&h->v, sizeof(double) * std::max(s.M, 1) * B));
+    }
+    else
+    {
+        CKB(cudaMalloc(&h->obj, sizeof(double) * h->obj_stride * B));
+        CKB(cudaMemsetAsync(h->obj, 0, sizeof(double) * h->obj_stride * B, h->stream));
+        if (s.m0)
+        {
+            CKB(cudaMalloc(&h->sb, sizeof(double) * 2 * s.m0 * B));
+            CKB(cudaMalloc(&h->sbidx, sizeof(unsigned) * s.m0 * B));
+        }
+        CKB(cudaMalloc(&h->v, sizeof(double) * s.Mall * B));
+        CKB(cudaMalloc(&h->viol, sizeof(double) * s.Mall * B));
+        CKB(cudaMalloc(&h->act, s.Mall * B));
+        CKB(cudaMalloc(&h->order, sizeof(unsigned) * s.Mall * B));
+    }
+    CKB(cudaMalloc(&h->x, sizeof(double) * nVar * B));
+    CKB(cudaMalloc(&h->status, sizeof(int) * B));
+    CKB(cudaMalloc(&h->counters, sizeof(unsigned) * 8 * B));
+    CKB(cudaMalloc(&h->ranks, sizeof(unsigned) * std::max(s.G, 1) * B));
+    CKB(cudaMalloc(&h->colperm, sizeof(unsigned) * nVar * B));
+    CKB(cudaMalloc(&h->queue, sizeof(unsigned long long)));
+    CKB(cudaMalloc(&h->flag, sizeof(int)));
+    CKB(cudaMemsetAsync(h->status, 0xff, sizeof(int) * B, h->stream));
+    CKB(cudaMemsetAsync(h->counters, 0, sizeof(unsigned) * 8 * B, h->stream));
+    CKB(cudaMemsetAsync(h->x, 0, sizeof(double) * nVar * B, h->stream));
+#undef CKB
+    *out = h;
+    return 0;
+}
+
+int lexls_b200_destroy(lexls_b200_batch_t *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
+                    h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int lexls_b200_reset(lexls_b200_batch_t *h)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    h->have_x0    = false;
+    h->have_guess = false;
+    std::fill(h->have_v0.begin(), h->have_v0.end(), 0);
+    if (h->guess) CK(cudaMemsetAsync(h->guess, 0, (size_t)h->sh.Mall * h->batch, h->stream));
+    CK(cudaMemsetAsync(h->status, 0xff, sizeof(int) * h->batch, h->stream));
+    CK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned) * 8 * h->batch, h->stream));
+    CK(cudaMemsetAsync(h->x, 0, sizeof(double) * h->sh.n * h->batch, h->stream));
+    return 0;
+}
+
+int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
+{
+    if (!h || !p) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (p->regularization_type != 0)
+        return fail(LEXLS_B200_EUNSUPPORTED, "regularization is outside the hot-path scope (REGULARIZATION_NONE only)");
+    if (p->deactivate_first_wrong_sign)
+        return fail(LEXLS_B200_EUNSUPPORTED, "deactivate_first_wrong_sign is not implemented (largest-multiplier rule only)");
+    if (p->max_number_of_factorizations == 0) return fail(LEXLS_B200_EINVAL, "max_number_of_factorizations must be positive");
+    h->user_params = *p;
+    to_dev_params(*p, h->pr);
+    return 0;
+}
+
+int lexls_b200_set_stream(lexls_b200_batch_t *h, void *cuda_stream)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return 0;
+}
+
+static int read_flag(lexls_b200_batch *h, int *val)
+{
+    CK(cudaMemcpyAsync(val, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int set_data_impl(lexls_b200_batch *h, uint32_t level, const double *data, uint32_t ld, uint64_t stride, bool on_device)
+{
+    if (!h || !data) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    const Shape &s = h->sh;
+    if ((int)level >= s.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    if (s.off && level == 0) return fail(LEXLS_B200_EINVAL, "ObjType = GENERAL_OBJECTIVE is assumed (use set_simple_bounds)");
+    const int m = s.dim[level], g = (int)level - s.off;
+    const bool lsi = h->kind == LEXLS_B200_LSI;
+    const int cols = s.n + (lsi ? 2 : 1);
+    if (m == 0)
+    {
+        h->data_set[level] = 1;
+        return 0;
+    }
+    if ((int)ld < m) return fail(LEXLS_B200_EINVAL, "Incorrect number of equations (ld < ObjDim)");
+    if (h->batch > 1 && stride < (uint64_t)ld * (cols - 1) + m) return fail(LEXLS_B200_EINVAL, "problem_stride too small");
+    CK(cudaSetDevice(h->device));
+    const double *src = data;
+    if (!on_device)
+    {
+        const size_t bytes = sizeof(double) * (stride * (h->batch - 1) + (uint64_t)ld * (cols - 1) + m);
+        if (int rc = ensure_stage(h, bytes)) return rc;
+        CK(cudaMemcpyAsync(h->stage, data, bytes, cudaMemcpyHostToDevice, h->stream));
+        src = (const double *)h->stage;
+    }
+    CK(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
+    const unsigned long long work = (unsigned long long)m * cols * h->batch;
+    if (lsi)
+        repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->obj, h->obj_stride, s.ldo, s.goff[g], src, stride, (int)ld, m,
+                                                                     cols, h->batch, s.n, s.n + 1, h->flag);
+    else
+        repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->rec, h->rec_stride, s.ld, s.goff[g], src, stride, (int)ld, m,
+                                                                     cols, h->batch, -1, -1, h->flag);
+    CK(cudaGetLastError());
+    int flag = 0;
+    if (int rc = read_flag(h, &flag)) return rc; // also makes the staging buffer reusable / the caller buffer releasable
+    if (flag & 1) return fail(LEXLS_B200_EBOUNDS, "(general) Lower bound is greater than upper bound.");
+    h->data_set[level] = 1;
+    return 0;
+}
+
+int lexls_b200_set_data(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride)
+{
+    return set_data_impl(h, level, data, ld, problem_stride, false);
+}
+int lexls_b200_set_data_dev(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride)
+{
+    return set_data_impl(h, level, data, ld, problem_stride, true);
+}
+
+static int set_sb_impl(lexls_b200_batch *h, const unsigned *var_index, uint64_t index_stride, const double *lbub, uint32_t ld,
+                       uint64_t stride, bool on_device)
+{
+    if (!h || !var_index || !lbub) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    const Shape &s = h->sh;
+    if (h->kind != LEXLS_B200_LSI || !s.off) return fail(LEXLS_B200_EINVAL, "ObjType = SIMPLE_BOUNDS_OBJECTIVE is assumed");
+    const int m = s.m0;
+    if (m == 0)
+    {
+        h->data_set[0] = 1;
+        return 0;
+    }
+    if ((int)ld < m) return fail(LEXLS_B200_EINVAL, "Incorrect number of equations (ld < ObjDim)");
+    if (index_stride != 0 && index_stride < (uint64_t)m) return fail(LEXLS_B200_EINVAL, "index_stride too small");
+    CK(cudaSetDevice(h->device));
+    const uint64_t nidx = index_stride ? (index_stride * (h->batch - 1) + m) : m;
+    const double *src   = lbub;
+    const unsigned *isrc = var_index;
+    if (!on_device)
+    {
+        const size_t dbytes = sizeof(double) * (stride * (h->batch - 1) + (uint64_t)ld + m);
+        const size_t ibytes = sizeof(unsigned) * nidx;
+        if (int rc = ensure_stage(h, dbytes + ibytes + 16)) return rc;
+        CK(cudaMemcpyAsync(h->stage, lbub, dbytes, cudaMemcpyHostToDevice, h->stream));
+        char *ip = (char *)h->stage + ((dbytes + 15) & ~(size_t)15);
+        CK(cudaMemcpyAsync(ip, var_index, ibytes, cudaMemcpyHostToDevice, h->stream));
+        src  = (const double *)h->stage;
+        isrc = (const unsigned *)ip;
+    }
+    CK(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
+    repack_level_kernel<<<blocks_for((unsigned long long)m * 2 * h->batch), 256, 0, h->stream>>>(h->sb, 2ull * m, m, 0, src, stride, (int)ld,
+                                                                                                 m, 2, h->batch, 0, 1, h->flag);
+    CK(cudaGetLastError());
+    if (index_stride)
+    {
+        CK(cudaMemcpy2DAsync(h->sbidx, sizeof(unsigned) * m, isrc, sizeof(unsigned) * index_stride, sizeof(unsigned) * m, h->batch,
+                             cudaMemcpyDeviceToDevice, h->stream));
+        h->sbidx_stride = m;
+    }
+    else
+    {
+        CK(cudaMemcpyAsync(h->sbidx, isrc, sizeof(unsigned) * m, cudaMemcpyDeviceToDevice, h->stream));
+        h->sbidx_stride = 0;
+    }
+    const unsigned long long cnt = index_stride ? h->batch : 1;
+    check_unique_kernel<<<blocks_for(cnt), 256, 0, h->stream>>>(h->sbidx, h->sbidx_stride, m, (unsigned)s.n, cnt, h->flag);
+    CK(cudaGetLastError());
+    int flag = 0;
+    if (int rc = read_flag(h, &flag)) return rc;
+    if (flag & 1) return fail(LEXLS_B200_EBOUNDS, "(simple) Lower bound is greater than upper bound.");
+    if (flag & 2) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
+    if (flag & 4) return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
+    h->data_set[0] = 1;
+    return 0;
+}
+int lexls_b200_set_simple_bounds(lexls_b200_batch_t *h, const uint32_t *var_index, uint64_t index_stride, const double *lbub,
+                                 uint32_t ld, uint64_t problem_stride)
+{
+    return set_sb_impl(h, var_index, index_stride, lbub, ld, problem_stride, false);
+}
+int lexls_b200_set_simple_bounds_dev(lexls_b200_batch_t *h, const uint32_t *var_index, uint64_t index_stride, const double *lbub,
+                                     uint32_t ld, uint64_t problem_stride)
+{
+    return set_sb_impl(h, var_index, index_stride, lbub, ld, problem_stride, true);
+}
+
+int lexls_b200_set_fixed_variables(lexls_b200_batch_t *h, uint32_t count, const uint32_t *var_index, const double *value,
+                                   const uint8_t *type)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (h->kind != LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "fixed variables belong to LexLSE; LexLSI uses a simple-bounds objective");
+    if (count > (uint32_t)h->sh.n) return fail(LEXLS_B200_EINVAL, "Cannot fix more than nVar variables");
+    CK(cudaSetDevice(h->device));
+    if (h->fidx) cudaFree(h->fidx);
+    if (h->fval) cudaFree(h->fval);
+    if (h->ftype) cudaFree(h->ftype);
+    h->fidx = nullptr; h->fval = nullptr; h->ftype = nullptr;
+    h->sh.nfix = (int)count;
+    h->planned = false;
+    if (count == 0) return 0;
+    if (!var_index || !value) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    const uint64_t N = (uint64_t)count * h->batch;
+    for (uint64_t p = 0; p < h->batch; p++)
+        for (uint32_t a = 0; a < count; a++)
+        {
+            if (var_index[p * count + a] >= (uint32_t)h->sh.n) return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
+            for (uint32_t b = a + 1; b < count; b++)
+                if (var_index[p * count + a] == var_index[p * count + b]) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
+        }
+    CK(cudaMalloc(&h->fidx, sizeof(unsigned) * N));
+    CK(cudaMalloc(&h->fval, sizeof(double) * N));
+    CK(cudaMemcpyAsync(h->fidx, var_index, sizeof(unsigned) * N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->fval, value, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+    if (type)
+    {
+        CK(cudaMalloc(&h->ftype, N));
+        CK(cudaMemcpyAsync(h->ftype, type, N, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+} // extern "C"
+template <typename T>
+static int scatter_level(lexls_b200_batch *h, T **dstbuf, uint32_t level, const T *src, bool on_device)
+{
+    const Shape &s = h->sh;
+    if ((int)level >= s.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    CK(cudaSetDevice(h->device));
+    if (!*dstbuf)
+    {
+        CK(cudaMalloc(dstbuf, sizeof(T) * s.Mall * h->batch));
+        CK(cudaMemsetAsync(*dstbuf, 0, sizeof(T) * s.Mall * h->batch, h->stream));
+    }
+    const int m = s.dim[level];
+    if (m == 0) return 0;
+    const T *dsrc = src;
+    if (!on_device)
+    {
+        const size_t bytes = sizeof(T) * m * h->batch;
+        if (int rc = ensure_stage(h, bytes)) return rc;
+        CK(cudaMemcpyAsync(h->stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        dsrc = (const T *)h->stage;
+    }
+    scatter_level_kernel<T><<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>(*dstbuf, dsrc, s.Mall, s.uoff[level], m,
+                                                                                                 h->batch);
+    CK(cudaGetLastError());
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" {
+static int set_guess_impl(lexls_b200_batch *h, uint32_t level, const uint8_t *types, bool on_device)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "active-set guesses belong to LexLSI");
+    if ((int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    if (!types)
+    {
+        if (h->guess && h->sh.dim[level])
+        {
+            std::vector<uint8_t> z((size_t)h->sh.dim[level] * h->batch, 0);
+            return scatter_level<unsigned char>(h, &h->guess, level, z.data(), false);
+        }
+        return 0;
+    }
+    h->have_guess = true;
+    return scatter_level<unsigned char>(h, &h->guess, level, types, on_device);
+}
+int lexls_b200_set_active_guess(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types)
+{
+    return set_guess_impl(h, level, types, false);
+}
+int lexls_b200_set_active_guess_dev(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types)
+{
+    return set_guess_impl(h, level, types, true);
+}
+
+static int set_x0_impl(lexls_b200_batch *h, const double *x0, bool on_device)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "x0 belongs to LexLSI");
+    if (!x0)
+    {
+        h->have_x0 = false;
+        return 0;
+    }
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * h->sh.n * h->batch;
+    if (!h->x0) CK(cudaMalloc(&h->x0, bytes));
+    CK(cudaMemcpyAsync(h->x0, x0, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));
+    h->have_x0 = true;
+    return 0;
+}
+int lexls_b200_set_x0(lexls_b200_batch_t *h, const double *x0)
+{
+    return set_x0_impl(h, x0, false);
+}
+int lexls_b200_set_x0_dev(lexls_b200_batch_t *h, const double *x0)
+{
+    return set_x0_impl(h, x0, true);
+}
+int lexls_b200_set_v0(lexls_b200_batch_t *h, uint32_t level, const double *v0)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "v0 belongs to LexLSI");
+    if ((int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    if (!v0)
+    {
+        h->have_v0[level] = 0;
+        return 0;
+    }
+    h->have_v0[level] = 1;
+    return scatter_level<double>(h, &h->v0, level, v0, false);
+}
+
+// ---- solve ------------------------------------------------------------------------------------------------------
+int lexls_b200_solve_batch(lexls_b200_batch_t *h)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    const Shape &s = h->sh;
+    for (int k = 0; k < s.P; k++)
+        if (!h->data_set[k] && s.dim[k] > 0) return fail(LEXLS_B200_EINVAL, "setData has not been called for every objective");
+    if (int rc = plan(h)) return rc;
+
+    // hot_start_related_tests, lexlsi.h:758-793: v0 is honoured only if given for ALL levels AND x0 is given
+    bool use_v0 = h->v0 != nullptr && h->have_x0;
+    for (int k = 0; k < s.P && use_v0; k++)
+        if (!h->have_v0[k]) use_v0 = false;
+    if (h->kind == LEXLS_B200_LSI && h->pr.phase1_v0 && !h->have_x0)
+        return fail(LEXLS_B200_EINVAL, "when use_phase1_v0 = true, x_guess has to be specified");
+
+    Buffers b{};
+    b.rec          = h->rec;
+    b.obj          = h->obj;
+    b.sb           = h->sb;
+    b.sbidx        = h->sbidx;
+    b.sbidx_stride = h->sbidx_stride;
+    b.fidx         = h->fidx;
+    b.fval         = h->fval;
+    b.ftype        = h->ftype;
+    b.guess        = h->have_guess ? h->guess : nullptr;
+    b.x0           = h->have_x0 ? h->x0 : nullptr;
+    b.v0           = use_v0 ? h->v0 : nullptr;
+    b.rec_stride   = h->rec_stride;
+    b.obj_stride   = h->obj_stride;
+    b.x            = h->x;
+    b.v            = h->v;
+    b.viol         = h->viol;
+    b.act          = h->act;
+    b.order        = h->order;
+    b.status       = h->status;
+    b.counters     = h->counters;
+    b.ranks        = h->ranks;
+    b.colperm      = (h->kind == LEXLS_B200_LSE) ? h->colperm : nullptr;
+    b.queue        = h->queue;
+    b.batch        = h->batch;
+    b.lod_scratch  = h->lod_scratch;
+    b.lod_stride   = h->lod_stride;
+
+    std::string name;
+    kernel_fn k = pick_kernel(h->kind, h->W, h->DS, h->LG, name);
+    CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    void *args[] = {(void *)&h->sh, (void *)&h->pr, (void *)&h->sm, (void *)&b};
+    CK(cudaLaunchKernel((const void *)k, dim3(h->grid), dim3(32 * h->W), args, h->smem, h->stream));
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    return 0;
+}
+
+int lexls_b200_synchronize(lexls_b200_batch_t *h)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int lexls_b200_solve_batch_sync(lexls_b200_batch_t *h)
+{
+    if (int rc = lexls_b200_solve_batch(h)) return rc;
+    return lexls_b200_synchronize(h);
+}
+
+// ---- results ----------------------------------------------------------------------------------------------------
+static int d2h(lexls_b200_batch *h, void *dst, const void *src, size_t bytes)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+} // extern "C"
+template <typename T> static int get_level(lexls_b200_batch *h, uint32_t level, const T *src, T *dst)
+{
+    if (!h || !dst) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    const Shape &s = h->sh;
+    if (!src) return fail(LEXLS_B200_EINVAL, "this result does not exist for this solver kind");
+    const bool lsi = h->kind == LEXLS_B200_LSI;
+    int off, m, width;
+    if (lsi)
+    {
+        if ((int)level >= s.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+        off = s.uoff[level]; m = s.dim[level]; width = s.Mall;
+    }
+    else
+    {
+        if ((int)level >= s.G) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+        off = s.goff[level]; m = s.dim[level]; width = s.M;
+    }
+    if (m == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(T) * m * h->batch;
+    if (int rc = ensure_stage(h, bytes)) return rc;
+    slice_level_kernel<T><<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>((T *)h->stage, src, width, off, m, h->batch);
+    CK(cudaGetLastError());
+    return d2h(h, dst, h->stage, bytes);
+}
+
+extern "C" {
+int lexls_b200_get_x(lexls_b200_batch_t *h, double *x)
+{
+    if (!h || !x) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    return d2h(h, x, h->x, sizeof(double) * h->sh.n * h->batch);
+}
+int lexls_b200_get_v(lexls_b200_batch_t *h, uint32_t level, double *v)
+{
+    return get_level<double>(h, level, h ? h->v : nullptr, v);
+}
+int lexls_b200_get_constraint_violation(lexls_b200_batch_t *h, uint32_t level, double *viol)
+{
+    return get_level<double>(h, level, h ? h->viol : nullptr, viol);
+}
+int lexls_b200_get_active_set(lexls_b200_batch_t *h, uint32_t level, uint8_t *types)
+{
+    return get_level<unsigned char>(h, level, h ? h->act : nullptr, types);
+}
+int lexls_b200_get_active_order(lexls_b200_batch_t *h, uint32_t level, uint32_t *order)
+{
+    return get_level<unsigned>(h, level, h ? h->order : nullptr, order);
+}
+int lexls_b200_get_status(lexls_b200_batch_t *h, int32_t *status)
+{
+    if (!h || !status) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    return d2h(h, status, h->status, sizeof(int) * h->batch);
+}
+int lexls_b200_get_counters(lexls_b200_batch_t *h, uint32_t *counters)
+{
+    if (!h || !counters) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    return d2h(h, counters, h->counters, sizeof(unsigned) * 8 * h->batch);
+}
+int lexls_b200_get_ranks(lexls_b200_batch_t *h, uint32_t *ranks)
+{
+    if (!h || !ranks) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    return d2h(h, ranks, h->ranks, sizeof(unsigned) * h->sh.G * h->batch);
+}
+int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
+{
+    if (!h || !colperm) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (h->kind != LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "column permutations are reported for LexLSE batches");
+    return d2h(h, colperm, h->colperm, sizeof(unsigned) * h->sh.n * h->batch);
+}
+int lexls_b200_device_results(lexls_b200_batch_t *h, const double **x, const int32_t **status, const uint32_t **counters)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (x) *x = h->x;
+    if (status) *status = h->status;
+    if (counters) *counters = h->counters;
+    return 0;
+}
+
+int lexls_b200_kernel_info(lexls_b200_batch_t *h, lexls_b200_kernel_info_t *info)
+{
+    if (!h || !info) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (int rc = plan(h)) return rc;
+    memset(info, 0, sizeof(*info));
+    snprintf(info->name, sizeof(info->name), "%s", h->kname.c_str());
+    info->grid               = h->grid;
+    info->block              = 32 * h->W;
+    info->smem_bytes         = h->smem;
+    info->problems_per_sm    = h->per_sm;
+    info->launches_per_solve = 1;
+    info->warps_per_problem  = h->W;
+    return 0;
+}
+
+int lexls_b200_last_solve_ms(lexls_b200_batch_t *h, float *ms)
+{
+    if (!h || !ms) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (!h->timed) return fail(LEXLS_B200_EINVAL, "no solve has been issued");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+} // extern "C"

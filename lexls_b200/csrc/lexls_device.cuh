@@ -1,0 +1,1472 @@
+// lexls_device.cuh — device side of the batched LexLSE / LexLSI solver (sm_100a, FP64).
+//
+// One "group" of W warps (one CTA) owns one problem at a time; its l-QR work matrix (the reference's LOD,
+// include/lexls/lexlse.h:2827) lives in shared memory for the whole solve, column-major with an ODD leading
+// dimension so that both "lanes over rows" and "lanes over columns" accesses are bank-conflict free.
+// The whole LexLSI active-set loop (lexlsi.h:205-246) runs on the device: no host round trip per iteration.
+//
+// Arithmetic contract (same as oracle/lexls_oracle.hpp, which restates the reference on the CPU):
+//   (S) sequential fused multiply-add, one accumulator, ascending index   -> every per-column / per-row sum
+//   (T) tree32: term i -> lane i%32 (fma, ascending), then xor-butterfly   -> every single-scalar reduction
+// The file is compiled with -fmad=false; every contraction is an explicit fma().
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lexls_dev
+{
+
+#define LX_MAX_LEVELS 16
+
+enum
+{
+    CTR_INACTIVE           = 0,
+    CTR_ACTIVE_LB          = 1,
+    CTR_ACTIVE_UB          = 2,
+    CTR_ACTIVE_EQ          = 3,
+    CORRECT_SIGN_OF_LAMBDA = 4
+};
+enum
+{
+    OP_UNDEFINED = 0,
+    OP_ADD       = 1,
+    OP_REMOVE    = 2
+};
+enum
+{
+    ST_UNKNOWN        = -1,
+    ST_SOLVED         = 0,
+    ST_SOLVED_CYCLING = 1,
+    ST_MAX_FACT       = 2
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------------------------
+struct Shape
+{
+    int kind;  // 0 LSE, 1 LSI
+    int n;     // nVar
+    int P;     // user levels (nObj)
+    int off;   // nObjOffset: 1 when level 0 is SIMPLE_BOUNDS (lexlsi.h:925-929)
+    int G;     // LexLSE levels = P - off
+    int m0;    // rows of the simple-bounds level (0 if none)
+    int M;     // rows of all general levels
+    int Mall;  // m0 + M
+    int ld;    // leading dimension of LOD in shared memory (odd, >= M)
+    int ldo;   // leading dimension of the stacked objective record [M x (n+2)] (LSI) / of the LSE record (= ld)
+    int nfix;  // LSE: number of fixed variables
+    int dim[LX_MAX_LEVELS];       // user ObjDim
+    int uoff[LX_MAX_LEVELS + 1];  // first row of user level k in the "all rows" numbering (simple bounds first)
+    int goff[LX_MAX_LEVELS + 1];  // first row of LexLSE level g in the stacked general rows
+};
+
+struct Params
+{
+    unsigned max_fact;
+    double tol_lindep, tol_wrong, tol_correct, tol_feas;
+    int cycling;
+    unsigned cyc_max;
+    double cyc_step;
+    int mod_x, mod_active, mod_inactive, min_viol, phase1_v0;
+};
+
+// byte offsets into the dynamic shared memory of one group
+struct SmemMap
+{
+    unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx;
+    unsigned active, inactive, atype, alltype, ctype, fidx, ftype, colperm, varofcol, sbidx;
+    unsigned ldim, frow, fcol, rank, nact, ninact, scal, mbar, total;
+};
+
+struct Buffers
+{
+    // inputs
+    const double *rec;      // LSE: [B][rec_stride] smem image of [A|b], column-major ld = shape.ld
+    double *obj;            // LSI: [B][obj_stride] stacked general levels [M x (n+2)] column-major ld = ldo (bounds may be relaxed)
+    double *sb;             // LSI: [B][2*m0] lb | ub of the simple-bounds level
+    const unsigned *sbidx;  // LSI: [B or 1][m0] variable indices
+    unsigned long long sbidx_stride;
+    const unsigned *fidx;   // LSE: [B][nfix]
+    const double *fval;     // LSE: [B][nfix]
+    const unsigned char *ftype;  // LSE: [B][nfix] or null
+    const unsigned char *guess;  // LSI: [B][Mall] or null
+    const double *x0;            // LSI: [B][n] or null
+    const double *v0;            // LSI: [B][Mall] or null (only used when given for every level and x0 is given)
+    unsigned long long rec_stride, obj_stride;
+    // outputs
+    double *x;                 // [B][n]
+    double *v;                 // [B][Mall]  (LSE: [B][M])
+    double *viol;              // [B][Mall]
+    unsigned char *act;        // [B][Mall]
+    unsigned *order;           // [B][Mall]
+    int *status;               // [B]
+    unsigned *counters;        // [B][8]
+    unsigned *ranks;           // [B][G]
+    unsigned *colperm;         // [B][n] or null (debug)
+    unsigned long long *queue; // work counter
+    unsigned long long batch;
+    double *lod_scratch;       // "LOD in global memory" variants: [grid][lod_stride] work matrices (L2 resident)
+    unsigned long long lod_stride;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// group primitives
+// ---------------------------------------------------------------------------------------------------------------
+template <int W> __device__ __forceinline__ void gsync()
+{
+    if constexpr (W == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+__device__ __forceinline__ double bfly_sum(double a)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+
+// (T) dot of two contiguous vectors, result uniform over the warp
+__device__ __forceinline__ double tree32_dot(int count, const double *a, const double *b, int lane)
+{
+    double acc = 0.0;
+    for (int i = lane; i < count; i += 32) acc = fma(a[i], b[i], acc);
+    return bfly_sum(acc);
+}
+
+struct ArgMin
+{
+    double v;
+    int pos;
+};
+// lexicographic (value, position) minimum over the warp
+__device__ __forceinline__ ArgMin bfly_argmin(ArgMin a)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+    {
+        double ov = __shfl_xor_sync(0xffffffffu, a.v, o);
+        int op    = __shfl_xor_sync(0xffffffffu, a.pos, o);
+        if (ov < a.v || (ov == a.v && op < a.pos))
+        {
+            a.v   = ov;
+            a.pos = op;
+        }
+    }
+    return a;
+}
+// (value, position) maximum, ties -> smaller position (Eigen maxCoeff: first maximum)
+__device__ __forceinline__ ArgMin bfly_argmax(ArgMin a)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+    {
+        double ov = __shfl_xor_sync(0xffffffffu, a.v, o);
+        int op    = __shfl_xor_sync(0xffffffffu, a.pos, o);
+        if (ov > a.v || (ov == a.v && op < a.pos))
+        {
+            a.v   = ov;
+            a.pos = op;
+        }
+    }
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-problem view of shared memory
+// ---------------------------------------------------------------------------------------------------------------
+struct Ctx
+{
+    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx;
+    unsigned short *active, *inactive, *fidx, *colperm, *varofcol, *sbidx;
+    unsigned char *atype, *alltype, *ctype, *ftype;
+    int *ldim, *frow, *fcol, *rank, *nact, *ninact, *scal;
+    unsigned long long *mbar;
+};
+
+__device__ __forceinline__ Ctx make_ctx(unsigned char *base, const SmemMap &m)
+{
+    Ctx c;
+    c.LOD      = (double *)(base + m.lod);
+    c.obj      = (double *)(base + m.obj);
+    c.sb       = (double *)(base + m.sb);
+    c.x        = (double *)(base + m.x);
+    c.dx       = (double *)(base + m.dx);
+    c.lx       = (double *)(base + m.lx);
+    c.lxo      = (double *)(base + m.lxo);
+    c.colnorm  = (double *)(base + m.colnorm);
+    c.invd     = (double *)(base + m.invd);
+    c.hh       = (double *)(base + m.hh);
+    c.wsp      = (double *)(base + m.wsp);
+    c.v        = (double *)(base + m.v);
+    c.dv       = (double *)(base + m.dv);
+    c.Ax       = (double *)(base + m.Ax);
+    c.Adx      = (double *)(base + m.Adx);
+    c.active   = (unsigned short *)(base + m.active);
+    c.inactive = (unsigned short *)(base + m.inactive);
+    c.atype    = (unsigned char *)(base + m.atype);
+    c.alltype  = (unsigned char *)(base + m.alltype);
+    c.ctype    = (unsigned char *)(base + m.ctype);
+    c.fidx     = (unsigned short *)(base + m.fidx);
+    c.ftype    = (unsigned char *)(base + m.ftype);
+    c.colperm  = (unsigned short *)(base + m.colperm);
+    c.varofcol = (unsigned short *)(base + m.varofcol);
+    c.sbidx    = (unsigned short *)(base + m.sbidx);
+    c.ldim     = (int *)(base + m.ldim);
+    c.frow     = (int *)(base + m.frow);
+    c.fcol     = (int *)(base + m.fcol);
+    c.rank     = (int *)(base + m.rank);
+    c.nact     = (int *)(base + m.nact);
+    c.ninact   = (int *)(base + m.ninact);
+    c.scal     = (int *)(base + m.scal);
+    c.mbar     = (unsigned long long *)(base + m.mbar);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (cp.async.bulk; SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// bulk copies are limited to < 2^20 bytes per instruction and need 16-byte granularity; issue in chunks
+__device__ __forceinline__ void tma_load_record(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    mbar_expect_tx(bar, bytes);
+    unsigned done = 0;
+    while (done < bytes)
+    {
+        unsigned chunk = bytes - done;
+        if (chunk > 65536u) chunk = 65536u;
+        tma_bulk_g2s((char *)dst + done, (const char *)src + done, chunk, bar);
+        done += chunk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flop accounting: the algorithmic count of BASELINE.md / SURVEY.md 8(d), evaluated with the ACTUAL dims and ranks
+// ---------------------------------------------------------------------------------------------------------------
+struct FlopCount
+{
+    unsigned long long f;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// l-QR factorization, lexlse.h:117-506 (REGULARIZATION_NONE)
+//   G levels with c.ldim[g] rows starting at c.frow[g]; nCtr = total rows; nFixed fixed variables whose values are in
+//   c.lx[0..nFixed) and indices in c.fidx.  Writes c.rank/c.fcol/c.hh/c.invd/c.colperm/c.varofcol; returns TotalRank.
+// ---------------------------------------------------------------------------------------------------------------
+template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const int ld, const int G, const int nCtr,
+                                              const int nFixed, const double tol, FlopCount &fl)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double *const LOD = c.LOD;
+
+    for (int k = tid; k < n; k += NT) c.varofcol[k] = (unsigned short)k;
+    for (int g = tid; g < G; g += NT)
+    {
+        c.rank[g] = 0;
+        c.fcol[g] = 0;
+    }
+    gsync<W>();
+
+    // ---- fixed variables, lexlse.h:132-156 ----------------------------------------------------------------
+    if (nFixed > 0)
+    {
+        for (int k = 0; k < nFixed; k++)
+        {
+            const int coeff = c.fidx[k];
+            if (k != coeff)
+                for (int r = tid; r < nCtr; r += NT)
+                {
+                    double a          = LOD[r + ld * k];
+                    LOD[r + ld * k]     = LOD[r + ld * coeff];
+                    LOD[r + ld * coeff] = a;
+                }
+            gsync<W>(); // everyone has read fidx[k] before it may be patched
+            if (tid == 0)
+            {
+                c.colperm[k] = (unsigned short)coeff;
+                if (k != coeff)
+                {
+                    unsigned short t   = c.varofcol[k];
+                    c.varofcol[k]      = c.varofcol[coeff];
+                    c.varofcol[coeff]  = t;
+                }
+                for (int i = k + 1; i < nFixed; i++)
+                    if (c.fidx[i] == k)
+                    {
+                        c.fidx[i] = (unsigned short)coeff;
+                        break;
+                    }
+            }
+            gsync<W>();
+        }
+        // RHS -= LOD[:, 0:nFixed] * x[0:nFixed]   (S)
+        for (int r = tid; r < nCtr; r += NT)
+        {
+            double acc = LOD[r + ld * n];
+            for (int f = 0; f < nFixed; f++) acc = fma(-LOD[r + ld * f], c.lx[f], acc);
+            LOD[r + ld * n] = acc;
+        }
+        gsync<W>();
+    }
+
+    int ColIndex = nFixed;
+    if (ColIndex >= n) return nFixed; // lexlse.h:164-175
+
+    int sumRank = 0;
+    for (int g = 0; g < G; g++)
+    {
+        const int fr = c.frow[g], dim = c.ldim[g], fc = ColIndex;
+        if (tid == 0) c.fcol[g] = fc;
+
+        // initial squared column norms over this level's rows, lexlse.h:193-196   (S)
+        for (int k = ColIndex + tid; k < n; k += NT)
+        {
+            const double *col = LOD + ld * k + fr;
+            double acc        = 0.0;
+            for (int i = 0; i < dim; i++) acc = fma(col[i], col[i], acc);
+            c.colnorm[k] = acc;
+        }
+        fl.f += 2ull * dim * (n - ColIndex);
+        gsync<W>();
+
+        for (int counter = 0; counter < dim; counter++)
+        {
+            const int row = fr + counter, rem = dim - counter;
+
+            // pivot = first maximum of the down-dated norms, lexlse.h:205-206 (every warp computes it redundantly)
+            ArgMin am;
+            am.v   = -DBL_MAX;
+            am.pos = n;
+            {
+                int k = ColIndex + lane;
+                if (k < n)
+                {
+                    am.v   = c.colnorm[k];
+                    am.pos = k;
+                    for (k += 32; k < n; k += 32)
+                    {
+                        double v = c.colnorm[k];
+                        if (v > am.v)
+                        {
+                            am.v   = v;
+                            am.pos = k;
+                        }
+                    }
+                }
+            }
+            am          = bfly_argmax(am);
+            const int p = am.pos < n ? am.pos : ColIndex;
+
+            // exact norm of the chosen column and of its tail (lexlse.h:210, makeHouseholderInPlace)   (T)
+            const double *colp = LOD + ld * p + row;
+            double acc1 = 0.0, acc2 = 0.0;
+            for (int i = lane; i < rem; i += 32)
+            {
+                double a = colp[i];
+                acc1     = fma(a, a, acc1);
+            }
+            for (int i = lane; i < rem - 1; i += 32)
+            {
+                double a = colp[i + 1];
+                acc2     = fma(a, a, acc2);
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1)
+            {
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+                acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+            }
+            const double maxval = acc1;
+            if (maxval < tol) break; // rank found, lexlse.h:214-217
+            const double c0 = colp[0];
+
+            double tau = 0.0, beta = c0, den = 1.0;
+            bool zero_tail = false;
+            if (rem > 1)
+            {
+                if (acc2 <= DBL_MIN)
+                    zero_tail = true;
+                else
+                {
+                    beta = sqrt(fma(c0, c0, acc2));
+                    if (c0 >= 0.0) beta = -beta;
+                    den = c0 - beta;
+                    tau = (beta - c0) / beta;
+                }
+            }
+            const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c), used by Gauss and solve
+
+            if constexpr (W > 1) gsync<W>(); // all warps finished reading colnorm / column p
+
+            if (tid == 0)
+            {
+                double t          = c.colnorm[ColIndex];
+                c.colnorm[ColIndex] = maxval;
+                c.colperm[ColIndex] = (unsigned short)p;
+                c.invd[ColIndex]    = inv;
+                if (p != ColIndex)
+                {
+                    c.colnorm[p]          = t;
+                    unsigned short s      = c.varofcol[ColIndex];
+                    c.varofcol[ColIndex]  = c.varofcol[p];
+                    c.varofcol[p]         = s;
+                }
+                if (rem > 1) c.hh[row] = tau;
+            }
+            // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242)
+            for (int r = tid; r < nCtr; r += NT)
+            {
+                double a = LOD[r + ld * p];
+                if (p != ColIndex) LOD[r + ld * p] = LOD[r + ld * ColIndex];
+                if (rem > 1)
+                {
+                    if (r == row)
+                        a = beta;
+                    else if (r > row && r < row + rem)
+                        a = zero_tail ? 0.0 : a / den;
+                }
+                LOD[r + ld * ColIndex] = a;
+            }
+            gsync<W>();
+
+            // apply H to columns ColIndex+1 .. n (RHS included), lexlse.h:243-246, and down-date the norms, :262-266
+            {
+                const double *ess = LOD + ld * ColIndex + row;
+                const bool apply  = (rem > 1) && (tau != 0.0);
+                for (int j = ColIndex + 1 + tid; j <= n; j += NT)
+                {
+                    double *colj = LOD + ld * j + row;
+                    double a0    = colj[0];
+                    if (apply)
+                    {
+                        double acc = 0.0;
+                        for (int i = 1; i < rem; i++) acc = fma(ess[i], colj[i], acc);
+                        const double tmp = acc + a0;
+                        const double w   = tau * tmp;
+                        a0               = a0 - w;
+                        colj[0]          = a0;
+                        for (int i = 1; i < rem; i++) colj[i] = fma(-ess[i], w, colj[i]);
+                    }
+                    if (j < n) c.colnorm[j] = fma(-a0, a0, c.colnorm[j]);
+                }
+            }
+            {
+                const unsigned long long m = rem, cc = n - ColIndex;
+                fl.f += 2 * m + (rem > 1 ? 3 * m + 4 + 4 * m * cc : 0) + 2 * (cc - 1);
+            }
+            ColIndex++;
+            gsync<W>();
+            if (ColIndex == n) break; // lexlse.h:255-258
+        }
+
+        const int rank = ColIndex - fc;
+        sumRank += rank;
+        if (tid == 0) c.rank[g] = rank;
+
+        // Gauss step, lexlse.h:431-471
+        if (g + 1 < G && rank > 0)
+        {
+            const int frn = fr + dim, Rows = nCtr - frn;
+            // Left := Left * inv(R), one thread per row of the lower levels
+            for (int r = tid; r < Rows; r += NT)
+            {
+                double *rowp = LOD + frn + r;
+                for (int cc = 0; cc < rank; cc++)
+                {
+                    const double *Rc = LOD + ld * (fc + cc) + fr;
+                    double acc       = rowp[ld * (fc + cc)];
+                    for (int k = 0; k < cc; k++) acc = fma(-rowp[ld * (fc + k)], Rc[k], acc);
+                    rowp[ld * (fc + cc)] = acc * c.invd[fc + cc];
+                }
+            }
+            gsync<W>();
+            // Trailing -= Left * Up over columns ColIndex .. n; work item = (row, strip of JS columns)
+            constexpr int JS = 4;
+            const int ncols = n - ColIndex + 1, nstrips = (ncols + JS - 1) / JS, items = Rows * nstrips;
+            for (int item = tid; item < items; item += NT)
+            {
+                const int s = item / Rows, r = item - s * Rows;
+                const int j0 = ColIndex + s * JS;
+                int jn = n + 1 - j0;
+                if (jn > JS) jn = JS;
+                double *rowp = LOD + frn + r;
+                double acc[JS];
+#pragma unroll
+                for (int jj = 0; jj < JS; jj++) acc[jj] = (jj < jn) ? rowp[ld * (j0 + jj)] : 0.0;
+                for (int k = 0; k < rank; k++)
+                {
+                    const double l   = -rowp[ld * (fc + k)];
+                    const double *up = LOD + fr + k + ld * j0;
+#pragma unroll
+                    for (int jj = 0; jj < JS; jj++)
+                        if (jj < jn) acc[jj] = fma(l, up[ld * jj], acc[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < JS; jj++)
+                    if (jj < jn) rowp[ld * (j0 + jj)] = acc[jj];
+            }
+            fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
+            gsync<W>();
+        }
+
+        if (ColIndex == n) // lexlse.h:475-490
+        {
+            if (tid == 0)
+                for (int k = g + 1; k < G; k++) c.fcol[k] = c.fcol[k - 1] + c.rank[k - 1];
+            break;
+        }
+    }
+    gsync<W>();
+    fl.f += (unsigned long long)sumRank * sumRank;
+    return nFixed + sumRank;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// back-substitution, lexlse.h:1015-1045; result (already un-permuted, x = P*x) in c.lx and c.lxo
+// ---------------------------------------------------------------------------------------------------------------
+template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int ld, const int G)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double *LOD = c.LOD;
+    if (tid < 32)
+    {
+        int accr = 0;
+        for (int g = G; g--;)
+        {
+            const int r = c.rank[g];
+            if (r == 0) continue;
+            const int fr = c.frow[g], fc = c.fcol[g];
+            const int fc1 = (accr > 0) ? c.fcol[g + 1] : 0;
+            if (r <= 32)
+            {
+                double xi = 0.0, inv = 0.0;
+                if (lane < r)
+                {
+                    double acc = LOD[fr + lane + ld * n];
+                    for (int j = 0; j < accr; j++) acc = fma(-LOD[fr + lane + ld * (fc1 + j)], c.lx[fc1 + j], acc);
+                    xi  = acc;
+                    inv = c.invd[fc + lane];
+                }
+                for (int j = r; j--;)
+                {
+                    const double t  = xi * inv;
+                    const double xj = __shfl_sync(0xffffffffu, t, j);
+                    if (lane == j)
+                        xi = xj;
+                    else if (lane < j)
+                        xi = fma(-LOD[fr + lane + ld * (fc + j)], xj, xi);
+                }
+                if (lane < r) c.lx[fc + lane] = xi;
+            }
+            else
+            {
+                for (int i = lane; i < r; i += 32)
+                {
+                    double acc = LOD[fr + i + ld * n];
+                    for (int j = 0; j < accr; j++) acc = fma(-LOD[fr + i + ld * (fc1 + j)], c.lx[fc1 + j], acc);
+                    c.lx[fc + i] = acc;
+                }
+                __syncwarp();
+                for (int j = r; j--;)
+                {
+                    const double xj = c.lx[fc + j] * c.invd[fc + j];
+                    __syncwarp();
+                    if (lane == 0) c.lx[fc + j] = xj;
+                    for (int i = lane; i < j; i += 32) c.lx[fc + i] = fma(-LOD[fr + i + ld * (fc + j)], xj, c.lx[fc + i]);
+                    __syncwarp();
+                }
+            }
+            accr += r;
+            __syncwarp();
+        }
+    }
+    gsync<W>();
+    // x = P*x (lexlse.h:1044): column c of the factorization belongs to variable varofcol[c]
+    for (int k = tid; k < n; k += NT) c.lxo[c.varofcol[k]] = c.lx[k];
+    gsync<W>();
+    for (int k = tid; k < n; k += NT) c.lx[k] = c.lxo[k];
+    gsync<W>();
+}
+
+// Q_g * y for LexLSE level g (householderSequence::applyOnTheLeft); y has ldim[g] entries; one warp, all lanes.
+__device__ __forceinline__ void apply_Q(const Ctx &c, const int ld, const int g, double *y, const int lane)
+{
+    const int fr = c.frow[g], fc = c.fcol[g], dim = c.ldim[g], rank = c.rank[g];
+    for (int i = rank; i--;)
+    {
+        const int len    = dim - i;
+        const double tau = c.hh[fr + i];
+        if (len == 1 || tau == 0.0) continue;
+        const double *ess = c.LOD + fr + i + 1 + ld * (fc + i);
+        double *yt        = y + i + 1;
+        const double acc  = tree32_dot(len - 1, ess, yt, lane);
+        const double y0   = y[i];
+        const double w    = tau * (acc + y0);
+        __syncwarp();
+        if (lane == 0) y[i] = y0 - w;
+        for (int t = lane; t < len - 1; t += 32) yt[t] = fma(-ess[t], w, yt[t]);
+        __syncwarp();
+    }
+}
+
+// residuals of the factorization, lexlse.h:1560-1582, into c.wsp[0..nCtr)   (warp 0)
+template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int ld, const int G)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32)
+    {
+        for (int g = 0; g < G; g++)
+        {
+            const int fr = c.frow[g], dim = c.ldim[g], rank = c.rank[g];
+            for (int i = lane; i < dim; i += 32) c.wsp[fr + i] = (i < rank) ? 0.0 : -c.LOD[fr + i + ld * n];
+            __syncwarp();
+            apply_Q(c, ld, g, c.wsp + fr, lane);
+        }
+    }
+    gsync<W>();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LexLSE kernel: one problem per group, record staged by one TMA bulk copy
+// ---------------------------------------------------------------------------------------------------------------
+template <int W, bool LG>
+__global__ void __launch_bounds__(32 * W) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+                                                      const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
+{
+    constexpr int NT = 32 * W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ctx c = make_ctx(smem_raw, sm);
+    if constexpr (LG) c.LOD = bf.lod_scratch + blockIdx.x * bf.lod_stride;
+    const int tid = threadIdx.x;
+    const int n = sh.n, ld = sh.ld, G = sh.G, nCtr = sh.M;
+
+    if (tid == 0)
+    {
+        mbar_init(c.mbar, 1);
+        fence_mbar_init();
+    }
+    for (int g = tid; g < G; g += NT)
+    {
+        c.ldim[g] = sh.dim[g];
+        c.frow[g] = sh.goff[g];
+    }
+    gsync<W>();
+
+    unsigned parity = 0;
+    for (;;)
+    {
+        if (tid == 0) *(unsigned long long *)c.scal = atomicAdd(bf.queue, 1ull);
+        gsync<W>();
+        const unsigned long long p = *(unsigned long long *)c.scal;
+        if (p >= bf.batch) break;
+
+        // stage [A|b] (already in the shared-memory layout) with one bulk copy
+        if constexpr (LG)
+        {
+            const double *src = bf.rec + p * bf.rec_stride;
+            for (unsigned long long e = tid; e < bf.rec_stride; e += NT) c.LOD[e] = src[e];
+        }
+        else if (tid == 0)
+        {
+            fence_proxy_async();
+            tma_load_record(c.LOD, bf.rec + p * bf.rec_stride, (unsigned)(bf.rec_stride * sizeof(double)), c.mbar);
+        }
+        for (int k = tid; k < nCtr; k += NT) c.hh[k] = 0.0;
+        for (int k = tid; k < n; k += NT) c.lx[k] = 0.0;
+        gsync<W>();
+        for (int f = tid; f < sh.nfix; f += NT)
+        {
+            c.fidx[f] = (unsigned short)bf.fidx[p * sh.nfix + f];
+            c.lx[f]   = bf.fval[p * sh.nfix + f];
+        }
+        if constexpr (!LG)
+        {
+            mbar_wait(c.mbar, parity);
+            parity ^= 1;
+        }
+        gsync<W>();
+
+        FlopCount fl;
+        fl.f                = 0;
+        const int totalRank = lse_factorize<W>(c, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
+        lse_solve<W>(c, n, ld, G);
+        for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
+        if (bf.v)
+        {
+            lse_get_v<W>(c, n, ld, G);
+            for (int k = tid; k < nCtr; k += NT) bf.v[p * nCtr + k] = c.wsp[k];
+        }
+        for (int g = tid; g < G; g += NT) bf.ranks[p * G + g] = c.rank[g];
+        if (bf.colperm)
+            for (int k = tid; k < n; k += NT) bf.colperm[p * n + k] = (k < totalRank) ? c.colperm[k] : 0u;
+        if (tid == 0)
+        {
+            bf.status[p]    = ST_SOLVED;
+            unsigned *cnt   = bf.counters + p * 8;
+            cnt[0]          = 1;
+            cnt[1] = cnt[2] = cnt[3] = cnt[4] = 0;
+            cnt[5]                            = (unsigned)totalRank;
+            cnt[6]                            = (unsigned)nCtr;
+            cnt[7]                            = (unsigned)((fl.f + 500) / 1000);
+        }
+        gsync<W>();
+    }
+}
+
+// ===============================================================================================================
+// LexLSI
+// ===============================================================================================================
+
+// working-set operations, workingset.h:57-115 (one thread)
+__device__ __forceinline__ void ws_activate(const Ctx &c, const Shape &sh, int k, int i, int type)
+{
+    const int o = sh.uoff[k];
+    int ni      = c.ninact[k];
+    int q       = 0;
+    while (q < ni && c.inactive[o + q] != i) q++;
+    c.inactive[o + q] = c.inactive[o + ni - 1];
+    c.ninact[k]       = ni - 1;
+    c.alltype[o + i]  = (unsigned char)type;
+    int na            = c.nact[k];
+    c.active[o + na]  = (unsigned short)i;
+    c.atype[o + na]   = (unsigned char)type;
+    c.nact[k]         = na + 1;
+}
+__device__ __forceinline__ void ws_deactivate(const Ctx &c, const Shape &sh, int k, int a)
+{
+    const int o  = sh.uoff[k];
+    const int i  = c.active[o + a];
+    const int na = c.nact[k];
+    for (int t = a; t + 1 < na; t++)
+    {
+        c.active[o + t] = c.active[o + t + 1];
+        c.atype[o + t]  = c.atype[o + t + 1];
+    }
+    c.nact[k]                   = na - 1;
+    c.alltype[o + i]            = CTR_INACTIVE;
+    c.inactive[o + c.ninact[k]] = (unsigned short)i;
+    c.ninact[k]++;
+}
+
+// bounds of row i of user level k
+template <bool DS> struct ObjView
+{
+    const Ctx &c;
+    const Shape &sh;
+    double *obj; // general rows [M x (n+2)], ld = ldo
+    double *sb;  // [2*m0]
+    __device__ __forceinline__ double A(int grow, int col) const { return obj[grow + sh.ldo * col]; }
+    __device__ __forceinline__ double &lb(int k, int i) const
+    {
+        if (sh.off && k == 0) return sb[i];
+        return obj[sh.goff[k - sh.off] + i + sh.ldo * sh.n];
+    }
+    __device__ __forceinline__ double &ub(int k, int i) const
+    {
+        if (sh.off && k == 0) return sb[sh.m0 + i];
+        return obj[sh.goff[k - sh.off] + i + sh.ldo * (sh.n + 1)];
+    }
+};
+
+// out[all rows] = A * vec (general levels, (S) per row) or a gather (simple bounds); objective.h:242-273
+template <int W, bool DS>
+__device__ __forceinline__ void obj_multiply(const Ctx &c, const Shape &sh, const ObjView<DS> &ov, const double *vec, double *out)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < sh.m0; i += NT) out[i] = vec[c.sbidx[i]];
+    for (int r = tid; r < sh.M; r += NT)
+    {
+        double acc = 0.0;
+        for (int col = 0; col < sh.n; col++) acc = fma(ov.A(r, col), vec[col], acc);
+        out[sh.m0 + r] = acc;
+    }
+}
+
+// Objective::formStep, objective.h:288-338 (Adx must be current)
+template <int W, bool DS> __device__ __forceinline__ void obj_form_dv(const Ctx &c, const Shape &sh, const ObjView<DS> &ov)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x;
+    for (int k = 0; k < sh.P; k++)
+    {
+        const int o = sh.uoff[k];
+        for (int i = tid; i < sh.dim[k]; i += NT)
+        {
+            const int t = c.alltype[o + i];
+            double d    = -c.v[o + i];
+            if (t != CTR_INACTIVE)
+            {
+                const double rhs = (t == CTR_ACTIVE_LB) ? ov.lb(k, i) : ov.ub(k, i);
+                d                = d + ((c.Ax[o + i] + c.Adx[o + i]) - rhs);
+            }
+            c.dv[o + i] = d;
+        }
+    }
+}
+
+// LexLSI::formLexLSE + Objective::formLexLSE, lexlsi.h:968-982, objective.h:434-494; returns nCtr, sets nFixed
+template <int W, bool DS>
+__device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, const ObjView<DS> &ov, int &nFixed, const int nFixedPrev)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x;
+    const int n = sh.n, ld = sh.ld;
+    // setObjDim -> initialize(): hh = 0, x.tail(nVar - OLD nVarFixed) = 0 (quirk kept, see oracle)
+    int nCtr = 0;
+    for (int g = 0; g < sh.G; g++)
+    {
+        const int d = c.nact[g + sh.off];
+        if (tid == 0)
+        {
+            c.ldim[g] = d;
+            c.frow[g] = nCtr;
+        }
+        nCtr += d;
+    }
+    for (int k = tid; k < nCtr; k += NT) c.hh[k] = 0.0;
+    for (int k = nFixedPrev + tid; k < n; k += NT) c.lx[k] = 0.0;
+    gsync<W>();
+    nFixed = 0;
+    if (sh.off)
+    {
+        nFixed = c.nact[0];
+        for (int a = tid; a < nFixed; a += NT)
+        {
+            const int i = c.active[a], t = c.atype[a];
+            c.fidx[a]  = c.sbidx[i];
+            c.ftype[a] = (unsigned char)t;
+            c.lx[a]    = (t == CTR_ACTIVE_LB) ? ov.sb[i] : ov.sb[sh.m0 + i];
+        }
+    }
+    for (int g = 0; g < sh.G; g++)
+    {
+        const int k = g + sh.off, o = sh.uoff[k], go = sh.goff[g], fr = c.frow[g], d = c.ldim[g];
+        for (int a = tid; a < d; a += NT)
+        {
+            const int i = c.active[o + a], t = c.atype[o + a];
+            c.ctype[fr + a] = (unsigned char)t;
+            double *dst     = c.LOD + fr + a;
+            for (int col = 0; col < n; col++) dst[ld * col] = ov.A(go + i, col);
+            dst[ld * n] = (t == CTR_ACTIVE_LB) ? ov.A(go + i, n) : ov.A(go + i, n + 1);
+        }
+    }
+    gsync<W>();
+    return nCtr;
+}
+
+// Lagrange multipliers of LexLSE objective j and the sign test, lexlse.h:611-762 + :935-987   (warp 0 only)
+// returns true when a constraint to drop was found; obj2rem = LexLSE level (or -1 for the fixed variables)
+__device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const int ld, const int j, const int nFixed,
+                                                const double tol_wrong, const double tol_correct, int &ctr2rem, int &obj2rem,
+                                                const int lane)
+{
+    int nLambda = 0, nRank = 0;
+    for (int k = 0; k < j; k++)
+    {
+        nLambda += c.ldim[k];
+        nRank += c.rank[k];
+    }
+    nLambda += c.ldim[j];
+    const int total = nFixed + nLambda + nRank + nFixed;
+    for (int i = lane; i < total; i += 32) c.wsp[i] = 0.0;
+    double *LambdaFixed = c.wsp;
+    double *Lambda      = c.wsp + nFixed;
+    double *rhs         = c.wsp + nFixed + nLambda;
+    __syncwarp();
+
+    ArgMin best;
+    best.v   = 0.0;        // maxAbsValue starts at 0 (lexlse.h:618); candidates are strictly below -tol_wrong
+    best.pos = 0x7fffffff; // scan position: (group order << 16) | k
+
+    auto sign_test = [&](int order, int first, int dim, const double *lam, unsigned char *types) {
+        // findDescentDirection, lexlse.h:935-987
+        for (int k = lane; k < dim; k += 32)
+        {
+            const int t = types[first + k];
+            if (t != CTR_ACTIVE_EQ && t != CORRECT_SIGN_OF_LAMBDA)
+            {
+                double a = lam[first + k];
+                if (t == CTR_ACTIVE_LB) a = -a;
+                if (a > tol_correct)
+                    types[first + k] = CORRECT_SIGN_OF_LAMBDA;
+                else if (a < -tol_wrong)
+                {
+                    const int pos = (order << 16) | k;
+                    if (a < best.v || (a == best.v && pos < best.pos))
+                    {
+                        best.v   = a;
+                        best.pos = pos;
+                    }
+                }
+            }
+        }
+    };
+    auto sub_transpose = [&](int ColDim, int fr, int dim) {
+        // rhs[0:ColDim] -= LOD(fr.., 0:ColDim)^T * Lambda[fr..]   (S) per column
+        for (int col = lane; col < ColDim; col += 32)
+        {
+            const double *colp = c.LOD + ld * col + fr;
+            double acc         = rhs[col];
+            for (int i = 0; i < dim; i++) acc = fma(-colp[i], Lambda[fr + i], acc);
+            rhs[col] = acc;
+        }
+    };
+
+    {
+        const int fr = c.frow[j], dim = c.ldim[j], rank = c.rank[j];
+        for (int i = rank + lane; i < dim; i += 32) Lambda[fr + i] = -c.LOD[fr + i + ld * n];
+        __syncwarp();
+        apply_Q(c, ld, j, Lambda + fr, lane);
+        sign_test(0, fr, dim, Lambda, c.ctype);
+        if (j > 0)
+        {
+            sub_transpose(c.fcol[j], fr, dim);
+            __syncwarp();
+        }
+    }
+    for (int k = j; k--;)
+    {
+        const int fr = c.frow[k], fc = c.fcol[k], dim = c.ldim[k], rank = c.rank[k];
+        for (int i = lane; i < rank; i += 32) Lambda[fr + i] = rhs[fc + i];
+        __syncwarp();
+        apply_Q(c, ld, k, Lambda + fr, lane);
+        sub_transpose(fc, fr, dim);
+        sign_test(j - k, fr, dim, Lambda, c.ctype);
+        __syncwarp();
+    }
+    if (nFixed > 0)
+    {
+        for (int f = lane; f < nFixed; f += 32)
+        {
+            const double *colp = c.LOD + ld * f;
+            double acc         = 0.0;
+            for (int i = 0; i < nLambda; i++) acc = fma(colp[i], Lambda[i], acc);
+            LambdaFixed[f] = -acc;
+        }
+        __syncwarp();
+        sign_test(j + 1, 0, nFixed, LambdaFixed, c.ftype);
+    }
+    best = bfly_argmin(best);
+    __syncwarp();
+    if (best.pos == 0x7fffffff) return false;
+    const int order = best.pos >> 16;
+    ctr2rem         = best.pos & 0xffff;
+    obj2rem         = (order == j + 1) ? -1 : (j - order);
+    return true;
+}
+
+template <int W, bool DS, bool LG>
+__global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+                                                      const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
+{
+    constexpr int NT = 32 * W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ctx c = make_ctx(smem_raw, sm);
+    if constexpr (LG) c.LOD = bf.lod_scratch + blockIdx.x * bf.lod_stride;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = sh.n, ld = sh.ld, G = sh.G, P = sh.P;
+
+    if (tid == 0)
+    {
+        mbar_init(c.mbar, 1);
+        fence_mbar_init();
+    }
+    gsync<W>();
+    unsigned parity = 0;
+
+    for (;;)
+    {
+        if (tid == 0) *(unsigned long long *)c.scal = atomicAdd(bf.queue, 1ull);
+        gsync<W>();
+        const unsigned long long p = *(unsigned long long *)c.scal;
+        if (p >= bf.batch) break;
+
+        double *gobj = bf.obj + p * bf.obj_stride;
+        double *gsb  = bf.sb ? bf.sb + p * 2ull * sh.m0 : nullptr;
+        ObjView<DS> ov{c, sh, DS ? c.obj : gobj, DS ? c.sb : gsb};
+
+        // ---- stage the objective record -----------------------------------------------------------------------
+        if constexpr (DS)
+        {
+            if (tid == 0)
+            {
+                fence_proxy_async();
+                tma_load_record(c.obj, gobj, (unsigned)(bf.obj_stride * sizeof(double)), c.mbar);
+            }
+            for (int i = tid; i < 2 * sh.m0; i += NT) c.sb[i] = gsb[i];
+        }
+        for (int i = tid; i < sh.m0; i += NT) c.sbidx[i] = (unsigned short)bf.sbidx[p * bf.sbidx_stride + i];
+        const bool have_x0 = bf.x0 != nullptr;
+        const bool have_v0 = bf.v0 != nullptr;
+        for (int k = tid; k < n; k += NT)
+        {
+            c.x[k]  = have_x0 ? bf.x0[p * n + k] : 0.0;
+            c.dx[k] = 0.0;
+            c.lx[k] = 0.0;
+        }
+        for (int i = tid; i < sh.Mall; i += NT)
+        {
+            c.v[i]       = have_v0 ? bf.v0[p * sh.Mall + i] : 0.0;
+            c.dv[i]      = 0.0;
+            c.alltype[i] = CTR_INACTIVE;
+        }
+        for (int k = 0; k < P; k++)
+        {
+            const int o = sh.uoff[k];
+            for (int i = tid; i < sh.dim[k]; i += NT) c.inactive[o + i] = (unsigned short)i;
+            if (tid == 0)
+            {
+                c.nact[k]   = 0;
+                c.ninact[k] = sh.dim[k];
+            }
+        }
+        if constexpr (DS)
+        {
+            mbar_wait(c.mbar, parity);
+            parity ^= 1;
+        }
+        gsync<W>();
+
+        // ---- initial working set: equalities in setData order (lexlsi.h:369-385, :463-476), then the user guess ---
+        // The per-row decisions are taken in parallel into byte flags (scratch: the not-yet-used dv / Adx arrays);
+        // one thread then replays them in the reference's order, which fixes the order of active[] / inactive[].
+        {
+            unsigned char *eqflag = (unsigned char *)c.Adx, *gs = (unsigned char *)c.dv;
+            for (int k = 0; k < P; k++)
+            {
+                const int o = sh.uoff[k];
+                for (int i = tid; i < sh.dim[k]; i += NT)
+                {
+                    const double bl = ov.lb(k, i), bu = ov.ub(k, i);
+                    bool eq = fabs(bl - bu) < 1e-15; // isEqual, utility.h:48-51
+                    if (eq && !(sh.off && k == 0))
+                    {
+                        // don't activate 0*x = b rows, lexlsi.h:377
+                        const int r = sh.goff[k - sh.off] + i;
+                        double s    = 0.0;
+                        for (int col = 0; col < n; col++) s = fma(ov.A(r, col), ov.A(r, col), s);
+                        eq = s > 0;
+                    }
+                    eqflag[o + i] = eq;
+                    gs[o + i]     = bf.guess ? bf.guess[p * sh.Mall + o + i] : 0;
+                }
+            }
+            gsync<W>();
+            if (tid == 0)
+            {
+                for (int k = 0; k < P; k++)
+                    for (int i = 0; i < sh.dim[k]; i++)
+                        if (eqflag[sh.uoff[k] + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
+                if (bf.guess)
+                    for (int k = 0; k < P; k++)
+                        for (int i = 0; i < sh.dim[k]; i++)
+                        {
+                            const int t = gs[sh.uoff[k] + i];
+                            if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[sh.uoff[k] + i] == CTR_INACTIVE)
+                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
+                        }
+            }
+            gsync<W>();
+            for (int i = tid; i < sh.Mall; i += NT) c.dv[i] = 0.0;
+            gsync<W>();
+        }
+
+        unsigned nIter = 0, nFact = 0, nAct = 0, nDeact = 0, cycCounter = 0;
+        int status = ST_UNKNOWN, totalRank = 0, nFixed = 0, nFixedPrev = 0;
+        int cycPrevOp = OP_UNDEFINED, cycPrevObj = 0, cycPrevCtr = 0, cycPrevType = CTR_INACTIVE;
+        FlopCount fl;
+        fl.f = 0;
+
+        auto factor_and_solve = [&]() {
+            const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
+            nFixedPrev     = nFixed;
+            totalRank      = lse_factorize<W>(c, n, ld, G, nCtr, nFixed, pr.tol_lindep, fl);
+            lse_solve<W>(c, n, ld, G);
+        };
+
+        // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------
+        if (!pr.phase1_v0 && !have_x0)
+        {
+            factor_and_solve();
+            for (int k = tid; k < n; k += NT) c.x[k] = c.lx[k];
+            gsync<W>();
+        }
+        // Objective::phase1 for every level, objective.h:353-374
+        obj_multiply<W, DS>(c, sh, ov, c.x, c.Ax);
+        gsync<W>();
+        if (!have_v0)
+        {
+            if (have_x0 && (pr.mod_active || pr.mod_inactive || pr.mod_x))
+            {
+                // formInitialWorkingSet, objective.h:115-172 — sequential semantics, level by level
+                for (int k = 0; k < P; k++)
+                {
+                    if (tid == 0 && (pr.mod_active || pr.mod_inactive))
+                    {
+                        const int o = sh.uoff[k];
+                        for (int i = 0; i < sh.dim[k]; i++)
+                        {
+                            const int t     = c.alltype[o + i];
+                            const double ax = c.Ax[o + i];
+                            if (t == CTR_INACTIVE && pr.mod_inactive)
+                            {
+                                if (ax <= ov.lb(k, i))
+                                    ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                else if (ax >= ov.ub(k, i))
+                                    ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                            }
+                            else if (t == CTR_ACTIVE_LB && pr.mod_active)
+                            {
+                                if (ax > ov.lb(k, i))
+                                {
+                                    int a = 0;
+                                    while (c.active[o + a] != i) a++;
+                                    ws_deactivate(c, sh, k, a);
+                                    if (ax >= ov.ub(k, i)) ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                }
+                            }
+                            else if (t == CTR_ACTIVE_UB && pr.mod_active)
+                            {
+                                if (ax < ov.ub(k, i))
+                                {
+                                    int a = 0;
+                                    while (c.active[o + a] != i) a++;
+                                    ws_deactivate(c, sh, k, a);
+                                    if (ax <= ov.lb(k, i)) ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                }
+                            }
+                        }
+                    }
+                    gsync<W>();
+                    if (k == 0 && sh.off && pr.mod_x)
+                    {
+                        // ensureZeroCtrViolationForSimpleBounds, objective.h:73-103; then every Ax is rebuilt from the new x
+                        for (int i = tid; i < sh.m0; i += NT)
+                        {
+                            const int t = c.alltype[i];
+                            double val;
+                            if (t == CTR_INACTIVE)
+                                val = 0.5 * (ov.sb[i] + ov.sb[sh.m0 + i]);
+                            else if (t == CTR_ACTIVE_LB)
+                                val = ov.sb[i];
+                            else
+                                val = ov.sb[sh.m0 + i];
+                            c.x[c.sbidx[i]] = val;
+                        }
+                        gsync<W>();
+                        obj_multiply<W, DS>(c, sh, ov, c.x, c.Ax);
+                        gsync<W>();
+                    }
+                }
+            }
+            // initialize_v0, objective.h:183-237
+            for (int k = 0; k < P; k++)
+            {
+                const int o = sh.uoff[k];
+                for (int i = tid; i < sh.dim[k]; i += NT)
+                {
+                    const int t     = c.alltype[o + i];
+                    const double ax = c.Ax[o + i], bl = ov.lb(k, i), bu = ov.ub(k, i);
+                    double val = ax - 0.5 * (bl + bu);
+                    if (t == CTR_ACTIVE_LB)
+                        val = ax - bl;
+                    else if (t == CTR_ACTIVE_UB)
+                        val = ax - bu;
+                    else if (t == CTR_INACTIVE)
+                    {
+                        if (pr.min_viol)
+                        {
+                            if (ax <= bl)
+                                val = ax - bl;
+                            else if (ax >= bu)
+                                val = ax - bu;
+                            else
+                                val = 0.0;
+                        }
+                        else if (ax >= (bl - pr.tol_feas) && ax <= (bu + pr.tol_feas))
+                            val = 0.0;
+                    }
+                    c.v[o + i] = val;
+                }
+            }
+            gsync<W>();
+        }
+        if (!pr.phase1_v0)
+        {
+            if (have_x0)
+            {
+                factor_and_solve();
+                for (int k = tid; k < n; k += NT) c.dx[k] = c.lx[k] - c.x[k];
+                gsync<W>();
+            }
+            nFact++;
+        }
+        obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
+        gsync<W>();
+        obj_form_dv<W, DS>(c, sh, ov);
+        gsync<W>();
+
+        // ---- active-set loop, lexlsi.h:223-244; body = verifyWorkingSet :1144-1265 ------------------------------
+        for (;;)
+        {
+            bool normalIteration = true;
+            if (nIter != 0)
+            {
+                factor_and_solve();
+                for (int k = tid; k < n; k += NT) c.dx[k] = c.lx[k] - c.x[k];
+                gsync<W>();
+                obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
+                gsync<W>();
+                obj_form_dv<W, DS>(c, sh, ov);
+                gsync<W>();
+                nFact++;
+            }
+            else if (pr.phase1_v0)
+                normalIteration = false;
+
+            // ratio test, lexlsi.h:1006-1029 + objective.h:521-578: first strict minimum in scan order
+            ArgMin bl;
+            bl.v   = 1.0;
+            bl.pos = 0x7fffffff;
+            for (int k = 0; k < P; k++)
+            {
+                const int o = sh.uoff[k], ni = c.ninact[k];
+                for (int q = lane; q < ni; q += 32)
+                {
+                    const int i      = c.inactive[o + q];
+                    const double den = c.Adx[o + i] - c.dv[o + i];
+                    double rhs;
+                    int t;
+                    if (den < -pr.tol_feas)
+                    {
+                        t   = CTR_ACTIVE_LB;
+                        rhs = ov.lb(k, i);
+                    }
+                    else if (den > pr.tol_feas)
+                    {
+                        t   = CTR_ACTIVE_UB;
+                        rhs = ov.ub(k, i);
+                    }
+                    else
+                        continue;
+                    const double num = (rhs - c.Ax[o + i]) + c.v[o + i];
+                    double ratio     = num / den;
+                    if (ratio < 0) ratio = 0;
+                    const int pos = ((o + q) << 1) | (t == CTR_ACTIVE_UB);
+                    if (ratio < bl.v)
+                    {
+                        bl.v   = ratio;
+                        bl.pos = pos;
+                    }
+                }
+            }
+            bl                 = bfly_argmin(bl);
+            const double alpha = bl.v;
+            int operation      = OP_UNDEFINED;
+            int idObj = 0, idCtr = 0, idType = CTR_INACTIVE;
+
+            if (alpha < 1.0)
+            {
+                // blocking constraint -> activate, lexlsi.h:1181-1198
+                const int gq = bl.pos >> 1;
+                int k        = 0;
+                while (gq >= sh.uoff[k + 1]) k++;
+                idObj  = k;
+                idCtr  = c.inactive[gq];
+                idType = (bl.pos & 1) ? CTR_ACTIVE_UB : CTR_ACTIVE_LB;
+                gsync<W>();
+                if (tid == 0) ws_activate(c, sh, idObj, idCtr, idType);
+                nAct++;
+                operation = OP_ADD;
+            }
+            else if (normalIteration)
+            {
+                // findActiveCtr2Remove_largest, lexlsi.h:1115-1139
+                gsync<W>();
+                if (tid < 32)
+                {
+                    int found = 0, ctr2rem = 0, obj2rem = 0;
+                    for (int j = 0; j < G; j++)
+                        if (lse_sensitivity(c, n, ld, j, nFixed, pr.tol_wrong, pr.tol_correct, ctr2rem, obj2rem, lane))
+                        {
+                            found = 1;
+                            break;
+                        }
+                    if (lane == 0)
+                    {
+                        c.scal[2] = found;
+                        c.scal[3] = ctr2rem;
+                        c.scal[4] = obj2rem + sh.off;
+                    }
+                }
+                gsync<W>();
+                if (c.scal[2])
+                {
+                    idObj  = c.scal[4];
+                    idCtr  = c.active[sh.uoff[idObj] + c.scal[3]];
+                    idType = c.atype[sh.uoff[idObj] + c.scal[3]];
+                    gsync<W>();
+                    if (tid == 0) ws_deactivate(c, sh, idObj, c.scal[3]);
+                    nDeact++;
+                    operation = OP_REMOVE;
+                }
+                else
+                    status = ST_SOLVED;
+            }
+
+            // step, lexlsi.h:1243-1250, objective.h:585-589
+            if (alpha > 0)
+            {
+                for (int k = tid; k < n; k += NT) c.x[k] = fma(alpha, c.dx[k], c.x[k]);
+                for (int i = tid; i < sh.Mall; i += NT)
+                {
+                    c.v[i]  = fma(alpha, c.dv[i], c.v[i]);
+                    c.Ax[i] = fma(alpha, c.Adx[i], c.Ax[i]);
+                }
+            }
+
+            // cycling handler, cycling.h:32-65
+            if (pr.cycling && operation != OP_UNDEFINED)
+            {
+                int ret    = ST_UNKNOWN;
+                bool early = false;
+                if (operation == OP_ADD && cycPrevOp == OP_REMOVE && idObj == cycPrevObj && idCtr == cycPrevCtr &&
+                    idType == cycPrevType)
+                {
+                    if (cycCounter >= pr.cyc_max)
+                    {
+                        ret   = ST_SOLVED_CYCLING;
+                        early = true;
+                    }
+                    else
+                    {
+                        if (tid == 0)
+                        {
+                            if (cycPrevType == CTR_ACTIVE_LB)
+                                ov.lb(cycPrevObj, cycPrevCtr) -= pr.cyc_step;
+                            else
+                                ov.ub(cycPrevObj, cycPrevCtr) += pr.cyc_step;
+                        }
+                        cycCounter++;
+                    }
+                }
+                if (!early)
+                {
+                    cycPrevOp   = operation;
+                    cycPrevObj  = idObj;
+                    cycPrevCtr  = idCtr;
+                    cycPrevType = idType;
+                }
+                status = ret;
+            }
+            nIter++;
+            gsync<W>();
+
+            if (status == ST_SOLVED || status == ST_SOLVED_CYCLING) break;
+            if (nFact >= pr.max_fact)
+            {
+                status = ST_MAX_FACT;
+                break;
+            }
+        }
+
+        // ---- results ------------------------------------------------------------------------------------------
+        for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.x[k];
+        unsigned nActive = 0;
+        for (int k = 0; k < P; k++)
+        {
+            const int o = sh.uoff[k];
+            nActive += c.nact[k];
+            for (int i = tid; i < sh.dim[k]; i += NT)
+            {
+                const unsigned long long gi = p * sh.Mall + o + i;
+                if (bf.v) bf.v[gi] = c.v[o + i];
+                if (bf.act) bf.act[gi] = c.alltype[o + i];
+                if (bf.order) bf.order[gi] = (i < c.nact[k]) ? (unsigned)c.active[o + i] : 0xFFFFFFFFu;
+                if (bf.viol)
+                {
+                    // getConstraintViolation, objective.h:611-630
+                    const double ax = c.Ax[o + i], bl2 = ov.lb(k, i), bu2 = ov.ub(k, i);
+                    bf.viol[gi] = (ax <= bl2) ? (ax - bl2) : ((ax >= bu2) ? (ax - bu2) : 0.0);
+                }
+            }
+        }
+        for (int g = tid; g < G; g += NT) bf.ranks[p * G + g] = c.rank[g];
+        if constexpr (DS)
+        {
+            // relaxed bounds (cycling handling) belong to the solver-owned copy of the data, objective.h:774-788
+            if (pr.cycling && cycCounter > 0)
+            {
+                for (int r = tid; r < sh.M; r += NT)
+                {
+                    gobj[r + sh.ldo * n]       = c.obj[r + sh.ldo * n];
+                    gobj[r + sh.ldo * (n + 1)] = c.obj[r + sh.ldo * (n + 1)];
+                }
+                for (int i = tid; i < 2 * sh.m0; i += NT) gsb[i] = c.sb[i];
+            }
+        }
+        if (tid == 0)
+        {
+            bf.status[p]  = status;
+            unsigned *cnt = bf.counters + p * 8;
+            cnt[0]        = nFact;
+            cnt[1]        = nAct;
+            cnt[2]        = nDeact;
+            cnt[3]        = nIter;
+            cnt[4]        = cycCounter;
+            cnt[5]        = (unsigned)totalRank;
+            cnt[6]        = nActive;
+            cnt[7]        = (unsigned)((fl.f + 500) / 1000);
+        }
+        gsync<W>();
+    }
+}
+
+} // namespace lexls_dev

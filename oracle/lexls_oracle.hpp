@@ -173,6 +173,7 @@ public:
         dWorkspace.assign(2 * dim + nVar + 1 + 2 * nVar, 0.0);
         column_permutations.assign(nVar, 0);
         ColNorms.assign(nVar, 0.0);
+        invdiag.assign(nVar, 0.0);
         nVarFixed = nVarFixedInit = 0;
         fixed_var_index.clear();
         fixed_var_type.clear();
@@ -372,6 +373,9 @@ public:
                     }
                     hh_scalars[FirstRowIndex + counter] = tau;
                 }
+                // reciprocal of the diagonal entry R(c,c): the Gauss step and solve() multiply by it (Eigen's
+                // matrix triangular solver does the same; its vector solver divides — last-bit difference only)
+                invdiag[ColIndex] = 1.0 / L(RowIndex, ColIndex);
 
                 ColIndex++;
                 RemainingColumns = nVar - ColIndex;
@@ -391,7 +395,7 @@ public:
                 // Left := Left * inv(R)  (R = upper-triangular ObjRank x ObjRank), column by column.
                 for (Index c = 0; c < ObjRank; c++)
                 {
-                    const double inv = 1.0 / L(FirstRowIndex + c, FirstColIndex + c);
+                    const double inv = invdiag[FirstColIndex + c];
                     for (Index r = 0; r < Rows; r++)
                     {
                         double acc = L(FirstRowNext + r, FirstColIndex + c);
@@ -448,7 +452,7 @@ public:
             // upper-triangular solve, column oriented
             for (Index j = ObjRank; j--;)
             {
-                xk[j] = xk[j] / L(fr + j, fc + j);
+                xk[j] = xk[j] * invdiag[fc + j];
                 for (Index i = 0; i < j; i++) xk[i] = fmad(-L(fr + i, fc + j), xk[j], xk[i]);
             }
             AccumulatedRanks += ObjRank;
@@ -664,7 +668,7 @@ private:
     Index nVarFixed = 0, nVarFixedInit = 0, TotalRank = 0;
     double tol_linear_dependence = 1e-12;
     std::vector<ObjectiveInfo> obj_info;
-    std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms;
+    std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms, invdiag;
     std::vector<int> ctr_type, fixed_var_type;
     std::vector<Index> fixed_var_index, column_permutations;
 };

@@ -1,0 +1,159 @@
+"""GPU parity: batched LexLSI (device-resident active-set loop) vs the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import compare_lsi, solve_lsi_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(oracle, w, data, vi, guess=None, x0=None, v0=None, **par):
+    import lexls_b200 as lx
+    B = data[0].shape[0]
+    vib = np.tile(vi, (B, 1)) if (vi is not None and vi.ndim == 1) else vi
+    ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, guess=guess, x0=x0, v0=v0,
+                                 params=oracle.OracleParams(**par) if par else None, threads=0)
+    got = solve_lsi_gpu(w.nVar, w.ObjDim, w.ObjType, data, var_index=vi, guess=guess, x0=x0, v0=v0,
+                        params=lx.Params(**par) if par else None)
+    return got, ref
+
+
+def test_tiny_lsi_cold(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("tiny_lsi")
+    data, vi = problems.generate(w)
+    got, ref = _both(oracle, w, data, vi)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]), "bit-exact parity expected"
+    assert (got["status"] == 0).all()
+
+
+def test_c3_cold_and_warm(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("c3", 1024)
+    data, vi = problems.generate(w)
+    got, ref = _both(oracle, w, data, vi)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"])
+    assert got["counters"][:, 0].max() > 3  # the active-set loop really iterated
+    # warm start: perturbed problem, previous active set and x as the guess
+    d2 = problems.perturb(w, data)
+    got2, ref2 = _both(oracle, w, d2, vi, guess=got["active"], x0=got["x"])
+    compare_lsi(got2, ref2, len(w.ObjDim))
+    assert np.array_equal(got2["x"], ref2["x"])
+    assert got2["counters"][:, 0].mean() < got["counters"][:, 0].mean()
+
+
+def test_test01_dat_golden(oracle, golden_dir):
+    """The reference's own fixture: x must match the file's #Solution (cold and with the file's active-set guess)."""
+    from lexls_b200 import datfile
+
+    class W:
+        pass
+    h = datfile.read_hierarchy(os.path.join(golden_dir, "test_01.dat"))
+    w = W()
+    w.nVar, w.ObjDim, w.ObjType = h.nVar, h.ObjDim, h.ObjType
+    data = [np.ascontiguousarray(M.T)[None] for M in h.objectives]
+    for guess in (None, [g[None] for g in h.active_set_guess]):
+        got, ref = _both(oracle, w, data, h.var_index, guess=guess)
+        compare_lsi(got, ref, len(w.ObjDim))
+        rel = np.linalg.norm(got["x"][0] - h.solution) / np.linalg.norm(h.solution)
+        assert rel < 1e-9, rel
+        assert got["status"][0] == 0
+
+
+@pytest.mark.parametrize("flags", [dict(modify_type_active_enabled=1, modify_type_inactive_enabled=1),
+                                   dict(modify_x_guess_enabled=1, modify_type_inactive_enabled=1),
+                                   dict(set_min_init_ctr_violation=0), dict(use_phase1_v0=1)])
+def test_hot_start_flags(oracle, flags):
+    from lexls_b200 import problems
+    w = problems.workload("tiny_lsi", 96)
+    data, vi = problems.generate(w)
+    rng = np.random.default_rng(5)
+    x0 = 0.3 * rng.standard_normal((96, w.nVar))
+    guess = [rng.integers(0, 3, size=(96, m)).astype(np.uint8) for m in w.ObjDim]
+    got, ref = _both(oracle, w, data, vi, guess=guess, x0=x0, **flags)
+    compare_lsi(got, ref, len(w.ObjDim))
+
+
+def test_x0_and_v0(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("tiny_lsi", 64)
+    data, vi = problems.generate(w)
+    got, ref = _both(oracle, w, data, vi)
+    # restart from the solution with its own residuals: must terminate after one factorization
+    got2, ref2 = _both(oracle, w, data, vi, guess=got["active"], x0=got["x"], v0=got["v"])
+    compare_lsi(got2, ref2, len(w.ObjDim))
+    # partially specified v0 is disregarded (lexlsi.h:758-793)
+    v0p = list(got["v"])
+    v0p[1] = None
+    got3, ref3 = _both(oracle, w, data, vi, x0=got["x"], v0=v0p)
+    compare_lsi(got3, ref3, len(w.ObjDim))
+
+
+def test_cycling_handling_and_iteration_cap(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("tiny_lsi", 128)
+    data, vi = problems.generate(w)
+    got, ref = _both(oracle, w, data, vi, cycling_handling_enabled=1, cycling_max_counter=3, cycling_relax_step=1e-8)
+    compare_lsi(got, ref, len(w.ObjDim))
+    got, ref = _both(oracle, w, data, vi, max_number_of_factorizations=2)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert (got["status"] == 2).any()
+
+
+def test_no_simple_bounds_and_degenerate_rows(oracle):
+    """general levels only; equality rows with zero normal (not activated, lexlsi.h:377); duplicated inequality rows (ties)."""
+    from lexls_b200 import problems
+    rng = np.random.default_rng(9)
+    B, n = 80, 9
+
+    class W:
+        nVar, ObjDim, ObjType = n, [4, 6, 9], [0, 0, 0]
+    data = []
+    for m in W.ObjDim:
+        A = rng.standard_normal((B, m, n))
+        ub = rng.random((B, m))
+        lb = ub - rng.random((B, m))
+        data.append(np.concatenate([A, lb[:, :, None], ub[:, :, None]], axis=2))
+    data[0][:, 0, :n] = 0.0
+    data[0][:, 0, n] = data[0][:, 0, n + 1] = 0.25        # 0*x = 0.25 : equality with zero normal
+    data[1][:, 1, :] = data[1][:, 0, :]                    # duplicated inequality -> exact ratio ties
+    data[2][:, :, n] = data[2][:, :, n + 1]                # last level: equalities
+    data = [np.ascontiguousarray(d.transpose(0, 2, 1)) for d in data]
+    got, ref = _both(oracle, W, data, None)
+    compare_lsi(got, ref, 3)
+
+
+@pytest.mark.parametrize("env", [{"LEXLS_B200_WARPS": "2"}, {"LEXLS_B200_WARPS": "4"}, {"LEXLS_B200_DATA": "l2"},
+                                 {"LEXLS_B200_FORCE_LODGLOBAL": "1"}])
+def test_kernel_variants_match(oracle, env, monkeypatch):
+    from lexls_b200 import problems
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    w = problems.workload("c3", 192)
+    data, vi = problems.generate(w)
+    got, ref = _both(oracle, w, data, vi)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"])
+
+
+def test_invalid_inputs_are_rejected():
+    import lexls_b200 as lx
+    with lx.LexLSIBatch(4, [3, 2], [1, 0], batch=2) as s:
+        bad = np.zeros((2, 2, 3))
+        bad[:, 0, :] = 1.0  # lb > ub
+        with pytest.raises(lx.LexLSError) as e:
+            s.setData(0, bad, var_index=np.array([0, 1, 2], dtype=np.uint32))
+        assert e.value.code == 4
+        ok = np.zeros((2, 2, 3))
+        ok[:, 1, :] = 1.0
+        with pytest.raises(lx.LexLSError):
+            s.setData(0, ok, var_index=np.array([0, 1, 1], dtype=np.uint32))  # duplicate indices, lexlsi.h:485
+        with pytest.raises(lx.LexLSError):
+            s.solve()  # setData missing
+        with pytest.raises(lx.LexLSError) as e:
+            s.setParameters(lx.Params(regularization_type=1))
+        assert e.value.code == 3
