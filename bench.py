@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched LexLSE / LexLSI hot path (BASELINE.json metric: problems solved / s).
+
+  python bench.py --gpus N --steps K --warmup W [--workload c2|c3] [--impl reference]
+
+A "step" is one pass of the hot path over one resident batch of synthetic problems (one solve_batch launch).
+Default workload = BASELINE.json configs[1] (batched LexLSE, 3 levels, n=40, rows 20/20/20, 65,536 problems); `--workload c3`
+is configs[2] (batched LexLSI, humanoid-IK shape, 5 levels, n=38, 16,384 problems, warm-started).  The other configs are
+parity-test cases.  With N > 1 (torchrun, one rank per GPU) every rank solves its own full batch (weak scaling, no data-path
+collective: the batch shards by contiguous problem ranges); timing = max over ranks, device events on the launch stream.
+`--impl reference` times the reference's CPU algorithm (the oracle restatement: the reference needs Eigen, which this image
+does not have) with all host threads on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "problems_solved_per_sec"
+UNIT = "problems/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2_60"])
+    ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's batch)")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=None)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload line items")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def make_workload(name, batch, rank):
+    from lexls_b200 import problems
+    w = problems.workload(name, batch)
+    data, vi = problems.generate(w, start=rank * w.batch, count=w.batch)
+    return w, data, vi
+
+
+def cpu_run(w, data, vi, sample, threads, guess=None, x0=None):
+    """The reference's CPU algorithm (oracle restatement) on the first `sample` problems; returns seconds."""
+    import oracle
+    sl = [d[:sample] for d in data]
+    t0 = time.perf_counter()
+    if w.kind == "lse":
+        oracle.lse_solve_batch(w.nVar, w.ObjDim, sl, threads=threads)
+    else:
+        vib = np.tile(vi, (sample, 1)) if vi is not None else None
+        oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, sl, var_index=vib,
+                               guess=[g[:sample] for g in guess] if guess is not None else None,
+                               x0=x0[:sample] if x0 is not None else None, threads=threads)
+    return time.perf_counter() - t0
+
+
+class Runner:
+    """Owns one resident batch on one GPU and knows how to run a device-resident step and an end-to-end step."""
+
+    def __init__(self, w, data, vi, device, torch):
+        import lexls_b200 as lx
+        self.lx, self.w, self.vi, self.torch = lx, w, vi, torch
+        self.P = len(w.ObjDim)
+        if w.kind == "lse":
+            self.s = lx.LexLSEBatch(w.nVar, w.ObjDim, batch=w.batch, device=device)
+        else:
+            self.s = lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch, device=device)
+        sp = torch.cuda.current_stream().cuda_stream
+        assert sp != 0, "bench must run on a non-default stream (NULL selects the handle's own stream)"
+        self.s.set_stream(sp)
+        self.guess = self.x0 = None
+        self._set(data)
+        if w.kind == "lsi":
+            # warm-start workload: cold solve, then the perturbed problem with the previous active set + x
+            from lexls_b200 import problems
+            self.s.solve()
+            self.cold_ms = self.s.last_solve_ms()
+            self.cold_counters = self.s.get_counters()
+            self.guess = [self.s.getActiveCtr(k) for k in range(self.P)]
+            self.x0 = self.s.get_x()
+            data = problems.perturb(w, data)
+            self._set(data)
+            for k, g in enumerate(self.guess):
+                self.s.set_active_guess(k, g)
+            self.s.set_x0(self.x0)
+        self.data = data
+        # pinned host copies for the end-to-end leg
+        self.pinned = []
+        for d in data:
+            t = torch.empty(d.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = d
+            self.pinned.append(t)
+        self.x_pinned = torch.empty((w.batch, w.nVar), dtype=torch.float64, pin_memory=True)
+        self.h2d_bytes = int(sum(d.nbytes for d in data))
+        self.d2h_bytes = int(self.x_pinned.numel() * 8)
+        if w.kind == "lsi":
+            self.guess_pinned = []
+            for g in self.guess:
+                t = torch.empty(g.shape, dtype=torch.uint8, pin_memory=True)
+                t.numpy()[...] = g
+                self.guess_pinned.append(t)
+            self.x0_pinned = torch.empty(self.x0.shape, dtype=torch.float64, pin_memory=True)
+            self.x0_pinned.numpy()[...] = self.x0
+            self.h2d_bytes += int(sum(g.nbytes for g in self.guess) + self.x0.nbytes)
+
+    def _set(self, data):
+        for k, d in enumerate(data):
+            if self.w.kind == "lsi" and self.w.ObjType[k] == 1:
+                self.s.setData(k, d, var_index=self.vi)
+            else:
+                self.s.setData(k, d)
+
+    def step(self):
+        self.s.solve(sync=False)
+
+    def e2e_step(self):
+        """What a caller does per batch: host data in (pinned), solve, x out (pinned)."""
+        for k, t in enumerate(self.pinned):
+            if self.w.kind == "lsi" and self.w.ObjType[k] == 1:
+                self.s.setData(k, t.numpy(), var_index=self.vi)
+            else:
+                self.s.setData(k, t.numpy())
+        if self.w.kind == "lsi":
+            for k, g in enumerate(self.guess_pinned):
+                self.s.set_active_guess(k, g.numpy())
+            self.s.set_x0(self.x0_pinned.numpy())
+        self.s.solve(sync=False)
+        self.s.get_x(out=self.x_pinned.numpy())
+
+
+def timed(torch, dist, world, fn, steps):
+    """barrier + sync, `steps` calls of fn, sync + barrier; device time by CUDA events on the current stream; max over ranks."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def flops_of(counters):
+    return float(counters[:, 7].astype(np.float64).sum()) * 1e3
+
+
+def load_traffic(kernel_name, workload):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("%s:%s" % (workload, kernel_name))
+    except Exception:
+        return None
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — lexls_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import lexls_b200 as lx
+
+    # a dedicated (non-default) stream: the library launches on it and the torch events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    w, data, vi = make_workload(args.workload, args.batch, rank)
+    r = Runner(w, data, vi, local, torch)
+    info = r.s.kernel_info()
+
+    for _ in range(max(args.warmup, 3)):
+        r.step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(torch, dist, world, r.step, args.steps)
+    clocks = sampler.stop()
+    counters = r.s.get_counters()
+    status = r.s.get_status()
+    ms_per_step = ms / args.steps
+    value = world * w.batch * args.steps / (ms * 1e-3)
+
+    # end-to-end through the public API with host buffers
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else max(3, min(args.steps, 10))
+    for _ in range(2):
+        r.e2e_step()
+    ms_e2e = timed(torch, dist, world, r.e2e_step, e2e_steps)
+    e2e_value = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
+
+    out = None
+    if rank == 0:
+        peaks = load_peaks()
+        fp = lx.measure_fp64_peak(local)
+        fl = flops_of(counters)
+        achieved = fl / (ms_per_step * 1e-3) / 1e12
+        in_bytes = float(r.h2d_bytes if w.kind == "lse" else sum(d.nbytes for d in r.data))
+        out_bytes = float(w.batch * (w.nVar * 8 + w.nCtr * 8 + 48))
+        hbm_gbs = (in_bytes + out_bytes) / (ms_per_step * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w.name, "kind": w.kind, "nVar": w.nVar, "levels": w.ObjDim, "batch_per_gpu": w.batch,
+                       "global_batch": w.batch * world, "seed": w.seed,
+                       "warm_start": w.kind == "lsi", "parallelism": "batch sharded by contiguous problem ranges, no collective",
+                       "l2": "inputs larger than L2: %.0f MB of problem records are re-read from HBM every step" % (in_bytes / 1e6),
+                       "kernel": info},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes, "d2h_bytes_per_step": r.d2h_bytes,
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": args.steps * info["launches_per_solve"],
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp["dfma_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / fp["dfma_tflops"], "traffic": load_traffic(info["name"], w.name),
+                         "peak_source": "measured here: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 entry); "
+                                        "DMMA mma.sync f64 chain = %.1f TFLOP/s" % fp["dmma_tflops"],
+                         "algorithmic_flops_per_launch": fl, "kernel": info["name"],
+                         "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": (hbm_gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                 "algorithmic_bytes_per_launch": in_bytes + out_bytes}},
+            "solve_stats": {"status_solved_frac": float((status == 0).mean()),
+                            "mean_factorizations": float(counters[:, 0].mean()), "mean_rank": float(counters[:, 5].mean())},
+        }
+        if world == 1:
+            threads = host_threads()
+            sample = args.cpu_sample or (32768 if w.kind == "lse" else 8192)
+            sample = min(sample, w.batch)
+            sec = cpu_run(w, r.data, vi, sample, threads, r.guess, r.x0)
+            out["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "first %d problems of the same workload, oracle restatement of the reference "
+                                             "(reference needs Eigen: not buildable here), %d host threads, %.2f s wall"
+                                             % (sample, threads, sec)}
+            if w.kind == "lsi":
+                out["cold_start"] = {"value": w.batch / (r.cold_ms * 1e-3), "unit": UNIT, "ms": r.cold_ms,
+                                     "mean_factorizations": float(r.cold_counters[:, 0].mean())}
+    r.s.close()
+
+    # secondary workload (the north-star LexLSI shape) as an extra object on the same line, 1 GPU only
+    if world == 1 and rank == 0 and not args.no_extra and args.workload == "c2":
+        try:
+            w3, d3, v3 = make_workload("c3", None, 0)
+            r3 = Runner(w3, d3, v3, local, torch)
+            for _ in range(3):
+                r3.step()
+            k3 = max(10, args.steps // 4)
+            ms3 = timed(torch, dist, 1, r3.step, k3)
+            c3 = r3.s.get_counters()
+            fp = out["roofline"]["peak"]
+            ach3 = flops_of(c3) / (ms3 / k3 * 1e-3) / 1e12
+            for _ in range(2):
+                r3.e2e_step()
+            e3 = timed(torch, dist, 1, r3.e2e_step, 5)
+            out["also"] = {"c3_lexlsi_warm": {
+                "workload": w3.name, "value": w3.batch * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
+                "mean_factorizations": float(c3[:, 0].mean()), "kernel": r3.s.kernel_info()["name"],
+                "roofline_frac": ach3 / fp, "achieved_tflops": ach3,
+                "e2e": {"value": w3.batch * 5 / (e3 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r3.h2d_bytes,
+                        "d2h_bytes_per_step": r3.d2h_bytes},
+                "cold_start": {"value": w3.batch / (r3.cold_ms * 1e-3), "ms": r3.cold_ms,
+                               "mean_factorizations": float(r3.cold_counters[:, 0].mean())}}}
+            r3.s.close()
+        except Exception as e:  # the headline line must still print
+            out["also"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    w, data, vi = make_workload(args.workload, None, 0)
+    threads = host_threads()
+    sample = args.cpu_sample or (4096 if w.kind == "lse" else 1024)
+    sample = min(sample, w.batch)
+    guess = x0 = None
+    if w.kind == "lsi":
+        # same warm-start workload as the GPU arm: cold solve of the sample (untimed), then the perturbed problems
+        import oracle
+        from lexls_b200 import problems
+        sl = [d[:sample] for d in data]
+        vib = np.tile(vi, (sample, 1)) if vi is not None else None
+        cold = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, sl, var_index=vib, threads=threads)
+        guess, x0 = cold["active"], cold["x"]
+        data = problems.perturb(w, data)
+    steps, warm = max(args.steps, 1), max(args.warmup, 1)
+    # bound the whole run to a few minutes
+    t_probe = cpu_run(w, data, vi, sample, threads, guess, x0)
+    budget = 120.0
+    if t_probe * (steps + warm) > budget:
+        steps = max(1, int(budget / t_probe) - warm)
+    for _ in range(warm - 1):
+        cpu_run(w, data, vi, sample, threads, guess, x0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_run(w, data, vi, sample, threads, guess, x0)
+    sec = time.perf_counter() - t0
+    value = sample * steps / sec
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": w.name, "kind": w.kind, "nVar": w.nVar, "levels": w.ObjDim, "batch_per_gpu": w.batch,
+                   "warm_start": w.kind == "lsi", "step": "bounded sample of %d problems of the workload per step" % sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d problems per step x %d steps; CPU oracle = restatement of the reference algorithm "
+                                   "(the reference's only dependency, Eigen, is absent, so its own build is impossible here)"
+                                   % (sample, steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

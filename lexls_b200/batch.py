@@ -87,8 +87,11 @@ class _Batch:
         check(lib().lexls_b200_synchronize(self._h))
 
     # ---- results ------------------------------------------------------------------------------------------------
-    def get_x(self):
-        x = np.empty((self.batch, self.nVar))
+    def get_x(self, out=None):
+        """x of every problem, [B, nVar]; `out` may be a caller buffer (e.g. pinned host memory)."""
+        x = np.empty((self.batch, self.nVar)) if out is None else out
+        if x.shape != (self.batch, self.nVar) or x.dtype != np.float64 or not x.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 [B, nVar] array")
         check(lib().lexls_b200_get_x(self._h, _dp(x)))
         return x
 

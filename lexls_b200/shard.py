@@ -1,0 +1,94 @@
+"""Multi-GPU sharding of a batch: problems are independent, so a batch is split into contiguous ranges,
+one per GPU, with no data-path collective; the only exchange is the final gather of results.
+
+Two ways to use several GPUs:
+  * inside ONE process: :class:`ShardedBatch` owns one handle (and stream) per device, launches all shards asynchronously
+    and concatenates the results;
+  * one process per GPU (torchrun): every rank solves ``shard_range(batch, world, rank)`` with a plain
+    LexLSEBatch / LexLSIBatch and calls :func:`gather_to_rank0` on the result arrays.
+"""
+import numpy as np
+
+
+def shard_range(batch, world, rank):
+    """Contiguous range [lo, hi) of rank `rank`; the first (batch % world) ranks get one extra problem."""
+    base, extra = divmod(int(batch), int(world))
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def shard_ranges(batch, world):
+    return [shard_range(batch, world, r) for r in range(world)]
+
+
+def gather_to_rank0(local, batch, group=None):
+    """Final gather over torch.distributed (any backend): rank 0 returns the [batch, ...] array, other ranks None."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    local = np.ascontiguousarray(local)
+    orig = local.dtype
+    if orig == np.uint32:      # collectives lack unsigned 32-bit: ship the bits as int32
+        local = local.view(np.int32)
+    t = torch.from_numpy(local)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    tail = tuple(t.shape[1:])
+    sizes = [hi - lo for lo, hi in shard_ranges(batch, world)]
+    smax = max(sizes)
+    if t.shape[0] < smax:  # gather needs equal shapes: pad ragged shards, trim after
+        pad = torch.zeros((smax - t.shape[0],) + tail, dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], dim=0)
+    bufs = [torch.empty((smax,) + tail, dtype=t.dtype, device=t.device) for _ in sizes] if rank == 0 else None
+    dist.gather(t, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0).cpu().numpy()
+    return out.view(np.uint32) if orig == np.uint32 else out
+
+
+class ShardedBatch:
+    """One logical batch over several GPUs of one box, inside one process."""
+
+    def __init__(self, cls, nVar, ObjDim, ObjType=None, batch=1, devices=(0,)):
+        self.devices = list(devices)
+        self.ranges = shard_ranges(batch, len(self.devices))
+        self.batch = int(batch)
+        self.parts = []
+        for dev, (lo, hi) in zip(self.devices, self.ranges):
+            if hi > lo:
+                kw = dict(batch=hi - lo, device=dev)
+                self.parts.append((lo, hi, cls(nVar, ObjDim, ObjType, **kw) if ObjType is not None else cls(nVar, ObjDim, **kw)))
+
+    def close(self):
+        for _, _, s in self.parts:
+            s.close()
+        self.parts = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def setParameters(self, p):
+        for _, _, s in self.parts:
+            s.setParameters(p)
+
+    def setData(self, level, data, **kw):
+        for lo, hi, s in self.parts:
+            s.setData(level, data[lo:hi], **kw)
+
+    def call_sliced(self, name, level, arr):
+        for lo, hi, s in self.parts:
+            getattr(s, name)(level, arr[lo:hi]) if level is not None else getattr(s, name)(arr[lo:hi])
+
+    def solve(self):
+        for _, _, s in self.parts:
+            s.solve(sync=False)      # all devices run concurrently
+        for _, _, s in self.parts:
+            s.synchronize()
+
+    def gather(self, name, *args):
+        return np.concatenate([getattr(s, name)(*args) for _, _, s in self.parts], axis=0)
