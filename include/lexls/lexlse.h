@@ -1,0 +1,139 @@
+// lexls/lexlse.h — drop-in LexLS::internal::LexLSE (reference include/lexls/lexlse.h; member signatures :43-103, :117, :1015,
+// :1381-1631) implemented as a batch-of-1 facade over the C-ABI in include/lexls_b200.h.  All arithmetic runs in the CUDA
+// library; there is no CPU path.  factorize() launches the device l-QR + back-substitution; solve() only fetches.
+#pragma once
+
+#include <lexls/typedefs.h>
+#include <lexls_b200.h>
+
+namespace LexLS
+{
+namespace internal
+{
+inline void lexls_b200_check(int rc)
+{
+    if (rc != 0) throw Exception(lexls_b200_last_error());
+}
+
+class LexLSE
+{
+public:
+    LexLSE() : h_(0), nVar(0), nObj(0), nCtr(0), nVarFixed(0), nVarFixedInit(0), TotalRank(0) {}
+    LexLSE(Index nVar_, Index nObj_, Index *ObjDim_) : h_(0), nVarFixed(0), nVarFixedInit(0), TotalRank(0)
+    {
+        resize(nVar_, nObj_, ObjDim_);
+        setObjDim(ObjDim_);
+    }
+    ~LexLSE() { release(); }
+    LexLSE(const LexLSE &) = delete;
+    LexLSE &operator=(const LexLSE &) = delete;
+
+    void resize(Index nVar_, Index nObj_, Index *maxObjDim) // lexlse.h:67
+    {
+        nVar = nVar_;
+        nObj = nObj_;
+        maxDim.assign(maxObjDim, maxObjDim + nObj);
+        dim = maxDim;
+        x.resize(nVar);
+    }
+    void setObjDim(Index *ObjDim_) // lexlse.h:1426 — (re)creates the device batch for these dimensions
+    {
+        dim.assign(ObjDim_, ObjDim_ + nObj);
+        nCtr = 0;
+        first_row.assign(nObj, 0);
+        for (Index k = 0; k < nObj; k++)
+        {
+            first_row[k] = nCtr;
+            nCtr += dim[k];
+        }
+        release();
+        lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSE, nVar, nObj, dim.data(), 0, 1, 0, &h_));
+        applyParameters();
+        nVarFixedInit = 0;
+        TotalRank     = 0;
+        ranks.assign(nObj, 0);
+        v.resize(nCtr > 0 ? nCtr : 1);
+    }
+    void setParameters(const ParametersLexLSE &p) // lexlse.h:1467
+    {
+        parameters = p;
+        if (h_) applyParameters();
+    }
+    void setData(Index ObjIndex, const dMatrixConstRef &data) // lexlse.h:1522
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        if (static_cast<Index>(data.rows()) != dim[ObjIndex] || static_cast<Index>(data.cols()) != nVar + 1)
+            throw Exception("Incorrect number of equations");
+        lexls_b200_check(lexls_b200_set_data(h_, ObjIndex, detail::data_of(data), detail::ld_of(data),
+                                             static_cast<uint64_t>(detail::ld_of(data)) * (nVar + 1)));
+    }
+    void setFixedVariablesCount(Index nVarFixed_) // lexlse.h:1449
+    {
+        if (nVarFixed_ > nVar) throw Exception("Cannot fix more than nVar variables");
+        nVarFixed = nVarFixed_;
+        fixed_index.assign(nVarFixed, 0);
+        fixed_value.assign(nVarFixed, 0.0);
+        fixed_type.assign(nVarFixed, static_cast<uint8_t>(CTR_ACTIVE_UB));
+        nVarFixedInit = 0;
+    }
+    void fixVariable(Index VarIndex, RealScalar VarValue, ConstraintActivationType type = CTR_ACTIVE_UB) // lexlse.h:1381
+    {
+        if (nVarFixedInit >= nVarFixed) throw Exception("more fixVariable calls than setFixedVariablesCount announced");
+        fixed_index[nVarFixedInit] = VarIndex;
+        fixed_value[nVarFixedInit] = VarValue;
+        fixed_type[nVarFixedInit]  = static_cast<uint8_t>(type);
+        nVarFixedInit++;
+    }
+    void fixVariables(Index nVarFixed_, Index *VarIndex, RealScalar *VarValue, ConstraintActivationType *type) // lexlse.h:1398
+    {
+        setFixedVariablesCount(nVarFixed_);
+        for (Index i = 0; i < nVarFixed_; i++) fixVariable(VarIndex[i], VarValue[i], type[i]);
+    }
+    void factorize() // lexlse.h:117 (+ :1015: the device kernel also back-substitutes)
+    {
+        lexls_b200_check(lexls_b200_set_fixed_variables(h_, nVarFixed, fixed_index.data(), fixed_value.data(), fixed_type.data()));
+        lexls_b200_check(lexls_b200_solve_batch_sync(h_));
+        lexls_b200_check(lexls_b200_get_ranks(h_, ranks.data()));
+        uint32_t cnt[LEXLS_B200_NCOUNTERS];
+        lexls_b200_check(lexls_b200_get_counters(h_, cnt));
+        TotalRank = cnt[LEXLS_B200_CNT_TOTAL_RANK];
+    }
+    void solve() { lexls_b200_check(lexls_b200_get_x(h_, x.data())); } // lexlse.h:1015
+    const dVectorType &get_x() const { return x; }                      // lexlse.h:1587
+    dVectorType &get_v()                                                // lexlse.h:1560 (use the first nCtr entries)
+    {
+        for (Index k = 0; k < nObj; k++)
+            if (dim[k]) lexls_b200_check(lexls_b200_get_v(h_, k, v.data() + first_row[k]));
+        return v;
+    }
+    Index getDim(Index k) const { return dim[k]; }
+    Index getRank(Index k) const { return ranks[k]; }
+    Index getTotalRank() const { return TotalRank; }
+    Index getFixedVariablesCount() const { return nVarFixed; }
+    Index get_nObj() const { return nObj; }
+    Index get_nVar() const { return nVar; }
+
+private:
+    void release()
+    {
+        if (h_) lexls_b200_destroy(h_);
+        h_ = 0;
+    }
+    void applyParameters()
+    {
+        if (parameters.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
+        lexls_b200_params_t p;
+        lexls_b200_default_params(&p);
+        p.tol_linear_dependence = parameters.tol_linear_dependence;
+        lexls_b200_check(lexls_b200_set_params(h_, &p));
+    }
+    lexls_b200_batch_t *h_;
+    Index nVar, nObj, nCtr, nVarFixed, nVarFixedInit, TotalRank;
+    std::vector<Index> maxDim, dim, first_row, ranks, fixed_index;
+    std::vector<RealScalar> fixed_value;
+    std::vector<uint8_t> fixed_type;
+    ParametersLexLSE parameters;
+    dVectorType x, v;
+};
+} // namespace internal
+} // namespace LexLS

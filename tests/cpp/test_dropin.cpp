@@ -1,0 +1,67 @@
+// Compiles against the drop-in headers exactly as a user of the reference would (#include <lexls/lexlsi.h>) and, on a GPU,
+// checks two analytic known answers: the Escande hierarchy (x_k = 1/k; interfaces/matlab-octave/tests/lexlsi/lambda_test.m)
+// and LexLSE {A1 x = b1; I x = 0} == minimum-norm solution (examples/example_lexlse.m:17-29) on a case with a closed form.
+#include <cmath>
+#include <cstdio>
+#include <lexls/lexls.h>
+
+using namespace LexLS;
+
+int main()
+{
+    try
+    {
+        const Index n = 6;
+        std::vector<Index> dims(n + 1, 1);
+        std::vector<ObjectiveType> types(n + 1, GENERAL_OBJECTIVE);
+        internal::LexLSI lsi(n, n + 1, dims.data(), types.data());
+        ParametersLexLSI par;
+        par.max_number_of_factorizations = 50;
+        lsi.setParameters(par);
+        for (Index k = 0; k <= n; k++)
+        {
+            dMatrixType row(1, n + 2);
+            for (Index j = 0; j < n; j++) row(0, j) = (k == n) ? 1.0 : (j == k ? double(k + 1) : 0.0);
+            row(0, n) = row(0, n + 1) = 1.0;
+            lsi.setData(k, row);
+        }
+        TerminationStatus st = lsi.solve();
+        if (st != PROBLEM_SOLVED) { std::printf("FAIL status %d\n", int(st)); return 1; }
+        for (Index k = 0; k < n; k++)
+            if (std::fabs(lsi.get_x()(k) - 1.0 / (k + 1)) > 1e-12) { std::printf("FAIL x[%u]\n", k); return 1; }
+        if (lsi.getFactorizationsCount() != 1 || lsi.getTotalRank() != n) { std::printf("FAIL counters\n"); return 1; }
+        std::vector<ConstraintActivationType> t;
+        lsi.getActiveCtr(n, t);
+        if (t[0] != CTR_ACTIVE_EQ) { std::printf("FAIL active type\n"); return 1; }
+
+        // LexLSE: x1 + x2 + x3 = 3 ; I x = 0  ->  minimum-norm solution (1,1,1); with x3 fixed to 2: (0.5, 0.5, 2)
+        Index d2[2] = {1, 3};
+        internal::LexLSE lse(3, 2, d2);
+        dMatrixType a(1, 4), e(3, 4);
+        a(0, 0) = a(0, 1) = a(0, 2) = 1.0; a(0, 3) = 3.0;
+        e.setZero();
+        e(0, 0) = e(1, 1) = e(2, 2) = 1.0;
+        lse.setData(0, a);
+        lse.setData(1, e);
+        lse.factorize();
+        lse.solve();
+        for (Index k = 0; k < 3; k++)
+            if (std::fabs(lse.get_x()(k) - 1.0) > 1e-12) { std::printf("FAIL lse x\n"); return 1; }
+        if (lse.getRank(0) != 1 || lse.getRank(1) != 2 || lse.getTotalRank() != 3) { std::printf("FAIL ranks\n"); return 1; }
+        lse.setObjDim(d2);
+        lse.setFixedVariablesCount(1);
+        lse.fixVariable(2, 2.0);
+        lse.setData(0, a);
+        lse.setData(1, e);
+        lse.factorize();
+        lse.solve();
+        if (std::fabs(lse.get_x()(0) - 0.5) > 1e-12 || std::fabs(lse.get_x()(2) - 2.0) > 1e-12) { std::printf("FAIL fixed\n"); return 1; }
+        std::printf("OK\n");
+        return 0;
+    }
+    catch (std::exception &e)
+    {
+        std::printf("EXCEPTION: %s\n", e.what());
+        return 2;
+    }
+}
