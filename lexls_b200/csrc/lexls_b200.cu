@@ -192,6 +192,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
     m.dv = take(vecs * 8, 8);
     m.Ax = take(vecs * 8, 8);
     m.Adx = take(vecs * 8, 8);
+    m.vv = take(((unsigned)sh.ld + 2) * 8, 16);
     m.active = take((Mall + 1) * 2, 4);
     m.inactive = take((Mall + 1) * 2, 4);
     m.fidx = take((std::max(m0, (unsigned)sh.nfix) + 1) * 2, 4);
@@ -425,7 +426,8 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     s.Mall = s.m0 + s.M;
     if (s.Mall > 60000) { delete h; return fail(LEXLS_B200_ECAPACITY, "too many constraints"); }
     if (s.off && s.G == 0) { delete h; return fail(LEXLS_B200_EINVAL, "a problem of one simple-bounds level is not supported"); }
-    s.ld   = std::max(s.M, 1) | 1; // odd
+    s.ld   = (std::max(s.M, 2) + 1) & ~1; // even, and ld/2 odd: 128-bit row-pair accesses are conflict-free both ways
+    if (((s.ld >> 1) & 1) == 0) s.ld += 2;
     s.nfix = 0;
     if (kind == LEXLS_B200_LSE)
     {

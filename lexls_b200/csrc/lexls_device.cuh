@@ -55,7 +55,7 @@ struct Shape
     int m0;    // rows of the simple-bounds level (0 if none)
     int M;     // rows of all general levels
     int Mall;  // m0 + M
-    int ld;    // leading dimension of LOD in shared memory (odd, >= M)
+    int ld;    // leading dimension of LOD in shared memory (even with ld/2 odd, >= M): see lse_factorize
     int ldo;   // leading dimension of the stacked objective record [M x (n+2)] (LSI) / of the LSE record (= ld)
     int nfix;  // LSE: number of fixed variables
     int dim[LX_MAX_LEVELS];       // user ObjDim
@@ -76,7 +76,7 @@ struct Params
 // byte offsets into the dynamic shared memory of one group
 struct SmemMap
 {
-    unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx;
+    unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx, vv;
     unsigned active, inactive, atype, alltype, ctype, fidx, ftype, colperm, varofcol, sbidx;
     unsigned ldim, frow, fcol, rank, nact, ninact, scal, mbar, total;
 };
@@ -181,7 +181,7 @@ __device__ __forceinline__ ArgMin bfly_argmax(ArgMin a)
 // ---------------------------------------------------------------------------------------------------------------
 struct Ctx
 {
-    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx;
+    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx, *vv;
     unsigned short *active, *inactive, *fidx, *colperm, *varofcol, *sbidx;
     unsigned char *atype, *alltype, *ctype, *ftype;
     int *ldim, *frow, *fcol, *rank, *nact, *ninact, *scal;
@@ -206,6 +206,7 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char *base, const SmemMap &m)
     c.dv       = (double *)(base + m.dv);
     c.Ax       = (double *)(base + m.Ax);
     c.Adx      = (double *)(base + m.Adx);
+    c.vv       = (double *)(base + m.vv);
     c.active   = (unsigned short *)(base + m.active);
     c.inactive = (unsigned short *)(base + m.inactive);
     c.atype    = (unsigned char *)(base + m.atype);
@@ -292,10 +293,30 @@ struct FlopCount
     unsigned long long f;
 };
 
+// aligned 2-double accesses (rows 2t, 2t+1 of one column): LDS.128 / STS.128 in shared memory
+__device__ __forceinline__ double2 ld2(const double *p)
+{
+    return *reinterpret_cast<const double2 *>(p);
+}
+__device__ __forceinline__ void st2(double *p, double2 v)
+{
+    *reinterpret_cast<double2 *>(p) = v;
+}
+
+// order-preserving map double -> u64 (so that integer max == floating max)
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+    const long long b = __double_as_longlong(v);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // l-QR factorization, lexlse.h:117-506 (REGULARIZATION_NONE)
 //   G levels with c.ldim[g] rows starting at c.frow[g]; nCtr = total rows; nFixed fixed variables whose values are in
 //   c.lx[0..nFixed) and indices in c.fidx.  Writes c.rank/c.fcol/c.hh/c.invd/c.colperm/c.varofcol; returns TotalRank.
+//   LOD is column-major with an EVEN leading dimension ld (ld/2 odd): every column starts 16-byte aligned, so rows are
+//   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
+//   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
 template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const int ld, const int G, const int nCtr,
                                               const int nFixed, const double tol, FlopCount &fl)
@@ -303,6 +324,7 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
     double *const LOD = c.LOD;
+    const int hp      = ld >> 1; // row pairs per column
 
     for (int k = tid; k < n; k += NT) c.varofcol[k] = (unsigned short)k;
     for (int g = tid; g < G; g += NT)
@@ -319,11 +341,11 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
         {
             const int coeff = c.fidx[k];
             if (k != coeff)
-                for (int r = tid; r < nCtr; r += NT)
+                for (int t = tid; t < hp; t += NT)
                 {
-                    double a          = LOD[r + ld * k];
-                    LOD[r + ld * k]     = LOD[r + ld * coeff];
-                    LOD[r + ld * coeff] = a;
+                    const double2 a = ld2(LOD + ld * k + 2 * t);
+                    st2(LOD + ld * k + 2 * t, ld2(LOD + ld * coeff + 2 * t));
+                    st2(LOD + ld * coeff + 2 * t, a);
                 }
             gsync<W>(); // everyone has read fidx[k] before it may be patched
             if (tid == 0)
@@ -331,9 +353,9 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
                 c.colperm[k] = (unsigned short)coeff;
                 if (k != coeff)
                 {
-                    unsigned short t   = c.varofcol[k];
-                    c.varofcol[k]      = c.varofcol[coeff];
-                    c.varofcol[coeff]  = t;
+                    unsigned short t  = c.varofcol[k];
+                    c.varofcol[k]     = c.varofcol[coeff];
+                    c.varofcol[coeff] = t;
                 }
                 for (int i = k + 1; i < nFixed; i++)
                     if (c.fidx[i] == k)
@@ -363,69 +385,58 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
         const int fr = c.frow[g], dim = c.ldim[g], fc = ColIndex;
         if (tid == 0) c.fcol[g] = fc;
 
-        // initial squared column norms over this level's rows, lexlse.h:193-196   (S)
+        // initial squared column norms over this level's rows, lexlse.h:193-196   (S2)
         for (int k = ColIndex + tid; k < n; k += NT)
         {
-            const double *col = LOD + ld * k + fr;
-            double acc        = 0.0;
-            for (int i = 0; i < dim; i++) acc = fma(col[i], col[i], acc);
-            c.colnorm[k] = acc;
+            const double *col = LOD + ld * k;
+            double acc[2]     = {0.0, 0.0};
+            for (int r = fr; r < fr + dim; r++) acc[r & 1] = fma(col[r], col[r], acc[r & 1]);
+            c.colnorm[k] = acc[0] + acc[1];
         }
-        fl.f += 2ull * dim * (n - ColIndex);
         gsync<W>();
 
         for (int counter = 0; counter < dim; counter++)
         {
             const int row = fr + counter, rem = dim - counter;
 
-            // pivot = first maximum of the down-dated norms, lexlse.h:205-206 (every warp computes it redundantly)
-            ArgMin am;
-            am.v   = -DBL_MAX;
-            am.pos = n;
+            // pivot = first maximum of the down-dated norms, lexlse.h:205-206 (every warp computes it redundantly):
+            // integer max over order-preserving keys (REDUX), then the smallest column index holding the maximum
+            int p;
             {
-                int k = ColIndex + lane;
-                if (k < n)
+                unsigned long long key = 0;
+                int col                = 0x7fffffff;
+                for (int k = ColIndex + lane; k < n; k += 32)
                 {
-                    am.v   = c.colnorm[k];
-                    am.pos = k;
-                    for (k += 32; k < n; k += 32)
+                    const unsigned long long kk = dkey(c.colnorm[k]);
+                    if (col == 0x7fffffff || kk > key)
                     {
-                        double v = c.colnorm[k];
-                        if (v > am.v)
-                        {
-                            am.v   = v;
-                            am.pos = k;
-                        }
+                        key = kk;
+                        col = k;
                     }
                 }
+                const unsigned hi = (unsigned)(key >> 32);
+                const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+                const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+                const bool mine   = (hi == mh) && ((unsigned)key == ml) && (col != 0x7fffffff);
+                p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)col : 0x7fffffffu);
+                if (p >= n) p = ColIndex;
             }
-            am          = bfly_argmax(am);
-            const int p = am.pos < n ? am.pos : ColIndex;
 
-            // exact norm of the chosen column and of its tail (lexlse.h:210, makeHouseholderInPlace)   (T)
+            // ||tail||^2 by (T); ||col||^2 = c0^2 + ||tail||^2 (lexlse.h:210 and makeHouseholderInPlace)
             const double *colp = LOD + ld * p + row;
-            double acc1 = 0.0, acc2 = 0.0;
-            for (int i = lane; i < rem; i += 32)
-            {
-                double a = colp[i];
-                acc1     = fma(a, a, acc1);
-            }
+            double acc2        = 0.0;
             for (int i = lane; i < rem - 1; i += 32)
             {
-                double a = colp[i + 1];
-                acc2     = fma(a, a, acc2);
+                const double a = colp[i + 1];
+                acc2           = fma(a, a, acc2);
             }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1)
-            {
-                acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-                acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-            }
-            const double maxval = acc1;
+            acc2                = bfly_sum(acc2);
+            const double c0     = colp[0];
+            const double maxval = fma(c0, c0, acc2);
             if (maxval < tol) break; // rank found, lexlse.h:214-217
-            const double c0 = colp[0];
 
-            double tau = 0.0, beta = c0, den = 1.0;
+            double tau = 0.0, beta = c0, rden = 0.0;
             bool zero_tail = false;
             if (rem > 1)
             {
@@ -433,71 +444,105 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
                     zero_tail = true;
                 else
                 {
-                    beta = sqrt(fma(c0, c0, acc2));
+                    beta = sqrt(maxval);
                     if (c0 >= 0.0) beta = -beta;
-                    den = c0 - beta;
-                    tau = (beta - c0) / beta;
+                    rden = 1.0 / (c0 - beta);
                 }
             }
-            const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c), used by Gauss and solve
+            const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c): Gauss step, solve, and tau
+            if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
 
             if constexpr (W > 1) gsync<W>(); // all warps finished reading colnorm / column p
 
             if (tid == 0)
             {
-                double t          = c.colnorm[ColIndex];
+                const double t      = c.colnorm[ColIndex];
                 c.colnorm[ColIndex] = maxval;
                 c.colperm[ColIndex] = (unsigned short)p;
                 c.invd[ColIndex]    = inv;
                 if (p != ColIndex)
                 {
-                    c.colnorm[p]          = t;
-                    unsigned short s      = c.varofcol[ColIndex];
-                    c.varofcol[ColIndex]  = c.varofcol[p];
-                    c.varofcol[p]         = s;
+                    c.colnorm[p]         = t;
+                    const unsigned short s = c.varofcol[ColIndex];
+                    c.varofcol[ColIndex] = c.varofcol[p];
+                    c.varofcol[p]        = s;
                 }
                 if (rem > 1) c.hh[row] = tau;
             }
-            // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242)
-            for (int r = tid; r < nCtr; r += NT)
+            // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242); the reflector
+            // v = [1; essential], zero outside its rows, is also written to c.vv for the broadcast reads of the apply
+            const int pb = row >> 1, pe = (row + rem + 1) >> 1; // pairs touched by the reflector
+            for (int t = tid; t < hp; t += NT)
             {
-                double a = LOD[r + ld * p];
-                if (p != ColIndex) LOD[r + ld * p] = LOD[r + ld * ColIndex];
-                if (rem > 1)
+                double2 a = ld2(LOD + ld * p + 2 * t);
+                if (p != ColIndex) st2(LOD + ld * p + 2 * t, ld2(LOD + ld * ColIndex + 2 * t));
+                if (rem > 1 && t >= pb && t < pe)
                 {
-                    if (r == row)
-                        a = beta;
-                    else if (r > row && r < row + rem)
-                        a = zero_tail ? 0.0 : a / den;
+                    const int r0 = 2 * t, r1 = r0 + 1;
+                    double2 v;
+                    if (r0 == row)
+                    {
+                        a.x = beta;
+                        v.x = 1.0;
+                    }
+                    else if (r0 > row && r0 < row + rem)
+                    {
+                        a.x = zero_tail ? 0.0 : a.x * rden;
+                        v.x = a.x;
+                    }
+                    else
+                        v.x = 0.0;
+                    if (r1 == row)
+                    {
+                        a.y = beta;
+                        v.y = 1.0;
+                    }
+                    else if (r1 > row && r1 < row + rem)
+                    {
+                        a.y = zero_tail ? 0.0 : a.y * rden;
+                        v.y = a.y;
+                    }
+                    else
+                        v.y = 0.0;
+                    st2(c.vv + 2 * t, v);
                 }
-                LOD[r + ld * ColIndex] = a;
+                st2(LOD + ld * ColIndex + 2 * t, a);
             }
             gsync<W>();
 
             // apply H to columns ColIndex+1 .. n (RHS included), lexlse.h:243-246, and down-date the norms, :262-266
             {
-                const double *ess = LOD + ld * ColIndex + row;
-                const bool apply  = (rem > 1) && (tau != 0.0);
+                const bool apply  = tau != 0.0;
+                const double *vp  = c.vv + 2 * pb;
+                const int np      = pe - pb;
                 for (int j = ColIndex + 1 + tid; j <= n; j += NT)
                 {
-                    double *colj = LOD + ld * j + row;
-                    double a0    = colj[0];
+                    double *cp = LOD + ld * j + 2 * pb;
                     if (apply)
                     {
-                        double acc = 0.0;
-                        for (int i = 1; i < rem; i++) acc = fma(ess[i], colj[i], acc);
-                        const double tmp = acc + a0;
-                        const double w   = tau * tmp;
-                        a0               = a0 - w;
-                        colj[0]          = a0;
-                        for (int i = 1; i < rem; i++) colj[i] = fma(-ess[i], w, colj[i]);
+                        double ae = 0.0, ao = 0.0;
+                        for (int q = 0; q < np; q++)
+                        {
+                            const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
+                            ae = fma(v.x, a.x, ae);
+                            ao = fma(v.y, a.y, ao);
+                        }
+                        const double w = tau * (ae + ao);
+                        for (int q = 0; q < np; q++)
+                        {
+                            const double2 v = ld2(vp + 2 * q);
+                            double2 a       = ld2(cp + 2 * q);
+                            a.x             = fma(-v.x, w, a.x);
+                            a.y             = fma(-v.y, w, a.y);
+                            st2(cp + 2 * q, a);
+                        }
                     }
-                    if (j < n) c.colnorm[j] = fma(-a0, a0, c.colnorm[j]);
+                    if (j < n)
+                    {
+                        const double a0 = LOD[ld * j + row];
+                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
+                    }
                 }
-            }
-            {
-                const unsigned long long m = rem, cc = n - ColIndex;
-                fl.f += 2 * m + (rem > 1 ? 3 * m + 4 + 4 * m * cc : 0) + 2 * (cc - 1);
             }
             ColIndex++;
             gsync<W>();
@@ -507,48 +552,122 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
         const int rank = ColIndex - fc;
         sumRank += rank;
         if (tid == 0) c.rank[g] = rank;
+        {
+            // algorithmic flops of this level's QR in closed form
+            const long long m = dim, cc = n - fc, r = rank, rp = (r < m) ? r : m - 1;
+            const long long T1 = rp * (rp - 1) / 2, T2 = (rp - 1) * rp * (2 * rp - 1) / 6, R1 = r * (r - 1) / 2;
+            long long f = 2 * m * cc + 2 * (r * m - R1) + 2 * (r * (cc - 1) - R1);
+            if (rp > 0) f += 3 * (rp * m - T1) + 4 * rp + 4 * (rp * m * cc - (m + cc) * T1 + T2);
+            fl.f += (unsigned long long)f;
+        }
 
         // Gauss step, lexlse.h:431-471
         if (g + 1 < G && rank > 0)
         {
             const int frn = fr + dim, Rows = nCtr - frn;
-            // Left := Left * inv(R), one thread per row of the lower levels
-            for (int r = tid; r < Rows; r += NT)
+            const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
+            // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
+            // then the 4x4 triangle); per entry the update order is k = 0,1,2,... as in the column-by-column solve
+            for (int t = t0 + tid; t < t1; t += NT)
             {
-                double *rowp = LOD + frn + r;
-                for (int cc = 0; cc < rank; cc++)
+                double *rp       = LOD + 2 * t;
+                const bool full  = (2 * t >= frn);
+                for (int cb = 0; cb < rank; cb += 4)
                 {
-                    const double *Rc = LOD + ld * (fc + cc) + fr;
-                    double acc       = rowp[ld * (fc + cc)];
-                    for (int k = 0; k < cc; k++) acc = fma(-rowp[ld * (fc + k)], Rc[k], acc);
-                    rowp[ld * (fc + cc)] = acc * c.invd[fc + cc];
+                    int col[4];
+                    double2 acc[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        col[q] = fc + ((cb + q < rank) ? cb + q : rank - 1);
+                        acc[q] = ld2(rp + ld * col[q]);
+                    }
+                    for (int k = 0; k < cb; k++)
+                    {
+                        const double2 x  = ld2(rp + ld * (fc + k));
+                        const double *Rk = LOD + fr + k;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            const double rr = Rk[ld * col[q]];
+                            acc[q].x        = fma(-x.x, rr, acc[q].x);
+                            acc[q].y        = fma(-x.y, rr, acc[q].y);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        if (cb + q < rank)
+                        {
+#pragma unroll
+                            for (int q2 = 0; q2 < q; q2++)
+                            {
+                                const double rr = LOD[fr + cb + q2 + ld * col[q]];
+                                acc[q].x        = fma(-acc[q2].x, rr, acc[q].x);
+                                acc[q].y        = fma(-acc[q2].y, rr, acc[q].y);
+                            }
+                            const double iv = c.invd[col[q]];
+                            acc[q].x *= iv;
+                            acc[q].y *= iv;
+                            if (full)
+                                st2(rp + ld * col[q], acc[q]);
+                            else
+                                rp[ld * col[q] + 1] = acc[q].y;
+                        }
+                    }
                 }
             }
             gsync<W>();
-            // Trailing -= Left * Up over columns ColIndex .. n; work item = (row, strip of JS columns)
-            constexpr int JS = 4;
-            const int ncols = n - ColIndex + 1, nstrips = (ncols + JS - 1) / JS, items = Rows * nstrips;
-            for (int item = tid; item < items; item += NT)
+            // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of 4 columns)
             {
-                const int s = item / Rows, r = item - s * Rows;
-                const int j0 = ColIndex + s * JS;
-                int jn = n + 1 - j0;
-                if (jn > JS) jn = JS;
-                double *rowp = LOD + frn + r;
-                double acc[JS];
-#pragma unroll
-                for (int jj = 0; jj < JS; jj++) acc[jj] = (jj < jn) ? rowp[ld * (j0 + jj)] : 0.0;
-                for (int k = 0; k < rank; k++)
+                const int ncols = n - ColIndex + 1, nstrips = (ncols + 3) >> 2, npairs = t1 - t0;
+                int s = 0, tt = tid;
+                while (tt >= npairs && s < nstrips)
                 {
-                    const double l   = -rowp[ld * (fc + k)];
-                    const double *up = LOD + fr + k + ld * j0;
-#pragma unroll
-                    for (int jj = 0; jj < JS; jj++)
-                        if (jj < jn) acc[jj] = fma(l, up[ld * jj], acc[jj]);
+                    tt -= npairs;
+                    s++;
                 }
+                while (s < nstrips)
+                {
+                    const int t = t0 + tt, j0 = ColIndex + 4 * s;
+                    double *rp      = LOD + 2 * t;
+                    const bool full = (2 * t >= frn);
+                    int col[4];
+                    double2 acc[4];
 #pragma unroll
-                for (int jj = 0; jj < JS; jj++)
-                    if (jj < jn) rowp[ld * (j0 + jj)] = acc[jj];
+                    for (int q = 0; q < 4; q++)
+                    {
+                        col[q] = (j0 + q <= n) ? j0 + q : n;
+                        acc[q] = ld2(rp + ld * col[q]);
+                    }
+                    for (int k = 0; k < rank; k++)
+                    {
+                        const double2 l  = ld2(rp + ld * (fc + k));
+                        const double *up = LOD + fr + k;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            const double u = up[ld * col[q]];
+                            acc[q].x       = fma(-l.x, u, acc[q].x);
+                            acc[q].y       = fma(-l.y, u, acc[q].y);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (j0 + q <= n)
+                        {
+                            if (full)
+                                st2(rp + ld * col[q], acc[q]);
+                            else
+                                rp[ld * col[q] + 1] = acc[q].y;
+                        }
+                    tt += NT;
+                    while (tt >= npairs && s < nstrips)
+                    {
+                        tt -= npairs;
+                        s++;
+                    }
+                }
             }
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
             gsync<W>();
@@ -872,6 +991,9 @@ __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, co
     }
     for (int k = tid; k < nCtr; k += NT) c.hh[k] = 0.0;
     for (int k = nFixedPrev + tid; k < n; k += NT) c.lx[k] = 0.0;
+    // rows are processed in aligned pairs: the partner of the last row must be a zero row, not a stale one
+    if (nCtr & 1)
+        for (int col = tid; col <= n; col += NT) c.LOD[nCtr + ld * col] = 0.0;
     gsync<W>();
     nFixed = 0;
     if (sh.off)

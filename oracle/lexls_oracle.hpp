@@ -16,8 +16,12 @@
 // reference order.  This oracle fixes one, chosen so that a warp-per-problem GPU kernel can
 // reproduce it bit for bit:
 //   (S) "sequential": one accumulator, explicit fused multiply-add, ascending index.  Used whenever
-//       many independent outputs exist (per-column dots of a Householder application, the Gauss /
-//       Schur update, gemv rows, initial column norms).
+//       many independent outputs exist and the sum runs over columns / pivots (the Gauss / Schur
+//       update, gemv rows, back-substitution).
+//   (S2) "sequential by row parity": a per-column sum over ROWS of the work matrix keeps two
+//       accumulators, one for even and one for odd absolute row indices (each sequential, fma,
+//       ascending), combined as even + odd.  Used for the initial column norms and for the dot
+//       product of a Householder application (the kernel reads rows in aligned pairs).
 //   (T) "tree32": the terms are dealt round-robin to 32 partial accumulators (term i -> slot i%32,
 //       fma, ascending i), which are then combined by an xor-butterfly of width
 //       min(32, nextpow2(count)).  Used for reductions that produce ONE scalar (pivot column norm,
@@ -288,9 +292,13 @@ public:
             // initial squared column norms over this level's rows, lexlse.h:193-196  (S)
             for (Index k = ColIndex; k < nVar; k++)
             {
-                double acc = 0.0;
-                for (Index i = 0; i < ObjDim; i++) acc = fmad(L(FirstRowIndex + i, k), L(FirstRowIndex + i, k), acc);
-                ColNorms[k] = acc;
+                double acc[2] = {0.0, 0.0};
+                for (Index i = 0; i < ObjDim; i++)
+                {
+                    const Index r = FirstRowIndex + i;
+                    acc[r & 1]    = fmad(L(r, k), L(r, k), acc[r & 1]);
+                }
+                ColNorms[k] = acc[0] + acc[1];
             }
 
             for (Index counter = 0; counter < ObjDim; counter++) // lexlse.h:199
@@ -314,9 +322,12 @@ public:
                 }
                 if (second >= 0.0 && best > 0.0) min_pivot_gap = std::min(min_pivot_gap, (best - second) / best);
 
-                // exact recomputation of the chosen column's norm, lexlse.h:210-211  (T)
-                double maxColNormValue =
-                    tree32_dot(RemainingRows, &L(RowIndex, maxColNormIndex), 1, &L(RowIndex, maxColNormIndex), 1);
+                // exact recomputation of the chosen column's norm, lexlse.h:210-211: ||col||^2 = c0^2 + ||tail||^2 with the
+                // tail norm by (T) — the same two quantities Eigen's makeHouseholder forms (beta^2 = |c0|^2 + tailSqNorm)
+                const double *pc        = &L(RowIndex, maxColNormIndex);
+                const double tailSqNorm = (RemainingRows > 1) ? tree32_dot(RemainingRows - 1, pc + 1, 1, pc + 1, 1) : 0.0;
+                const double c0         = pc[0];
+                double maxColNormValue  = fmad(c0, c0, tailSqNorm);
                 ColNorms[maxColNormIndex] = maxColNormValue;
 
                 if (maxColNormValue > 0.0)
@@ -336,38 +347,37 @@ public:
                 // Householder, lexlse.h:239-248 (Eigen primitives restated from
                 // interfaces/matlab-octave/tests/implementation/lexqr/eigen_like_syntax/
                 //   makeHouseholderInPlace.m:33-58, applyHouseholderOnTheLeft.m:11-20)
+                double beta = c0;
                 if (RemainingRows > 1)
                 {
-                    double *col       = &L(RowIndex, ColIndex);
-                    double tailSqNorm = tree32_dot(RemainingRows - 1, col + 1, 1, col + 1, 1); // (T)
-                    double c0         = col[0];
-                    double tau, beta;
+                    double *col = &L(RowIndex, ColIndex);
+                    double tau;
                     if (tailSqNorm <= DBL_MIN) // Eigen >= 3.3 (the .m file, Eigen 3.2 style, has == 0)
                     {
-                        tau  = 0.0;
-                        beta = c0;
+                        tau = 0.0;
                         for (Index i = 1; i < RemainingRows; i++) col[i] = 0.0;
                     }
                     else
                     {
-                        beta = std::sqrt(fmad(c0, c0, tailSqNorm));
+                        beta = std::sqrt(maxColNormValue);
                         if (c0 >= 0.0) beta = -beta;
-                        double den = c0 - beta;
-                        for (Index i = 1; i < RemainingRows; i++) col[i] = col[i] / den;
-                        tau = (beta - c0) / beta;
+                        const double rden = 1.0 / (c0 - beta); // essential = tail * (1/(c0-beta)) (Eigen 3.2 form of tail/(c0-beta))
+                        for (Index i = 1; i < RemainingRows; i++) col[i] = col[i] * rden;
+                        tau = (beta - c0) * (1.0 / beta);
                     }
                     col[0] = beta;
                     if (tau != 0.0)
                     {
-                        // block rows RowIndex.., columns ColIndex+1 .. nVar (RHS included)
+                        // block rows RowIndex.., columns ColIndex+1 .. nVar (RHS included); v = [1; essential]   (S2)
                         for (Index j = ColIndex + 1; j <= nVar; j++)
                         {
-                            double *a  = &L(RowIndex, j);
-                            double acc = 0.0;
-                            for (Index i = 1; i < RemainingRows; i++) acc = fmad(col[i], a[i], acc); // (S)
-                            double tmp = acc + a[0];
-                            double w   = tau * tmp;
-                            a[0]       = a[0] - w;
+                            double *a     = &L(RowIndex, j);
+                            double acc[2] = {0.0, 0.0};
+                            acc[RowIndex & 1] = fmad(1.0, a[0], acc[RowIndex & 1]);
+                            for (Index i = 1; i < RemainingRows; i++)
+                                acc[(RowIndex + i) & 1] = fmad(col[i], a[i], acc[(RowIndex + i) & 1]);
+                            const double w = tau * (acc[0] + acc[1]);
+                            a[0]           = fmad(-1.0, w, a[0]);
                             for (Index i = 1; i < RemainingRows; i++) a[i] = fmad(-col[i], w, a[i]);
                         }
                     }
@@ -375,7 +385,7 @@ public:
                 }
                 // reciprocal of the diagonal entry R(c,c): the Gauss step and solve() multiply by it (Eigen's
                 // matrix triangular solver does the same; its vector solver divides — last-bit difference only)
-                invdiag[ColIndex] = 1.0 / L(RowIndex, ColIndex);
+                invdiag[ColIndex] = 1.0 / beta;
 
                 ColIndex++;
                 RemainingColumns = nVar - ColIndex;
