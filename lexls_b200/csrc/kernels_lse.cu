@@ -1,0 +1,16 @@
+// kernels_lse.cu — instantiations of the LexLSE kernel (one translation unit per kernel family: parallel compilation)
+#include "lexls_device.cuh"
+namespace lexls_dev
+{
+kernel_fn pick_lse_kernel(int W, bool LG)
+{
+    if (LG) return (kernel_fn)lse_kernel<16, true>;
+    switch (W)
+    {
+    case 1: return (kernel_fn)lse_kernel<1, false>;
+    case 2: return (kernel_fn)lse_kernel<2, false>;
+    case 4: return (kernel_fn)lse_kernel<4, false>;
+    default: return (kernel_fn)lse_kernel<8, false>;
+    }
+}
+} // namespace lexls_dev

@@ -175,8 +175,9 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
         return at;
     };
     const unsigned n = sh.n, M = sh.M, Mall = sh.Mall, m0 = sh.m0, G = sh.G, P = sh.P;
-    // LOD first: it is the target of a TMA bulk copy (LSE) -> 128-byte alignment; size rounded to 16 bytes
-    m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16), 128);
+    // LOD first: it is the target of a TMA bulk copy (LSE) -> 128-byte alignment; size rounded to 16 bytes, followed by
+    // 32 bytes of zeros (the register-window Gauss step reads row pairs that may end up to 3 rows past the matrix)
+    m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16) + 32, 128);
     m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, 128);
     m.sb  = take((lsi && DS) ? 2 * m0 * 8 + 16 : 16, 16);
     m.x = take(n * 8, 8);
@@ -193,6 +194,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
     m.Ax = take(vecs * 8, 8);
     m.Adx = take(vecs * 8, 8);
     m.vv = take(((unsigned)sh.ld + 2) * 8, 16);
+    m.ptmp = take(LX_PANEL_TMP_DOUBLES * 8, 16);
     m.active = take((Mall + 1) * 2, 4);
     m.inactive = take((Mall + 1) * 2, 4);
     m.fidx = take((std::max(m0, (unsigned)sh.nfix) + 1) * 2, 4);
@@ -222,7 +224,14 @@ template <typename K> static int occupancy_of(K kernel, int threads, unsigned sm
     return 0;
 }
 
-typedef void (*kernel_fn)(const Shape, const Params, const SmemMap, const Buffers);
+
+// the solver kernels are instantiated in their own translation units (kernels_*.cu), compiled in parallel
+namespace lexls_dev
+{
+kernel_fn pick_lse_kernel(int W, bool LG);
+kernel_fn pick_lsi_w1_kernel(bool DS);
+kernel_fn pick_lsi_wn_kernel(int W, bool DS, bool LG);
+} // namespace lexls_dev
 
 static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &name)
 {
@@ -231,32 +240,12 @@ static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &nam
     {
         snprintf(buf, sizeof buf, "lse_w%d%s", W, LG ? "_lodglobal" : "");
         name = buf;
-        if (LG) return (kernel_fn)lse_kernel<16, true>;
-        switch (W)
-        {
-        case 1: return (kernel_fn)lse_kernel<1, false>;
-        case 2: return (kernel_fn)lse_kernel<2, false>;
-        case 4: return (kernel_fn)lse_kernel<4, false>;
-        default: return (kernel_fn)lse_kernel<8, false>;
-        }
+        return pick_lse_kernel(W, LG);
     }
     snprintf(buf, sizeof buf, "lsi_w%d%s", W, LG ? "_lodglobal" : (DS ? "_smemdata" : "_l2data"));
     name = buf;
-    if (LG) return (kernel_fn)lsi_kernel<16, false, true>;
-    if (DS) switch (W)
-        {
-        case 1: return (kernel_fn)lsi_kernel<1, true, false>;
-        case 2: return (kernel_fn)lsi_kernel<2, true, false>;
-        case 4: return (kernel_fn)lsi_kernel<4, true, false>;
-        default: return (kernel_fn)lsi_kernel<8, true, false>;
-        }
-    switch (W)
-    {
-    case 1: return (kernel_fn)lsi_kernel<1, false, false>;
-    case 2: return (kernel_fn)lsi_kernel<2, false, false>;
-    case 4: return (kernel_fn)lsi_kernel<4, false, false>;
-    default: return (kernel_fn)lsi_kernel<8, false, false>;
-    }
+    if (!LG && W == 1) return pick_lsi_w1_kernel(DS);
+    return pick_lsi_wn_kernel(W, DS, LG);
 }
 
 static int plan(lexls_b200_batch *h)

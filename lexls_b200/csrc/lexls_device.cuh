@@ -76,7 +76,7 @@ struct Params
 // byte offsets into the dynamic shared memory of one group
 struct SmemMap
 {
-    unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx, vv;
+    unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx, vv, ptmp;
     unsigned active, inactive, atype, alltype, ctype, fidx, ftype, colperm, varofcol, sbidx;
     unsigned ldim, frow, fcol, rank, nact, ninact, scal, mbar, total;
 };
@@ -181,7 +181,7 @@ __device__ __forceinline__ ArgMin bfly_argmax(ArgMin a)
 // ---------------------------------------------------------------------------------------------------------------
 struct Ctx
 {
-    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx, *vv;
+    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx, *vv, *ptmp;
     unsigned short *active, *inactive, *fidx, *colperm, *varofcol, *sbidx;
     unsigned char *atype, *alltype, *ctype, *ftype;
     int *ldim, *frow, *fcol, *rank, *nact, *ninact, *scal;
@@ -207,6 +207,7 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char *base, const SmemMap &m)
     c.Ax       = (double *)(base + m.Ax);
     c.Adx      = (double *)(base + m.Adx);
     c.vv       = (double *)(base + m.vv);
+    c.ptmp     = (double *)(base + m.ptmp);
     c.active   = (unsigned short *)(base + m.active);
     c.inactive = (unsigned short *)(base + m.inactive);
     c.atype    = (unsigned char *)(base + m.atype);
@@ -310,6 +311,311 @@ __device__ __forceinline__ unsigned long long dkey(double v)
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
 }
 
+} // namespace lexls_dev
+#include "lexls_panel.cuh"
+namespace lexls_dev
+{
+
+// ---------------------------------------------------------------------------------------------------------------
+// column-pivoted Householder QR of one level in shared memory, lexlse.h:182-272 (any shape, W warps)
+// ---------------------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const int ld, const int fr, const int dim, int &ColIndex,
+                                              const double tol)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double *const LOD = c.LOD;
+    const int hp      = ld >> 1; // row pairs per column
+    // initial squared column norms over this level's rows, lexlse.h:193-196   (S2)
+    for (int k = ColIndex + tid; k < n; k += NT)
+    {
+        const double *col = LOD + ld * k;
+        double acc[2]     = {0.0, 0.0};
+        for (int r = fr; r < fr + dim; r++) acc[r & 1] = fma(col[r], col[r], acc[r & 1]);
+        c.colnorm[k] = acc[0] + acc[1];
+    }
+    gsync<W>();
+
+    for (int counter = 0; counter < dim; counter++)
+    {
+        const int row = fr + counter, rem = dim - counter;
+
+        // pivot = first maximum of the down-dated norms, lexlse.h:205-206 (every warp computes it redundantly):
+        // integer max over order-preserving keys (REDUX), then the smallest column index holding the maximum
+        int p;
+        {
+            unsigned long long key = 0;
+            int col                = 0x7fffffff;
+            for (int k = ColIndex + lane; k < n; k += 32)
+            {
+                const unsigned long long kk = dkey(c.colnorm[k]);
+                if (col == 0x7fffffff || kk > key)
+                {
+                    key = kk;
+                    col = k;
+                }
+            }
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+            const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+            const bool mine   = (hi == mh) && ((unsigned)key == ml) && (col != 0x7fffffff);
+            p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)col : 0x7fffffffu);
+            if (p >= n) p = ColIndex;
+        }
+
+        // ||tail||^2 by (W8): row i > counter -> slot (i - wb) % 8 with wb = counter & ~3, butterfly 4, 2, 1;
+        // ||col||^2 = c0^2 + ||tail||^2 (lexlse.h:210 and makeHouseholderInPlace)
+        const double *colp = LOD + ld * p + fr;
+        double acc2        = 0.0;
+        if (lane < 8)
+            for (int i = (counter & ~3) + lane; i < dim; i += 8)
+                if (i > counter)
+                {
+                    const double a = colp[i];
+                    acc2           = fma(a, a, acc2);
+                }
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
+        acc2 = __shfl_sync(0xffffffffu, acc2, 0);
+        const double c0     = colp[counter];
+        const double maxval = fma(c0, c0, acc2);
+        if (maxval < tol) break; // rank found, lexlse.h:214-217
+
+        double tau = 0.0, beta = c0, rden = 0.0;
+        bool zero_tail = false;
+        if (rem > 1)
+        {
+            if (acc2 <= DBL_MIN)
+                zero_tail = true;
+            else
+            {
+                beta = sqrt(maxval);
+                if (c0 >= 0.0) beta = -beta;
+                rden = 1.0 / (c0 - beta);
+            }
+        }
+        const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c): Gauss step, solve, and tau
+        if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
+
+        if constexpr (W > 1) gsync<W>(); // all warps finished reading colnorm / column p
+
+        if (tid == 0)
+        {
+            const double t      = c.colnorm[ColIndex];
+            c.colnorm[ColIndex] = maxval;
+            c.colperm[ColIndex] = (unsigned short)p;
+            c.invd[ColIndex]    = inv;
+            if (p != ColIndex)
+            {
+                c.colnorm[p]         = t;
+                const unsigned short s = c.varofcol[ColIndex];
+                c.varofcol[ColIndex] = c.varofcol[p];
+                c.varofcol[p]        = s;
+            }
+            if (rem > 1) c.hh[row] = tau;
+        }
+        // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242); the reflector
+        // v = [1; essential], zero outside its rows, is also written to c.vv for the broadcast reads of the apply
+        const int pb = row >> 1, pe = (row + rem + 1) >> 1; // pairs touched by the reflector
+        for (int t = tid; t < hp; t += NT)
+        {
+            double2 a = ld2(LOD + ld * p + 2 * t);
+            if (p != ColIndex) st2(LOD + ld * p + 2 * t, ld2(LOD + ld * ColIndex + 2 * t));
+            if (rem > 1 && t >= pb && t < pe)
+            {
+                const int r0 = 2 * t, r1 = r0 + 1;
+                double2 v;
+                if (r0 == row)
+                {
+                    a.x = beta;
+                    v.x = 1.0;
+                }
+                else if (r0 > row && r0 < row + rem)
+                {
+                    a.x = zero_tail ? 0.0 : a.x * rden;
+                    v.x = a.x;
+                }
+                else
+                    v.x = 0.0;
+                if (r1 == row)
+                {
+                    a.y = beta;
+                    v.y = 1.0;
+                }
+                else if (r1 > row && r1 < row + rem)
+                {
+                    a.y = zero_tail ? 0.0 : a.y * rden;
+                    v.y = a.y;
+                }
+                else
+                    v.y = 0.0;
+                st2(c.vv + 2 * t, v);
+            }
+            st2(LOD + ld * ColIndex + 2 * t, a);
+        }
+        gsync<W>();
+
+        // apply H to columns ColIndex+1 .. n (RHS included), lexlse.h:243-246, and down-date the norms, :262-266
+        {
+            const bool apply  = tau != 0.0;
+            const double *vp  = c.vv + 2 * pb;
+            const int np      = pe - pb;
+            for (int j = ColIndex + 1 + tid; j <= n; j += NT)
+            {
+                double *cp = LOD + ld * j + 2 * pb;
+                if (apply)
+                {
+                    double ae = 0.0, ao = 0.0;
+                    for (int q = 0; q < np; q++)
+                    {
+                        const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
+                        ae = fma(v.x, a.x, ae);
+                        ao = fma(v.y, a.y, ao);
+                    }
+                    const double w = tau * (ae + ao);
+                    for (int q = 0; q < np; q++)
+                    {
+                        const double2 v = ld2(vp + 2 * q);
+                        double2 a       = ld2(cp + 2 * q);
+                        a.x             = fma(-v.x, w, a.x);
+                        a.y             = fma(-v.y, w, a.y);
+                        st2(cp + 2 * q, a);
+                    }
+                }
+                if (j < n)
+                {
+                    const double a0 = LOD[ld * j + row];
+                    c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
+                }
+            }
+        }
+        ColIndex++;
+        gsync<W>();
+        if (ColIndex == n) break; // lexlse.h:255-258
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gauss step of one level in shared memory, lexlse.h:431-471: Left := Left * inv(R), Trailing -= Left * Up
+// ---------------------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const int ld, const int nCtr, const int fr, const int dim,
+                                                const int fc, const int rank, const int ColIndex)
+{
+    constexpr int NT = 32 * W;
+    const int tid = threadIdx.x;
+    double *const LOD = c.LOD;
+    const int frn = fr + dim, Rows = nCtr - frn;
+    const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
+    // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
+    // then the 4x4 triangle); per entry the update order is k = 0,1,2,... as in the column-by-column solve
+    for (int t = t0 + tid; t < t1; t += NT)
+    {
+        double *rp       = LOD + 2 * t;
+        const bool full  = (2 * t >= frn);
+        for (int cb = 0; cb < rank; cb += 4)
+        {
+            int col[4];
+            double2 acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                col[q] = fc + ((cb + q < rank) ? cb + q : rank - 1);
+                acc[q] = ld2(rp + ld * col[q]);
+            }
+            for (int k = 0; k < cb; k++)
+            {
+                const double2 x  = ld2(rp + ld * (fc + k));
+                const double *Rk = LOD + fr + k;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double rr = Rk[ld * col[q]];
+                    acc[q].x        = fma(-x.x, rr, acc[q].x);
+                    acc[q].y        = fma(-x.y, rr, acc[q].y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                if (cb + q < rank)
+                {
+#pragma unroll
+                    for (int q2 = 0; q2 < q; q2++)
+                    {
+                        const double rr = LOD[fr + cb + q2 + ld * col[q]];
+                        acc[q].x        = fma(-acc[q2].x, rr, acc[q].x);
+                        acc[q].y        = fma(-acc[q2].y, rr, acc[q].y);
+                    }
+                    const double iv = c.invd[col[q]];
+                    acc[q].x *= iv;
+                    acc[q].y *= iv;
+                    if (full)
+                        st2(rp + ld * col[q], acc[q]);
+                    else
+                        rp[ld * col[q] + 1] = acc[q].y;
+                }
+            }
+        }
+    }
+    gsync<W>();
+    // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of 4 columns)
+    {
+        const int ncols = n - ColIndex + 1, nstrips = (ncols + 3) >> 2, npairs = t1 - t0;
+        int s = 0, tt = tid;
+        while (tt >= npairs && s < nstrips)
+        {
+            tt -= npairs;
+            s++;
+        }
+        while (s < nstrips)
+        {
+            const int t = t0 + tt, j0 = ColIndex + 4 * s;
+            double *rp      = LOD + 2 * t;
+            const bool full = (2 * t >= frn);
+            int col[4];
+            double2 acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                col[q] = (j0 + q <= n) ? j0 + q : n;
+                acc[q] = ld2(rp + ld * col[q]);
+            }
+            for (int k = 0; k < rank; k++)
+            {
+                const double2 l  = ld2(rp + ld * (fc + k));
+                const double *up = LOD + fr + k;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double u = up[ld * col[q]];
+                    acc[q].x       = fma(-l.x, u, acc[q].x);
+                    acc[q].y       = fma(-l.y, u, acc[q].y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (j0 + q <= n)
+                {
+                    if (full)
+                        st2(rp + ld * col[q], acc[q]);
+                    else
+                        rp[ld * col[q] + 1] = acc[q].y;
+                }
+            tt += NT;
+            while (tt >= npairs && s < nstrips)
+            {
+                tt -= npairs;
+                s++;
+            }
+        }
+    }
+    gsync<W>();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // l-QR factorization, lexlse.h:117-506 (REGULARIZATION_NONE)
 //   G levels with c.ldim[g] rows starting at c.frow[g]; nCtr = total rows; nFixed fixed variables whose values are in
@@ -318,9 +624,10 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 //   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
-template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const int ld, const int G, const int nCtr,
-                                              const int nFixed, const double tol, FlopCount &fl)
+template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
+                                              const int nCtr, const int nFixed, const double tol, FlopCount &fl)
 {
+    const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol);
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
     double *const LOD = c.LOD;
@@ -385,169 +692,9 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
         const int fr = c.frow[g], dim = c.ldim[g], fc = ColIndex;
         if (tid == 0) c.fcol[g] = fc;
 
-        // initial squared column norms over this level's rows, lexlse.h:193-196   (S2)
-        for (int k = ColIndex + tid; k < n; k += NT)
-        {
-            const double *col = LOD + ld * k;
-            double acc[2]     = {0.0, 0.0};
-            for (int r = fr; r < fr + dim; r++) acc[r & 1] = fma(col[r], col[r], acc[r & 1]);
-            c.colnorm[k] = acc[0] + acc[1];
-        }
-        gsync<W>();
-
-        for (int counter = 0; counter < dim; counter++)
-        {
-            const int row = fr + counter, rem = dim - counter;
-
-            // pivot = first maximum of the down-dated norms, lexlse.h:205-206 (every warp computes it redundantly):
-            // integer max over order-preserving keys (REDUX), then the smallest column index holding the maximum
-            int p;
-            {
-                unsigned long long key = 0;
-                int col                = 0x7fffffff;
-                for (int k = ColIndex + lane; k < n; k += 32)
-                {
-                    const unsigned long long kk = dkey(c.colnorm[k]);
-                    if (col == 0x7fffffff || kk > key)
-                    {
-                        key = kk;
-                        col = k;
-                    }
-                }
-                const unsigned hi = (unsigned)(key >> 32);
-                const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-                const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
-                const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
-                const bool mine   = (hi == mh) && ((unsigned)key == ml) && (col != 0x7fffffff);
-                p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)col : 0x7fffffffu);
-                if (p >= n) p = ColIndex;
-            }
-
-            // ||tail||^2 by (T); ||col||^2 = c0^2 + ||tail||^2 (lexlse.h:210 and makeHouseholderInPlace)
-            const double *colp = LOD + ld * p + row;
-            double acc2        = 0.0;
-            for (int i = lane; i < rem - 1; i += 32)
-            {
-                const double a = colp[i + 1];
-                acc2           = fma(a, a, acc2);
-            }
-            acc2                = bfly_sum(acc2);
-            const double c0     = colp[0];
-            const double maxval = fma(c0, c0, acc2);
-            if (maxval < tol) break; // rank found, lexlse.h:214-217
-
-            double tau = 0.0, beta = c0, rden = 0.0;
-            bool zero_tail = false;
-            if (rem > 1)
-            {
-                if (acc2 <= DBL_MIN)
-                    zero_tail = true;
-                else
-                {
-                    beta = sqrt(maxval);
-                    if (c0 >= 0.0) beta = -beta;
-                    rden = 1.0 / (c0 - beta);
-                }
-            }
-            const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c): Gauss step, solve, and tau
-            if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
-
-            if constexpr (W > 1) gsync<W>(); // all warps finished reading colnorm / column p
-
-            if (tid == 0)
-            {
-                const double t      = c.colnorm[ColIndex];
-                c.colnorm[ColIndex] = maxval;
-                c.colperm[ColIndex] = (unsigned short)p;
-                c.invd[ColIndex]    = inv;
-                if (p != ColIndex)
-                {
-                    c.colnorm[p]         = t;
-                    const unsigned short s = c.varofcol[ColIndex];
-                    c.varofcol[ColIndex] = c.varofcol[p];
-                    c.varofcol[p]        = s;
-                }
-                if (rem > 1) c.hh[row] = tau;
-            }
-            // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242); the reflector
-            // v = [1; essential], zero outside its rows, is also written to c.vv for the broadcast reads of the apply
-            const int pb = row >> 1, pe = (row + rem + 1) >> 1; // pairs touched by the reflector
-            for (int t = tid; t < hp; t += NT)
-            {
-                double2 a = ld2(LOD + ld * p + 2 * t);
-                if (p != ColIndex) st2(LOD + ld * p + 2 * t, ld2(LOD + ld * ColIndex + 2 * t));
-                if (rem > 1 && t >= pb && t < pe)
-                {
-                    const int r0 = 2 * t, r1 = r0 + 1;
-                    double2 v;
-                    if (r0 == row)
-                    {
-                        a.x = beta;
-                        v.x = 1.0;
-                    }
-                    else if (r0 > row && r0 < row + rem)
-                    {
-                        a.x = zero_tail ? 0.0 : a.x * rden;
-                        v.x = a.x;
-                    }
-                    else
-                        v.x = 0.0;
-                    if (r1 == row)
-                    {
-                        a.y = beta;
-                        v.y = 1.0;
-                    }
-                    else if (r1 > row && r1 < row + rem)
-                    {
-                        a.y = zero_tail ? 0.0 : a.y * rden;
-                        v.y = a.y;
-                    }
-                    else
-                        v.y = 0.0;
-                    st2(c.vv + 2 * t, v);
-                }
-                st2(LOD + ld * ColIndex + 2 * t, a);
-            }
-            gsync<W>();
-
-            // apply H to columns ColIndex+1 .. n (RHS included), lexlse.h:243-246, and down-date the norms, :262-266
-            {
-                const bool apply  = tau != 0.0;
-                const double *vp  = c.vv + 2 * pb;
-                const int np      = pe - pb;
-                for (int j = ColIndex + 1 + tid; j <= n; j += NT)
-                {
-                    double *cp = LOD + ld * j + 2 * pb;
-                    if (apply)
-                    {
-                        double ae = 0.0, ao = 0.0;
-                        for (int q = 0; q < np; q++)
-                        {
-                            const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
-                            ae = fma(v.x, a.x, ae);
-                            ao = fma(v.y, a.y, ao);
-                        }
-                        const double w = tau * (ae + ao);
-                        for (int q = 0; q < np; q++)
-                        {
-                            const double2 v = ld2(vp + 2 * q);
-                            double2 a       = ld2(cp + 2 * q);
-                            a.x             = fma(-v.x, w, a.x);
-                            a.y             = fma(-v.y, w, a.y);
-                            st2(cp + 2 * q, a);
-                        }
-                    }
-                    if (j < n)
-                    {
-                        const double a0 = LOD[ld * j + row];
-                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
-                    }
-                }
-            }
-            ColIndex++;
-            gsync<W>();
-            if (ColIndex == n) break; // lexlse.h:255-258
-        }
+        bool done = false;
+        if constexpr (W == 1) done = qr_level_panel_dispatch(pa, fr, dim, ColIndex);
+        if (!done) qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
@@ -564,113 +711,11 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const int n, const i
         // Gauss step, lexlse.h:431-471
         if (g + 1 < G && rank > 0)
         {
-            const int frn = fr + dim, Rows = nCtr - frn;
-            const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
-            // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
-            // then the 4x4 triangle); per entry the update order is k = 0,1,2,... as in the column-by-column solve
-            for (int t = t0 + tid; t < t1; t += NT)
-            {
-                double *rp       = LOD + 2 * t;
-                const bool full  = (2 * t >= frn);
-                for (int cb = 0; cb < rank; cb += 4)
-                {
-                    int col[4];
-                    double2 acc[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        col[q] = fc + ((cb + q < rank) ? cb + q : rank - 1);
-                        acc[q] = ld2(rp + ld * col[q]);
-                    }
-                    for (int k = 0; k < cb; k++)
-                    {
-                        const double2 x  = ld2(rp + ld * (fc + k));
-                        const double *Rk = LOD + fr + k;
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                        {
-                            const double rr = Rk[ld * col[q]];
-                            acc[q].x        = fma(-x.x, rr, acc[q].x);
-                            acc[q].y        = fma(-x.y, rr, acc[q].y);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        if (cb + q < rank)
-                        {
-#pragma unroll
-                            for (int q2 = 0; q2 < q; q2++)
-                            {
-                                const double rr = LOD[fr + cb + q2 + ld * col[q]];
-                                acc[q].x        = fma(-acc[q2].x, rr, acc[q].x);
-                                acc[q].y        = fma(-acc[q2].y, rr, acc[q].y);
-                            }
-                            const double iv = c.invd[col[q]];
-                            acc[q].x *= iv;
-                            acc[q].y *= iv;
-                            if (full)
-                                st2(rp + ld * col[q], acc[q]);
-                            else
-                                rp[ld * col[q] + 1] = acc[q].y;
-                        }
-                    }
-                }
-            }
-            gsync<W>();
-            // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of 4 columns)
-            {
-                const int ncols = n - ColIndex + 1, nstrips = (ncols + 3) >> 2, npairs = t1 - t0;
-                int s = 0, tt = tid;
-                while (tt >= npairs && s < nstrips)
-                {
-                    tt -= npairs;
-                    s++;
-                }
-                while (s < nstrips)
-                {
-                    const int t = t0 + tt, j0 = ColIndex + 4 * s;
-                    double *rp      = LOD + 2 * t;
-                    const bool full = (2 * t >= frn);
-                    int col[4];
-                    double2 acc[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        col[q] = (j0 + q <= n) ? j0 + q : n;
-                        acc[q] = ld2(rp + ld * col[q]);
-                    }
-                    for (int k = 0; k < rank; k++)
-                    {
-                        const double2 l  = ld2(rp + ld * (fc + k));
-                        const double *up = LOD + fr + k;
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                        {
-                            const double u = up[ld * col[q]];
-                            acc[q].x       = fma(-l.x, u, acc[q].x);
-                            acc[q].y       = fma(-l.y, u, acc[q].y);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (j0 + q <= n)
-                        {
-                            if (full)
-                                st2(rp + ld * col[q], acc[q]);
-                            else
-                                rp[ld * col[q] + 1] = acc[q].y;
-                        }
-                    tt += NT;
-                    while (tt >= npairs && s < nstrips)
-                    {
-                        tt -= npairs;
-                        s++;
-                    }
-                }
-            }
+            const int Rows = nCtr - (fr + dim);
+            bool gdone     = false;
+            if constexpr (W == 1) gdone = gauss_step_panel_dispatch(pa, fr, dim, fc, rank, ColIndex);
+            if (!gdone) gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
-            gsync<W>();
         }
 
         if (ColIndex == n) // lexlse.h:475-490
@@ -815,6 +860,8 @@ __global__ void __launch_bounds__(32 * W) lse_kernel(const __grid_constant__ Sha
         c.ldim[g] = sh.dim[g];
         c.frow[g] = sh.goff[g];
     }
+    if constexpr (!LG)
+        if (tid < 4) c.LOD[ld * (n + 1) + tid] = 0.0; // zero pad behind LOD (see build_map)
     gsync<W>();
 
     unsigned parity = 0;
@@ -853,7 +900,7 @@ __global__ void __launch_bounds__(32 * W) lse_kernel(const __grid_constant__ Sha
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W>(c, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
+        const int totalRank = lse_factorize<W>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
         lse_solve<W>(c, n, ld, G);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v)
@@ -1140,6 +1187,8 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
         mbar_init(c.mbar, 1);
         fence_mbar_init();
     }
+    if constexpr (!LG)
+        if (tid < 4) c.LOD[ld * (n + 1) + tid] = 0.0; // zero pad behind LOD (see build_map)
     gsync<W>();
     unsigned parity = 0;
 
@@ -1249,7 +1298,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
         auto factor_and_solve = [&]() {
             const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
             nFixedPrev     = nFixed;
-            totalRank      = lse_factorize<W>(c, n, ld, G, nCtr, nFixed, pr.tol_lindep, fl);
+            totalRank      = lse_factorize<W>(c, sm, n, ld, G, nCtr, nFixed, pr.tol_lindep, fl);
             lse_solve<W>(c, n, ld, G);
         };
 
@@ -1591,4 +1640,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
     }
 }
 
+typedef void (*kernel_fn)(const Shape, const Params, const SmemMap, const Buffers);
+
 } // namespace lexls_dev
+

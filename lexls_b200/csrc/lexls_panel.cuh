@@ -1,0 +1,548 @@
+// lexls_panel.cuh — register-window l-QR for the warp-per-problem kernels (included by lexls_device.cuh).
+//
+// The shared-memory factorization (qr_level_smem / gauss_step_smem in lexls_device.cuh) needs two LDS per DFMA, so it is
+// bound by the LSU and by load-use latency (ncu, profiles/r1_lse_c2_smem_w1_full.txt: fp64 pipe 9.7 % busy, 30.8 k warp
+// instructions per C2 problem).  Here the block being transformed lives in REGISTERS and the inner loops are pure DFMA.
+//
+// QR of one level (lexlse.h:182-272), qr_level_win<NG,S>:
+//   lane = (par, cl),  par = lane >> 4 (row parity),  cl = lane & 15 (column lane);  S column slots per lane
+//   a[q][s] = level row (wb + 2q + par), PHYSICAL column slot (cl, s)          q < 2 NG  (NG groups of 4 rows)
+//   * sliding window: the pivot row is always inside the first 4-row group of the window.  The four pivot steps of a
+//     group are unrolled with a STATIC sub-step r (pivot row = wb + r), so "rows above the pivot" never need masks and
+//     every register index is static; after four steps the window slides down by one group (register moves).
+//     Rows beyond the level's dimension are zero and whole groups beyond it are skipped by uniform branches.
+//   * columns never move inside the window: each slot carries its LOGICAL column position pos[s] (what the reference's
+//     swaps would have produced, lexlse.h:222-232) and the variable it belongs to.  Rows that are NOT in the window
+//     (other levels, finished pivot rows) live in the shared-memory LOD in logical order and are swapped there.
+//   * per step the pivot column is published once through shared memory (double buffered); every lane rebuilds the
+//     reflector for its rows, the Householder application is straight register FMA code: per parity one sequential
+//     chain per column — the (S2) order of the arithmetic contract — closed by one xor-16 shuffle.
+//   * the finished reflector column and the finished pivot row (R entries) go to LOD as they are produced.
+// Gauss step (lexlse.h:431-471), gauss_rows_win<NB,ODD>: one lower ROW per lane, Left(row, :) in registers; R and Up are
+//   read as warp-uniform (broadcast) 128-bit loads, two pivots per load.  Per entry the updates arrive in ascending k.
+// Shapes not covered by a compiled instance fall back to the shared-memory code, level by level (same arithmetic).
+#pragma once
+
+namespace lexls_dev
+{
+
+#define LX_PANEL_MAXRH 20
+// staging buffer (doubles): 2 phases x [2 parities x RH rows of the pivot column]
+#define LX_PANEL_TMP_PHASE (2 * LX_PANEL_MAXRH)
+#define LX_PANEL_TMP_DOUBLES (2 * LX_PANEL_TMP_PHASE)
+
+// The panel routines are real calls (not inlined).  They rebuild their pointers from the dynamic shared-memory base and
+// byte offsets, so that the compiler emits LDS/STS instead of generic loads and stores.
+struct PanelArgs
+{
+    unsigned lod, ptmp, invd, hh, colperm, varofcol; // byte offsets into the group's shared memory
+    int n, ld, nCtr;
+    double tol;
+};
+__device__ __forceinline__ PanelArgs make_panel_args(const SmemMap &m, int n, int ld, int nCtr, double tol)
+{
+    PanelArgs a;
+    a.lod      = m.lod;
+    a.ptmp     = m.ptmp;
+    a.invd     = m.invd;
+    a.hh       = m.hh;
+    a.colperm  = m.colperm;
+    a.varofcol = m.varofcol;
+    a.n        = n;
+    a.ld       = ld;
+    a.nCtr     = nCtr;
+    a.tol      = tol;
+    return a;
+}
+#define LX_PANEL_PTRS                                                                                                   \
+    extern __shared__ __align__(128) unsigned char lx_panel_smem[];                                                     \
+    double *const LOD              = (double *)(lx_panel_smem + pa.lod);                                                \
+    double *const ptmp             = (double *)(lx_panel_smem + pa.ptmp);                                               \
+    double *const invd             = (double *)(lx_panel_smem + pa.invd);                                               \
+    double *const hh               = (double *)(lx_panel_smem + pa.hh);                                                 \
+    unsigned short *const colperm  = (unsigned short *)(lx_panel_smem + pa.colperm);                                    \
+    unsigned short *const varofcol = (unsigned short *)(lx_panel_smem + pa.varofcol);                                   \
+    const int n = pa.n, ld = pa.ld;
+
+// ---------------------------------------------------------------------------------------------------------------
+// one pivot step with static sub-step R4 (pivot row = wb + R4).  Returns false when the level is finished.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NG, int S, int R4>
+__device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)[S], int (&pos)[S], const int (&var)[S],
+                                            int &ColIndex, const int wb, const int ng, const int dim, const int fr,
+                                            const PanelArgs &pa)
+{
+    constexpr int RH = 2 * NG;
+    constexpr int QP = R4 >> 1, PP = R4 & 1; // register and parity of the pivot row
+    LX_PANEL_PTRS
+    const int lane = threadIdx.x & 31, par = lane >> 4, cl = lane & 15;
+    const int counter = wb + R4;
+    if (counter >= dim) return false;
+    const int rem    = dim - counter;
+    double *const tp = ptmp + PP * LX_PANEL_TMP_PHASE; // counter & 1 == R4 & 1
+
+    // pivot = first maximum of the down-dated norms over logical columns ColIndex .. n-1, lexlse.h:205-206
+    int p;
+    {
+        unsigned long long key = 0;
+        int bpos               = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (pos[s] >= ColIndex && pos[s] < n)
+            {
+                const unsigned long long kk = dkey(cn[s]);
+                if (bpos == 0x7fffffff || kk > key || (kk == key && pos[s] < bpos))
+                {
+                    key  = kk;
+                    bpos = pos[s];
+                }
+            }
+        const unsigned hi = (unsigned)(key >> 32);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+        const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+        const bool mine   = (hi == mh) && ((unsigned)key == ml);
+        p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)bpos : 0x7fffffffu);
+    }
+
+    // the owner lanes (one per parity) publish the pivot column's window rows (rows past the level are zeros)
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        if (pos[s] == p)
+        {
+#pragma unroll
+            for (int g = 0; g < NG; g++) st2(tp + par * RH + 2 * g, make_double2(a[2 * g][s], a[2 * g + 1][s]));
+        }
+    __syncwarp();
+    double x[RH];
+#pragma unroll
+    for (int g = 0; g < NG; g++)
+    {
+        const double2 t = ld2(tp + par * RH + 2 * g);
+        x[2 * g]        = t.x;
+        x[2 * g + 1]    = t.y;
+    }
+    const double c0 = tp[PP * RH + QP];
+
+    // ||tail||^2 by (W8): slot of window row j = 2q + par is j % 8 = 2 (q % 4) + par; ||col||^2 = c0^2 + ||tail||^2
+    double acc2;
+    {
+        // window rows of the first group that are below the pivot row: 2q + par > R4
+        const double x0 = (R4 == 0) ? (par ? x[0] : 0.0) : 0.0;
+        const double x1 = (R4 <= 1) ? x[1] : ((R4 == 2) ? (par ? x[1] : 0.0) : 0.0);
+        double t[4];
+        t[0] = x0 * x0;
+        t[1] = x1 * x1;
+        t[2] = x[2] * x[2];
+        t[3] = x[3] * x[3];
+#pragma unroll
+        for (int g = 2; g < NG; g++)
+            if (g < ng)
+            {
+                t[(2 * g) & 3]     = fma(x[2 * g], x[2 * g], t[(2 * g) & 3]);
+                t[(2 * g + 1) & 3] = fma(x[2 * g + 1], x[2 * g + 1], t[(2 * g + 1) & 3]);
+            }
+        const double P = (t[0] + t[2]) + (t[1] + t[3]);
+        acc2           = P + __shfl_xor_sync(0xffffffffu, P, 16);
+    }
+    const double maxval = fma(c0, c0, acc2);
+    if (maxval < pa.tol) return false; // rank found, lexlse.h:214-217 (nothing has been modified)
+
+    double tau = 0.0, beta = c0, rden = 0.0;
+    bool zero_tail = false;
+    if (rem > 1)
+    {
+        if (acc2 <= DBL_MIN)
+            zero_tail = true;
+        else
+        {
+            beta = sqrt(maxval);
+            if (c0 >= 0.0) beta = -beta;
+            rden = 1.0 / (c0 - beta);
+        }
+    }
+    const double inv = 1.0 / beta;
+    if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
+
+    // column swap p <-> ColIndex (lexlse.h:222-232): relabel the slots, swap the rows that live in LOD
+    const bool swap = p != ColIndex;
+    {
+        int pvar = -1;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+        {
+            const bool isp = pos[s] == p, isc = pos[s] == ColIndex;
+            pvar           = isp ? var[s] : pvar;
+            pos[s]         = isp ? ColIndex : (isc ? p : pos[s]);
+        }
+        if (pvar >= 0 && par == 0) varofcol[ColIndex] = (unsigned short)pvar;
+    }
+    if (swap)
+    {
+        const int hp = ld >> 1;
+#pragma unroll 1
+        for (int t = lane; t < hp; t += 32)
+        {
+            const double2 u = ld2(LOD + ld * p + 2 * t), w = ld2(LOD + ld * ColIndex + 2 * t);
+            st2(LOD + ld * p + 2 * t, w);
+            st2(LOD + ld * ColIndex + 2 * t, u);
+        }
+        __syncwarp();
+    }
+    // the finished column: beta on the diagonal, essential part of the reflector below (lexlse.h:241-242)
+#pragma unroll 1
+    for (int l = lane; l < dim - wb; l += 32)
+        if (l >= R4)
+        {
+            const double xr                   = tp[(l & 1) * RH + (l >> 1)];
+            LOD[fr + wb + l + ld * ColIndex] = (l == R4) ? beta : (zero_tail ? 0.0 : xr * rden);
+        }
+    if (lane == 0)
+    {
+        colperm[ColIndex] = (unsigned short)p;
+        invd[ColIndex]    = inv;
+        if (rem > 1) hh[fr + counter] = tau;
+    }
+
+    // apply H = I - tau v v' to the other columns (RHS included), lexlse.h:243-246   (S2); x becomes the reflector v
+    if (tau != 0.0)
+    {
+        x[0] = (R4 == 0) ? (par ? x[0] * rden : 1.0) : ((R4 == 1) ? (par ? 1.0 : 0.0) : 0.0);
+        x[1] = (R4 <= 1) ? x[1] * rden : ((R4 == 2) ? (par ? x[1] * rden : 1.0) : (par ? 1.0 : 0.0));
+        constexpr int Q0 = (R4 >= 2) ? 1 : 0; // register 0 is above the pivot row for both parities
+        double e[S];
+#pragma unroll
+        for (int s = 0; s < S; s++)
+        {
+            e[s] = 0.0;
+#pragma unroll
+            for (int q = Q0; q < 2; q++) e[s] = fma(x[q], a[q][s], e[s]);
+        }
+#pragma unroll
+        for (int g = 1; g < NG; g++)
+            if (g < ng)
+            {
+                x[2 * g] *= rden;
+                x[2 * g + 1] *= rden;
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                {
+                    e[s] = fma(x[2 * g], a[2 * g][s], e[s]);
+                    e[s] = fma(x[2 * g + 1], a[2 * g + 1][s], e[s]);
+                }
+            }
+#pragma unroll
+        for (int s = 0; s < S; s++)
+        {
+            e[s] = tau * (e[s] + __shfl_xor_sync(0xffffffffu, e[s], 16));
+#pragma unroll
+            for (int q = Q0; q < 2; q++) a[q][s] = fma(-x[q], e[s], a[q][s]);
+        }
+#pragma unroll
+        for (int g = 1; g < NG; g++)
+            if (g < ng)
+            {
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                {
+                    a[2 * g][s]     = fma(-x[2 * g], e[s], a[2 * g][s]);
+                    a[2 * g + 1][s] = fma(-x[2 * g + 1], e[s], a[2 * g + 1][s]);
+                }
+            }
+    }
+    // the pivot row is final: R entries of the columns that are still open (and of the RHS)
+    if (par == PP)
+    {
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (pos[s] > ColIndex) LOD[fr + counter + ld * pos[s]] = a[QP][s];
+    }
+    ColIndex++;
+    if (ColIndex == n) return false; // lexlse.h:255-258
+
+    // down-date the norms with the pivot row, lexlse.h:262-266
+#pragma unroll
+    for (int s = 0; s < S; s++)
+    {
+        const double a0 = __shfl_sync(0xffffffffu, a[QP][s], (PP << 4) | cl);
+        cn[s]           = fma(-a0, a0, cn[s]);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// QR of one level in registers.  cb = first not yet eliminated column on entry; returns ColIndex (rank = result - cb).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArgs pa, const int fr, const int dim, const int cb)
+{
+    constexpr int RH = 2 * NG;
+    LX_PANEL_PTRS
+    (void)hh; (void)invd; (void)colperm; (void)ptmp;
+    const int lane = threadIdx.x & 31, par = lane >> 4, cl = lane & 15;
+    int ColIndex   = cb;
+
+    double a[RH][S], cn[S];
+    int pos[S], var[S];
+#pragma unroll
+    for (int s = 0; s < S; s++)
+    {
+        const int col = cb + cl + 16 * s;
+        pos[s]        = (col <= n) ? col : -1;
+        var[s]        = (col < n) ? varofcol[col] : 0;
+#pragma unroll
+        for (int q = 0; q < RH; q++)
+        {
+            const int i = 2 * q + par;
+            a[q][s]     = (i < dim && col <= n) ? LOD[fr + i + ld * col] : 0.0;
+        }
+    }
+    // initial squared column norms over the level's rows, lexlse.h:193-196   (S2)
+#pragma unroll
+    for (int s = 0; s < S; s++)
+    {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < RH; q++) acc = fma(a[q][s], a[q][s], acc);
+        cn[s] = acc + __shfl_xor_sync(0xffffffffu, acc, 16);
+    }
+
+    int wb = 0;
+    for (;;)
+    {
+        const int ng = (dim - wb + 3) >> 2; // groups of 4 rows left in the window (>= 1)
+        if (!qr_win_step<NG, S, 0>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
+        if (!qr_win_step<NG, S, 1>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
+        if (!qr_win_step<NG, S, 2>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
+        if (!qr_win_step<NG, S, 3>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
+        // slide the window down by one group
+#pragma unroll
+        for (int s = 0; s < S; s++)
+        {
+#pragma unroll
+            for (int q = 0; q + 2 < RH; q++) a[q][s] = a[q + 2][s];
+            a[RH - 2][s] = 0.0;
+            a[RH - 1][s] = 0.0;
+        }
+        wb += 4;
+        if (wb >= dim) break;
+    }
+
+    // the open columns (the not yet eliminated rest, and the RHS) go back to LOD at their logical positions
+    const int nrem = dim - wb;
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        if (pos[s] >= ColIndex)
+        {
+            if (nrem > 0)
+            {
+#pragma unroll
+                for (int q = 0; q < RH; q++)
+                    if (2 * q + par < nrem) LOD[fr + wb + 2 * q + par + ld * pos[s]] = a[q][s];
+            }
+            if (par == 0 && pos[s] < n) varofcol[pos[s]] = (unsigned short)var[s];
+        }
+    __syncwarp();
+    return ColIndex;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gauss step of level (frg, fc, rank) for the lower rows [r0, r0 + rows), rows <= 32: one row per lane.
+//   Left(row, 0:rank) := Left * inv(R)   (left-looking over blocks of 4 columns), kept in registers l[];
+//   Trailing(row, ColIndex..n) -= l * Up (four columns at a time).
+// R(k, c) and Up(k, c) sit in LOD rows frg + k: warp-uniform addresses, read in aligned row pairs (LDS.128 broadcast);
+// ODD = frg is odd, the pairs are then (1,2), (3,4), ...  Reads may touch up to 3 rows past the level (finite LOD data
+// or the zero pad behind LOD), always multiplied by l = 0.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NB, bool ODD>
+__device__ __noinline__ void gauss_rows_win(const PanelArgs pa, const int r0, const int rows, const int frg, const int fc,
+                                            const int rank, const int ColIndex)
+{
+    constexpr int NK = 4 * NB;
+    LX_PANEL_PTRS
+    (void)hh; (void)colperm; (void)varofcol; (void)ptmp;
+    const int lane     = threadIdx.x & 31;
+    const bool act     = lane < rows;
+    double *const rowp = LOD + r0 + (act ? lane : 0);
+    const double *Rp   = LOD + frg;
+    double l[NK + 1];
+    l[NK] = 0.0;
+
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+    {
+        if (4 * b >= rank)
+        {
+#pragma unroll
+            for (int q = 0; q < 4; q++) l[4 * b + q] = 0.0;
+            continue;
+        }
+        int col[4];
+        double acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            col[q] = fc + ((4 * b + q < rank) ? 4 * b + q : rank - 1);
+            acc[q] = rowp[ld * col[q]];
+        }
+        // contributions of the finished columns k < 4b, ascending k
+        if constexpr (!ODD)
+        {
+#pragma unroll
+            for (int k = 0; k < 4 * b; k += 2)
+            {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double2 r = ld2(Rp + k + ld * col[q]);
+                    acc[q]          = fma(-l[k], r.x, acc[q]);
+                    acc[q]          = fma(-l[k + 1], r.y, acc[q]);
+                }
+            }
+        }
+        else if (b > 0)
+        {
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] = fma(-l[0], Rp[ld * col[q]], acc[q]);
+#pragma unroll
+            for (int k = 1; k + 1 < 4 * b; k += 2)
+            {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double2 r = ld2(Rp + k + ld * col[q]);
+                    acc[q]          = fma(-l[k], r.x, acc[q]);
+                    acc[q]          = fma(-l[k + 1], r.y, acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] = fma(-l[4 * b - 1], Rp[4 * b - 1 + ld * col[q]], acc[q]);
+        }
+        // the 4 x 4 triangle
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+#pragma unroll
+            for (int q2 = 0; q2 < q; q2++) acc[q] = fma(-acc[q2], Rp[4 * b + q2 + ld * col[q]], acc[q]);
+            acc[q] *= invd[col[q]];
+            if (4 * b + q < rank)
+            {
+                l[4 * b + q] = acc[q];
+                if (act) rowp[ld * col[q]] = acc[q];
+            }
+            else
+                l[4 * b + q] = 0.0;
+        }
+    }
+
+    // Trailing -= Left * Up over columns ColIndex .. n
+    for (int c = ColIndex; c <= n; c += 4)
+    {
+        int cc[4];
+        double t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            cc[q] = (c + q <= n) ? c + q : n;
+            t[q]  = rowp[ld * cc[q]];
+        }
+        if constexpr (!ODD)
+        {
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+            {
+                if (4 * b >= rank) break;
+#pragma unroll
+                for (int k = 4 * b; k < 4 * b + 4; k += 2)
+                {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        const double2 u = ld2(Rp + k + ld * cc[q]);
+                        t[q]            = fma(-l[k], u.x, t[q]);
+                        t[q]            = fma(-l[k + 1], u.y, t[q]);
+                    }
+                }
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < 4; q++) t[q] = fma(-l[0], Rp[ld * cc[q]], t[q]);
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+            {
+                if (4 * b + 1 >= rank) break;
+#pragma unroll
+                for (int k = 4 * b + 1; k < 4 * b + 5; k += 2)
+                {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        const double2 u = ld2(Rp + k + ld * cc[q]);
+                        t[q]            = fma(-l[k], u.x, t[q]);
+                        t[q]            = fma(-l[k + 1], u.y, t[q]);
+                    }
+                }
+            }
+        }
+        if (act)
+        {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (c + q <= n) rowp[ld * cc[q]] = t[q];
+        }
+    }
+    __syncwarp();
+}
+
+// dispatch on (rows, columns); false = shape not covered by a compiled instance
+__device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, int &ColIndex)
+{
+    const int ncols = pa.n + 1 - ColIndex;
+    const int S     = (ncols + 15) >> 4;
+    if (S > 3 || dim > 40 || dim < 1) return false;
+#define LX_QR(NGv)                                                                                                      \
+    {                                                                                                                   \
+        if (S == 1)                                                                                                     \
+            ColIndex = qr_level_win<NGv, 1>(pa, fr, dim, ColIndex);                                                     \
+        else if (S == 2)                                                                                                \
+            ColIndex = qr_level_win<NGv, 2>(pa, fr, dim, ColIndex);                                                     \
+        else                                                                                                            \
+            ColIndex = qr_level_win<NGv, 3>(pa, fr, dim, ColIndex);                                                     \
+        return true;                                                                                                    \
+    }
+    if (dim <= 8) LX_QR(2)
+    if (dim <= 12) LX_QR(3)
+    if (dim <= 20) LX_QR(5)
+    if (dim <= 28) LX_QR(7)
+    LX_QR(10)
+#undef LX_QR
+}
+
+// Gauss step over all lower rows, 32 at a time; false = rank too large for a compiled instance
+__device__ __forceinline__ bool gauss_step_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, const int fc,
+                                                          const int rank, const int ColIndex)
+{
+    if (rank > 40) return false;
+    const int frn = fr + dim;
+    const bool odd = fr & 1;
+    for (int r0 = frn; r0 < pa.nCtr; r0 += 32)
+    {
+        const int rows = min(32, pa.nCtr - r0);
+#define LX_GS(NBv)                                                                                                      \
+    {                                                                                                                   \
+        if (odd)                                                                                                        \
+            gauss_rows_win<NBv, true>(pa, r0, rows, fr, fc, rank, ColIndex);                                            \
+        else                                                                                                            \
+            gauss_rows_win<NBv, false>(pa, r0, rows, fr, fc, rank, ColIndex);                                           \
+    }
+        if (rank <= 8) LX_GS(2)
+        else if (rank <= 12) LX_GS(3)
+        else if (rank <= 20) LX_GS(5)
+        else LX_GS(10)
+#undef LX_GS
+    }
+    return true;
+}
+
+} // namespace lexls_dev

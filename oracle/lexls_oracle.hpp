@@ -24,8 +24,12 @@
 //       product of a Householder application (the kernel reads rows in aligned pairs).
 //   (T) "tree32": the terms are dealt round-robin to 32 partial accumulators (term i -> slot i%32,
 //       fma, ascending i), which are then combined by an xor-butterfly of width
-//       min(32, nextpow2(count)).  Used for reductions that produce ONE scalar (pivot column norm,
-//       Householder tail norm, Householder-sequence dots on a single vector).
+//       min(32, nextpow2(count)).  Used for Householder-sequence dots on a single vector.
+//   (W8) "window tree8": the squared norm of the pivot column's tail at pivot step `counter` of a
+//       level.  With wb = counter & ~3 (the base of the 4-row group holding the pivot row), the
+//       term of in-level row i > counter goes to slot (i - wb) % 8 (fma, ascending i); the 8 slots
+//       are combined by an xor-butterfly with offsets 4, 2, 1.  (The register-window kernel keeps
+//       row wb + 2q + par in register q of the lanes of parity par: slot = 2 (q % 4) + par.)
 // No other floating-point contraction is allowed: compile with -ffp-contract=off.
 #pragma once
 
@@ -119,6 +123,22 @@ static inline double tree32_dot(Index count, const double *a, long sa, const dou
         double q[32];
         for (Index l = 0; l < width; l++) q[l] = p[l] + p[l ^ off];
         for (Index l = 0; l < width; l++) p[l] = q[l];
+    }
+    return p[0];
+}
+
+// (W8) squared norm of col[counter+1 .. dim-1] (col = the level's rows of the pivot column, contiguous)
+static inline double tail_sqnorm_w8(const double *col, Index counter, Index dim)
+{
+    const Index wb = counter & ~3u;
+    double p[8];
+    for (int l = 0; l < 8; l++) p[l] = 0.0;
+    for (Index i = counter + 1; i < dim; i++) p[(i - wb) & 7] = fmad(col[i], col[i], p[(i - wb) & 7]);
+    for (Index off = 4; off >= 1; off >>= 1)
+    {
+        double q[8];
+        for (Index l = 0; l < 8; l++) q[l] = p[l] + p[l ^ off];
+        for (Index l = 0; l < 8; l++) p[l] = q[l];
     }
     return p[0];
 }
@@ -323,9 +343,9 @@ public:
                 if (second >= 0.0 && best > 0.0) min_pivot_gap = std::min(min_pivot_gap, (best - second) / best);
 
                 // exact recomputation of the chosen column's norm, lexlse.h:210-211: ||col||^2 = c0^2 + ||tail||^2 with the
-                // tail norm by (T) — the same two quantities Eigen's makeHouseholder forms (beta^2 = |c0|^2 + tailSqNorm)
+                // tail norm by (W8) — the same two quantities Eigen's makeHouseholder forms (beta^2 = |c0|^2 + tailSqNorm)
                 const double *pc        = &L(RowIndex, maxColNormIndex);
-                const double tailSqNorm = (RemainingRows > 1) ? tree32_dot(RemainingRows - 1, pc + 1, 1, pc + 1, 1) : 0.0;
+                const double tailSqNorm = (RemainingRows > 1) ? tail_sqnorm_w8(pc - counter, counter, ObjDim) : 0.0;
                 const double c0         = pc[0];
                 double maxColNormValue  = fmad(c0, c0, tailSqNorm);
                 ColNorms[maxColNormIndex] = maxColNormValue;

@@ -6,8 +6,8 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lexls_b200", "liblexls_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-cub = os.path.join(tmp, "lexls_b200.sm_100a.cubin")
-sass = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
+sass = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+               for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))
 # walk: function sections ".text.<mangled>" ; line markers '//## File "...", line N' ; instructions '/*0010*/'
 addr2line = {}
 cur_fn, cur_line = None, None

@@ -7,7 +7,8 @@ for a in sys.argv[3:]:
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lexls_b200", "liblexls_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "lexls_b200.sm_100a.cubin")], capture_output=True, text=True).stdout
+sass = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+               for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))
 addr2line, cur_fn, cur = {}, None, None
 for ln in sass.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
