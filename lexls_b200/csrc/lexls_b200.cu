@@ -164,7 +164,7 @@ static unsigned align_up(unsigned v, unsigned a)
     return (v + a - 1) / a * a;
 }
 
-static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
+static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel_only = false)
 {
     SmemMap m{};
     unsigned o = 0;
@@ -180,11 +180,13 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
     m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16) + 32, 128);
     m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, 128);
     m.sb  = take((lsi && DS) ? 2 * m0 * 8 + 16 : 16, 16);
-    m.x = take(n * 8, 8);
-    m.dx = take(n * 8, 8);
+    // x / dx: LexLSI iterates; colnorm / vv: scratch of the shared-memory QR (not needed when every level runs in the
+    // register-window panel)
+    m.x = take(lsi ? n * 8 : 8, 8);
+    m.dx = take(lsi ? n * 8 : 8, 8);
     m.lx = take(n * 8, 8);
     m.lxo = take(n * 8, 8);
-    m.colnorm = take(n * 8, 8);
+    m.colnorm = take(panel_only ? 8 : n * 8, 8);
     m.invd = take(n * 8, 8);
     m.hh = take((M + 1) * 8, 8);
     m.wsp = take((2 * m0 + M + n + 2) * 8, 8);
@@ -193,7 +195,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG)
     m.dv = take(vecs * 8, 8);
     m.Ax = take(vecs * 8, 8);
     m.Adx = take(vecs * 8, 8);
-    m.vv = take(((unsigned)sh.ld + 2) * 8, 16);
+    m.vv = take(panel_only ? 16 : ((unsigned)sh.ld + 2) * 8, 16);
     m.ptmp = take(LX_PANEL_TMP_DOUBLES * 8, 16);
     m.active = take((Mall + 1) * 2, 4);
     m.inactive = take((Mall + 1) * 2, 4);
@@ -268,12 +270,17 @@ static int plan(lexls_b200_batch *h)
     {
         if (!strcmp(e, "l2")) DS = false;
     }
-    SmemMap m = build_map(h->sh, lsi, DS, LG);
+    // every level handled by the register-window panel (lexls_panel.cuh): <= 48 columns, <= 40 rows per level
+    bool panel_only = (W == 1) && cols <= 48;
+    for (int k = 0; k < h->sh.P; k++)
+        if (h->sh.dim[k] > 40 && !(lsi && h->sh.off && k == 0)) panel_only = false;
+    if (W == 1 && !panel_only) W = 2; // the W = 1 kernels have no shared-memory QR (see lse_factorize)
+    SmemMap m = build_map(h->sh, lsi, DS, LG, panel_only);
     // keep the objective data in shared memory only while at least 3 problems stay resident per SM
     if (lsi && DS && m.total * 3 > max_smem)
     {
         DS = false;
-        m  = build_map(h->sh, lsi, DS, LG);
+        m  = build_map(h->sh, lsi, DS, LG, panel_only);
     }
     if (m.total > max_smem || getenv("LEXLS_B200_FORCE_LODGLOBAL"))
     {

@@ -692,9 +692,12 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap,
         const int fr = c.frow[g], dim = c.ldim[g], fc = ColIndex;
         if (tid == 0) c.fcol[g] = fc;
 
-        bool done = false;
-        if constexpr (W == 1) done = qr_level_panel_dispatch(pa, fr, dim, ColIndex);
-        if (!done) qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
+        // warp-per-problem kernels are only planned for shapes that the register-window panel covers (plan() in
+        // lexls_b200.cu), so they carry no shared-memory fallback code
+        if constexpr (W == 1)
+            qr_level_panel_dispatch(pa, fr, dim, ColIndex);
+        else
+            qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
@@ -712,9 +715,10 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap,
         if (g + 1 < G && rank > 0)
         {
             const int Rows = nCtr - (fr + dim);
-            bool gdone     = false;
-            if constexpr (W == 1) gdone = gauss_step_panel_dispatch(pa, fr, dim, fc, rank, ColIndex);
-            if (!gdone) gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
+            if constexpr (W == 1)
+                gauss_step_panel_dispatch(pa, fr, dim, fc, rank, ColIndex);
+            else
+                gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
         }
 
@@ -830,7 +834,7 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
             const int fr = c.frow[g], dim = c.ldim[g], rank = c.rank[g];
             for (int i = lane; i < dim; i += 32) c.wsp[fr + i] = (i < rank) ? 0.0 : -c.LOD[fr + i + ld * n];
             __syncwarp();
-            apply_Q(c, ld, g, c.wsp + fr, lane);
+            if (rank < dim) apply_Q(c, ld, g, c.wsp + fr, lane); // full row rank: Q * 0 = 0 exactly
         }
     }
     gsync<W>();
@@ -840,7 +844,7 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool LG>
-__global__ void __launch_bounds__(32 * W) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, W == 1 ? 9 : 1) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
@@ -1171,6 +1175,23 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
     return true;
 }
 
+// formLexLSE + factorize + solve of one active-set iteration as ONE real call: the LexLSI kernel needs it at three places
+// (phase 1, the first step from a user guess, the loop), and three inlined copies do not fit the instruction cache.
+// The context is rebuilt from the shared-memory map (kernel parameter, __grid_constant__: its address may be taken).
+template <int W, bool DS>
+__device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap &sm, const double tol, double *lod, double *objp,
+                                                  double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl)
+{
+    extern __shared__ __align__(128) unsigned char smem_fs[];
+    Ctx c = make_ctx(smem_fs, sm);
+    c.LOD = lod;
+    ObjView<DS> ov{c, sh, objp, sbp};
+    const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
+    nFixedPrev     = nFixed;
+    totalRank      = lse_factorize<W>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
+    lse_solve<W>(c, sh.n, sh.ld, sh.G);
+}
+
 template <int W, bool DS, bool LG>
 __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
@@ -1296,10 +1317,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
         fl.f = 0;
 
         auto factor_and_solve = [&]() {
-            const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
-            nFixedPrev     = nFixed;
-            totalRank      = lse_factorize<W>(c, sm, n, ld, G, nCtr, nFixed, pr.tol_lindep, fl);
-            lse_solve<W>(c, n, ld, G);
+            lsi_factor_and_solve<W, DS>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl);
         };
 
         // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------

@@ -7,9 +7,9 @@
 // QR of one level (lexlse.h:182-272), qr_level_win<NG,S>:
 //   lane = (par, cl),  par = lane >> 4 (row parity),  cl = lane & 15 (column lane);  S column slots per lane
 //   a[q][s] = level row (wb + 2q + par), PHYSICAL column slot (cl, s)          q < 2 NG  (NG groups of 4 rows)
-//   * sliding window: the pivot row is always inside the first 4-row group of the window.  The four pivot steps of a
-//     group are unrolled with a STATIC sub-step r (pivot row = wb + r), so "rows above the pivot" never need masks and
-//     every register index is static; after four steps the window slides down by one group (register moves).
+//   * sliding window: the pivot row is always inside the first 4-row group of the window: register Q0 (static, 0 or 1)
+//     of the lanes of parity h (dynamic), so "rows above the pivot" never need masks and every register index is
+//     static; after four steps the window slides down by one group (register moves).
 //     Rows beyond the level's dimension are zero and whole groups beyond it are skipped by uniform branches.
 //   * columns never move inside the window: each slot carries its LOGICAL column position pos[s] (what the reference's
 //     swaps would have produced, lexlse.h:222-232) and the variable it belongs to.  Rows that are NOT in the window
@@ -65,38 +65,36 @@ __device__ __forceinline__ PanelArgs make_panel_args(const SmemMap &m, int n, in
     const int n = pa.n, ld = pa.ld;
 
 // ---------------------------------------------------------------------------------------------------------------
-// one pivot step with static sub-step R4 (pivot row = wb + R4).  Returns false when the level is finished.
+// one pivot step.  The pivot row is window row 2 Q0 + h: register Q0 (static) of the lanes of parity h (dynamic), so the
+// code of the steps (wb + 0, wb + 1) and of (wb + 2, wb + 3) is shared.  Returns false when the level is finished.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NG, int S, int R4>
+template <int NG, int S, int Q0>
 __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)[S], int (&pos)[S], const int (&var)[S],
-                                            int &ColIndex, const int wb, const int ng, const int dim, const int fr,
-                                            const PanelArgs &pa)
+                                            int &ColIndex, const int wb, const int h, const int ng, const int dim,
+                                            const int fr, const PanelArgs &pa)
 {
     constexpr int RH = 2 * NG;
-    constexpr int QP = R4 >> 1, PP = R4 & 1; // register and parity of the pivot row
     LX_PANEL_PTRS
     const int lane = threadIdx.x & 31, par = lane >> 4, cl = lane & 15;
-    const int counter = wb + R4;
+    const int counter = wb + 2 * Q0 + h;
     if (counter >= dim) return false;
     const int rem    = dim - counter;
-    double *const tp = ptmp + PP * LX_PANEL_TMP_PHASE; // counter & 1 == R4 & 1
+    double *const tp = ptmp + h * LX_PANEL_TMP_PHASE; // h == counter & 1
 
     // pivot = first maximum of the down-dated norms over logical columns ColIndex .. n-1, lexlse.h:205-206
     int p;
     {
-        unsigned long long key = 0;
-        int bpos               = 0x7fffffff;
+        double best = 0.0;
+        int bpos    = 0x7fffffff;
 #pragma unroll
         for (int s = 0; s < S; s++)
-            if (pos[s] >= ColIndex && pos[s] < n)
-            {
-                const unsigned long long kk = dkey(cn[s]);
-                if (bpos == 0x7fffffff || kk > key || (kk == key && pos[s] < bpos))
-                {
-                    key  = kk;
-                    bpos = pos[s];
-                }
-            }
+        {
+            const bool open = pos[s] >= ColIndex && pos[s] < n;
+            const bool take = open && (bpos == 0x7fffffff || cn[s] > best || (cn[s] == best && pos[s] < bpos));
+            best            = take ? cn[s] : best;
+            bpos            = take ? pos[s] : bpos;
+        }
+        const unsigned long long key = (bpos == 0x7fffffff) ? 0ull : dkey(best);
         const unsigned hi = (unsigned)(key >> 32);
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
         const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
@@ -122,17 +120,16 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
         x[2 * g]        = t.x;
         x[2 * g + 1]    = t.y;
     }
-    const double c0 = tp[PP * RH + QP];
+    const double c0 = tp[h * RH + Q0];
 
     // ||tail||^2 by (W8): slot of window row j = 2q + par is j % 8 = 2 (q % 4) + par; ||col||^2 = c0^2 + ||tail||^2
+    const bool below = par > h; // register Q0 of this lane is below the pivot row
     double acc2;
     {
-        // window rows of the first group that are below the pivot row: 2q + par > R4
-        const double x0 = (R4 == 0) ? (par ? x[0] : 0.0) : 0.0;
-        const double x1 = (R4 <= 1) ? x[1] : ((R4 == 2) ? (par ? x[1] : 0.0) : 0.0);
+        const double xq = below ? x[Q0] : 0.0;
         double t[4];
-        t[0] = x0 * x0;
-        t[1] = x1 * x1;
+        t[0] = (Q0 == 0) ? xq * xq : 0.0;
+        t[1] = (Q0 == 0) ? x[1] * x[1] : xq * xq;
         t[2] = x[2] * x[2];
         t[3] = x[3] * x[3];
 #pragma unroll
@@ -147,6 +144,31 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
     }
     const double maxval = fma(c0, c0, acc2);
     if (maxval < pa.tol) return false; // rank found, lexlse.h:214-217 (nothing has been modified)
+
+    // column swap p <-> ColIndex (lexlse.h:222-232): relabel the slots, swap the rows that live in LOD
+    {
+        int pvar = -1;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+        {
+            const bool isp = pos[s] == p, isc = pos[s] == ColIndex;
+            pvar           = isp ? var[s] : pvar;
+            pos[s]         = isp ? ColIndex : (isc ? p : pos[s]);
+        }
+        if (pvar >= 0 && par == 0) varofcol[ColIndex] = (unsigned short)pvar;
+    }
+    if (p != ColIndex)
+    {
+        const int hp = ld >> 1;
+#pragma unroll 1
+        for (int t = lane; t < hp; t += 32)
+        {
+            const double2 u = ld2(LOD + ld * p + 2 * t), w = ld2(LOD + ld * ColIndex + 2 * t);
+            st2(LOD + ld * p + 2 * t, w);
+            st2(LOD + ld * ColIndex + 2 * t, u);
+        }
+        __syncwarp();
+    }
 
     double tau = 0.0, beta = c0, rden = 0.0;
     bool zero_tail = false;
@@ -164,52 +186,29 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
     const double inv = 1.0 / beta;
     if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
 
-    // column swap p <-> ColIndex (lexlse.h:222-232): relabel the slots, swap the rows that live in LOD
-    const bool swap = p != ColIndex;
-    {
-        int pvar = -1;
-#pragma unroll
-        for (int s = 0; s < S; s++)
-        {
-            const bool isp = pos[s] == p, isc = pos[s] == ColIndex;
-            pvar           = isp ? var[s] : pvar;
-            pos[s]         = isp ? ColIndex : (isc ? p : pos[s]);
-        }
-        if (pvar >= 0 && par == 0) varofcol[ColIndex] = (unsigned short)pvar;
-    }
-    if (swap)
-    {
-        const int hp = ld >> 1;
-#pragma unroll 1
-        for (int t = lane; t < hp; t += 32)
-        {
-            const double2 u = ld2(LOD + ld * p + 2 * t), w = ld2(LOD + ld * ColIndex + 2 * t);
-            st2(LOD + ld * p + 2 * t, w);
-            st2(LOD + ld * ColIndex + 2 * t, u);
-        }
-        __syncwarp();
-    }
     // the finished column: beta on the diagonal, essential part of the reflector below (lexlse.h:241-242)
-#pragma unroll 1
-    for (int l = lane; l < dim - wb; l += 32)
-        if (l >= R4)
-        {
-            const double xr                   = tp[(l & 1) * RH + (l >> 1)];
-            LOD[fr + wb + l + ld * ColIndex] = (l == R4) ? beta : (zero_tail ? 0.0 : xr * rden);
-        }
-    if (lane == 0)
     {
-        colperm[ColIndex] = (unsigned short)p;
-        invd[ColIndex]    = inv;
-        if (rem > 1) hh[fr + counter] = tau;
+        double *const dst = LOD + fr + wb + ld * ColIndex;
+#pragma unroll 1
+        for (int l = lane; l < dim - wb; l += 32)
+            if (l >= 2 * Q0 + h)
+            {
+                const double xr = tp[(l & 1) * RH + (l >> 1)];
+                dst[l]          = (l == 2 * Q0 + h) ? beta : (zero_tail ? 0.0 : xr * rden);
+            }
+        if (lane == 0)
+        {
+            colperm[ColIndex] = (unsigned short)p;
+            invd[ColIndex]    = inv;
+            if (rem > 1) hh[fr + counter] = tau;
+        }
     }
 
     // apply H = I - tau v v' to the other columns (RHS included), lexlse.h:243-246   (S2); x becomes the reflector v
     if (tau != 0.0)
     {
-        x[0] = (R4 == 0) ? (par ? x[0] * rden : 1.0) : ((R4 == 1) ? (par ? 1.0 : 0.0) : 0.0);
-        x[1] = (R4 <= 1) ? x[1] * rden : ((R4 == 2) ? (par ? x[1] * rden : 1.0) : (par ? 1.0 : 0.0));
-        constexpr int Q0 = (R4 >= 2) ? 1 : 0; // register 0 is above the pivot row for both parities
+        x[Q0] = below ? x[Q0] * rden : ((par == h) ? 1.0 : 0.0);
+        if (Q0 == 0) x[1] *= rden;
         double e[S];
 #pragma unroll
         for (int s = 0; s < S; s++)
@@ -251,11 +250,11 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
             }
     }
     // the pivot row is final: R entries of the columns that are still open (and of the RHS)
-    if (par == PP)
     {
+        double *const dst = LOD + fr + counter;
 #pragma unroll
         for (int s = 0; s < S; s++)
-            if (pos[s] > ColIndex) LOD[fr + counter + ld * pos[s]] = a[QP][s];
+            if (par == h && pos[s] > ColIndex) dst[ld * pos[s]] = a[Q0][s];
     }
     ColIndex++;
     if (ColIndex == n) return false; // lexlse.h:255-258
@@ -264,7 +263,7 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
 #pragma unroll
     for (int s = 0; s < S; s++)
     {
-        const double a0 = __shfl_sync(0xffffffffu, a[QP][s], (PP << 4) | cl);
+        const double a0 = __shfl_sync(0xffffffffu, a[Q0][s], (h << 4) | cl);
         cn[s]           = fma(-a0, a0, cn[s]);
     }
     return true;
@@ -289,12 +288,9 @@ template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArg
         const int col = cb + cl + 16 * s;
         pos[s]        = (col <= n) ? col : -1;
         var[s]        = (col < n) ? varofcol[col] : 0;
+        const double *src = LOD + fr + par + ld * ((col <= n) ? col : n);
 #pragma unroll
-        for (int q = 0; q < RH; q++)
-        {
-            const int i = 2 * q + par;
-            a[q][s]     = (i < dim && col <= n) ? LOD[fr + i + ld * col] : 0.0;
-        }
+        for (int q = 0; q < RH; q++) a[q][s] = (2 * q + par < dim && col <= n) ? src[2 * q] : 0.0;
     }
     // initial squared column norms over the level's rows, lexlse.h:193-196   (S2)
 #pragma unroll
@@ -310,10 +306,13 @@ template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArg
     for (;;)
     {
         const int ng = (dim - wb + 3) >> 2; // groups of 4 rows left in the window (>= 1)
-        if (!qr_win_step<NG, S, 0>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
-        if (!qr_win_step<NG, S, 1>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
-        if (!qr_win_step<NG, S, 2>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
-        if (!qr_win_step<NG, S, 3>(a, cn, pos, var, ColIndex, wb, ng, dim, fr, pa)) break;
+        bool go      = true;
+#pragma unroll 1
+        for (int h = 0; h < 2 && go; h++) go = qr_win_step<NG, S, 0>(a, cn, pos, var, ColIndex, wb, h, ng, dim, fr, pa);
+        if (!go) break;
+#pragma unroll 1
+        for (int h = 0; h < 2 && go; h++) go = qr_win_step<NG, S, 1>(a, cn, pos, var, ColIndex, wb, h, ng, dim, fr, pa);
+        if (!go) break;
         // slide the window down by one group
 #pragma unroll
         for (int s = 0; s < S; s++)
@@ -335,9 +334,10 @@ template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArg
         {
             if (nrem > 0)
             {
+                double *const dst = LOD + fr + wb + par + ld * pos[s];
 #pragma unroll
                 for (int q = 0; q < RH; q++)
-                    if (2 * q + par < nrem) LOD[fr + wb + 2 * q + par + ld * pos[s]] = a[q][s];
+                    if (2 * q + par < nrem) dst[2 * q] = a[q][s];
             }
             if (par == 0 && pos[s] < n) varofcol[pos[s]] = (unsigned short)var[s];
         }
@@ -500,7 +500,8 @@ __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, con
 {
     const int ncols = pa.n + 1 - ColIndex;
     const int S     = (ncols + 15) >> 4;
-    if (S > 3 || dim > 40 || dim < 1) return false;
+    if (dim < 1) return true; // empty level: rank 0
+    if (S > 3 || dim > 40) return false;
 #define LX_QR(NGv)                                                                                                      \
     {                                                                                                                   \
         if (S == 1)                                                                                                     \
@@ -511,10 +512,8 @@ __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, con
             ColIndex = qr_level_win<NGv, 3>(pa, fr, dim, ColIndex);                                                     \
         return true;                                                                                                    \
     }
-    if (dim <= 8) LX_QR(2)
     if (dim <= 12) LX_QR(3)
     if (dim <= 20) LX_QR(5)
-    if (dim <= 28) LX_QR(7)
     LX_QR(10)
 #undef LX_QR
 }
@@ -536,8 +535,7 @@ __device__ __forceinline__ bool gauss_step_panel_dispatch(const PanelArgs &pa, c
         else                                                                                                            \
             gauss_rows_win<NBv, false>(pa, r0, rows, fr, fc, rank, ColIndex);                                           \
     }
-        if (rank <= 8) LX_GS(2)
-        else if (rank <= 12) LX_GS(3)
+        if (rank <= 12) LX_GS(3)
         else if (rank <= 20) LX_GS(5)
         else LX_GS(10)
 #undef LX_GS
