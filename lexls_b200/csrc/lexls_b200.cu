@@ -259,16 +259,19 @@ static int plan(lexls_b200_batch *h)
     const bool lsi          = h->kind == LEXLS_B200_LSI;
     const int cols          = h->sh.n + 1;
 
-    int W = cols <= 64 ? 1 : (cols <= 128 ? 2 : (cols <= 256 ? 4 : 8));
+    // LexLSE: one warp per problem (register-window panel).  LexLSI: the active-set loop is latency bound and its code
+    // has to stay small (32 KB instruction cache), so two warps per problem on the compact shared-memory routines with
+    // the objective data read through L2 keep more warps resident (measured on C3: 18.5 ms vs 29.8 ms, profiles/).
+    int W = cols <= 64 ? (lsi ? 2 : 1) : (cols <= 128 ? 2 : (cols <= 256 ? 4 : 8));
     if (const char *e = getenv("LEXLS_B200_WARPS"))
     {
         int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8) W = w;
     }
-    bool DS = lsi, LG = false;
+    bool DS = false, LG = false;
     if (const char *e = getenv("LEXLS_B200_DATA"))
     {
-        if (!strcmp(e, "l2")) DS = false;
+        if (!strcmp(e, "smem")) DS = lsi;
     }
     // every level handled by the register-window panel (lexls_panel.cuh): <= 48 columns, <= 40 rows per level
     bool panel_only = (W == 1) && cols <= 48;

@@ -624,7 +624,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 //   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
-template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
+template <int W, bool CQ = false> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
                                               const int nCtr, const int nFixed, const double tol, FlopCount &fl)
 {
     const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol);
@@ -695,7 +695,7 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap,
         // warp-per-problem kernels are only planned for shapes that the register-window panel covers (plan() in
         // lexls_b200.cu), so they carry no shared-memory fallback code
         if constexpr (W == 1)
-            qr_level_panel_dispatch(pa, fr, dim, ColIndex);
+            qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
             qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
 
@@ -716,7 +716,7 @@ template <int W> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap,
         {
             const int Rows = nCtr - (fr + dim);
             if constexpr (W == 1)
-                gauss_step_panel_dispatch(pa, fr, dim, fc, rank, ColIndex);
+                gauss_step_panel_dispatch<CQ>(pa, fr, dim, fc, rank, ColIndex);
             else
                 gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
@@ -1188,7 +1188,7 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     ObjView<DS> ov{c, sh, objp, sbp};
     const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
     nFixedPrev     = nFixed;
-    totalRank      = lse_factorize<W>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
+    totalRank      = lse_factorize<W, true>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
     lse_solve<W>(c, sh.n, sh.ld, sh.G);
 }
 

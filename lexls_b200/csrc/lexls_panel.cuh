@@ -18,8 +18,8 @@
 //     reflector for its rows, the Householder application is straight register FMA code: per parity one sequential
 //     chain per column — the (S2) order of the arithmetic contract — closed by one xor-16 shuffle.
 //   * the finished reflector column and the finished pivot row (R entries) go to LOD as they are produced.
-// Gauss step (lexlse.h:431-471), gauss_rows_win<NB,ODD>: one lower ROW per lane, Left(row, :) in registers; R and Up are
-//   read as warp-uniform (broadcast) 128-bit loads, two pivots per load.  Per entry the updates arrive in ascending k.
+// Gauss step (lexlse.h:431-471), gauss_rows_dyn: one lower ROW per lane; R and Up are read as warp-uniform (broadcast)
+//   128-bit loads, two pivots per load.  Per entry the updates arrive in ascending k.
 // Shapes not covered by a compiled instance fall back to the shared-memory code, level by level (same arithmetic).
 #pragma once
 
@@ -272,7 +272,8 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
 // ---------------------------------------------------------------------------------------------------------------
 // QR of one level in registers.  cb = first not yet eliminated column on entry; returns ColIndex (rank = result - cb).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArgs pa, const int fr, const int dim, const int cb)
+template <int NG, int S, bool COMPACT>
+__device__ __noinline__ int qr_level_win(const PanelArgs pa, const int fr, const int dim, const int cb)
 {
     constexpr int RH = 2 * NG;
     LX_PANEL_PTRS
@@ -310,19 +311,35 @@ template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArg
 #pragma unroll 1
         for (int h = 0; h < 2 && go; h++) go = qr_win_step<NG, S, 0>(a, cn, pos, var, ColIndex, wb, h, ng, dim, fr, pa);
         if (!go) break;
-#pragma unroll 1
-        for (int h = 0; h < 2 && go; h++) go = qr_win_step<NG, S, 1>(a, cn, pos, var, ColIndex, wb, h, ng, dim, fr, pa);
-        if (!go) break;
-        // slide the window down by one group
-#pragma unroll
-        for (int s = 0; s < S; s++)
+        if constexpr (COMPACT)
         {
+            // one step body only (instruction-cache footprint): slide by one register (two rows) every two steps.
+            // (W8) still holds: the accumulator a row feeds rotates with the window, the final sum is symmetric.
 #pragma unroll
-            for (int q = 0; q + 2 < RH; q++) a[q][s] = a[q + 2][s];
-            a[RH - 2][s] = 0.0;
-            a[RH - 1][s] = 0.0;
+            for (int s = 0; s < S; s++)
+            {
+#pragma unroll
+                for (int q = 0; q + 1 < RH; q++) a[q][s] = a[q + 1][s];
+                a[RH - 1][s] = 0.0;
+            }
+            wb += 2;
         }
-        wb += 4;
+        else
+        {
+#pragma unroll 1
+            for (int h = 0; h < 2 && go; h++) go = qr_win_step<NG, S, 1>(a, cn, pos, var, ColIndex, wb, h, ng, dim, fr, pa);
+            if (!go) break;
+            // slide the window down by one group
+#pragma unroll
+            for (int s = 0; s < S; s++)
+            {
+#pragma unroll
+                for (int q = 0; q + 2 < RH; q++) a[q][s] = a[q + 2][s];
+                a[RH - 2][s] = 0.0;
+                a[RH - 1][s] = 0.0;
+            }
+            wb += 4;
+        }
         if (wb >= dim) break;
     }
 
@@ -346,7 +363,129 @@ template <int NG, int S> __device__ __noinline__ int qr_level_win(const PanelArg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Gauss step of level (frg, fc, rank) for the lower rows [r0, r0 + rows), rows <= 32: one row per lane.
+// Gauss step of level (frg, fc, rank) for ALL lower rows [r0, nCtr): one row per lane, 32 rows per pass.
+//   Left(row, 0:rank) := Left * inv(R)   (left-looking over blocks of 4 columns), then
+//   Trailing(row, ColIndex..n) -= Left * Up (four columns at a time).
+// Left(row, k) is re-read from the lane's own LOD row; R(k, c) and Up(k, c) sit in LOD rows frg + k at warp-uniform
+// addresses and are read as aligned row pairs (LDS.128 broadcast, two pivots per load; a first odd pivot is peeled).
+// Plain dynamic loops: one small routine for every shape (the instruction cache holds 32 KB).  Per entry the updates
+// arrive in ascending k, as in the oracle.
+// ---------------------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void gauss_rows_dyn(const PanelArgs pa, const int r0, const int frg, const int fc, const int rank,
+                                            const int ColIndex)
+{
+    LX_PANEL_PTRS
+    (void)hh; (void)colperm; (void)varofcol; (void)ptmp;
+    const int lane  = threadIdx.x & 31;
+    const int kpeel = frg & 1; // rows frg + k with k >= kpeel, k - kpeel even, start an aligned pair
+    for (int rb = r0; rb < pa.nCtr; rb += 32)
+    {
+        const bool act     = rb + lane < pa.nCtr;
+        double *const rowp = LOD + (act ? rb + lane : rb);
+        const double *Rp   = LOD + frg;
+        const double *lp   = rowp + ld * fc; // Left(row, k) = lp[ld * k]
+
+        for (int cb = 0; cb < rank; cb += 4)
+        {
+            const double *Rc[4];
+            double acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int cq = fc + ((cb + q < rank) ? cb + q : rank - 1);
+                Rc[q]        = Rp + ld * cq;
+                acc[q]       = rowp[ld * cq];
+            }
+            // finished columns k < cb (cb is a multiple of 4), ascending k
+            int k = 0;
+            if (kpeel && cb > 0)
+            {
+                const double l0 = lp[0];
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[q] = fma(-l0, Rc[q][0], acc[q]);
+                k = 1;
+            }
+#pragma unroll 2
+            for (; k + 1 < cb; k += 2)
+            {
+                const double l0 = lp[ld * k], l1 = lp[ld * (k + 1)];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double2 r = ld2(Rc[q] + k);
+                    acc[q]          = fma(-l0, r.x, acc[q]);
+                    acc[q]          = fma(-l1, r.y, acc[q]);
+                }
+            }
+            if (k < cb)
+            {
+                const double l0 = lp[ld * k];
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[q] = fma(-l0, Rc[q][k], acc[q]);
+            }
+            // the 4 x 4 triangle
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+#pragma unroll
+                for (int q2 = 0; q2 < q; q2++) acc[q] = fma(-acc[q2], Rc[q][cb + q2], acc[q]);
+                acc[q] *= invd[fc + ((cb + q < rank) ? cb + q : rank - 1)];
+                if (act && cb + q < rank) rowp[ld * (fc + cb + q)] = acc[q];
+            }
+            __syncwarp(); // lanes re-read their own stores only, but keep the passes in step
+        }
+
+        // Trailing -= Left * Up over columns ColIndex .. n
+        for (int c = ColIndex; c <= n; c += 4)
+        {
+            const double *Uc[4];
+            double t[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int cq = (c + q <= n) ? c + q : n;
+                Uc[q]        = Rp + ld * cq;
+                t[q]         = rowp[ld * cq];
+            }
+            int k = 0;
+            if (kpeel)
+            {
+                const double l0 = lp[0];
+#pragma unroll
+                for (int q = 0; q < 4; q++) t[q] = fma(-l0, Uc[q][0], t[q]);
+                k = 1;
+            }
+#pragma unroll 2
+            for (; k + 1 < rank; k += 2)
+            {
+                const double l0 = lp[ld * k], l1 = lp[ld * (k + 1)];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const double2 u = ld2(Uc[q] + k);
+                    t[q]            = fma(-l0, u.x, t[q]);
+                    t[q]            = fma(-l1, u.y, t[q]);
+                }
+            }
+            if (k < rank)
+            {
+                const double l0 = lp[ld * k];
+#pragma unroll
+                for (int q = 0; q < 4; q++) t[q] = fma(-l0, Uc[q][k], t[q]);
+            }
+            if (act)
+            {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (c + q <= n) rowp[ld * (c + q)] = t[q];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (register variant, used by the LexLSE kernel) Gauss step of level (frg, fc, rank) for the lower rows [r0, r0 + rows), rows <= 32: one row per lane.
 //   Left(row, 0:rank) := Left * inv(R)   (left-looking over blocks of 4 columns), kept in registers l[];
 //   Trailing(row, ColIndex..n) -= l * Up (four columns at a time).
 // R(k, c) and Up(k, c) sit in LOD rows frg + k: warp-uniform addresses, read in aligned row pairs (LDS.128 broadcast);
@@ -496,6 +635,7 @@ __device__ __noinline__ void gauss_rows_win(const PanelArgs pa, const int r0, co
 }
 
 // dispatch on (rows, columns); false = shape not covered by a compiled instance
+template <bool COMPACT>
 __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, int &ColIndex)
 {
     const int ncols = pa.n + 1 - ColIndex;
@@ -505,25 +645,29 @@ __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, con
 #define LX_QR(NGv)                                                                                                      \
     {                                                                                                                   \
         if (S == 1)                                                                                                     \
-            ColIndex = qr_level_win<NGv, 1>(pa, fr, dim, ColIndex);                                                     \
+            ColIndex = qr_level_win<NGv, 1, COMPACT>(pa, fr, dim, ColIndex);                                            \
         else if (S == 2)                                                                                                \
-            ColIndex = qr_level_win<NGv, 2>(pa, fr, dim, ColIndex);                                                     \
+            ColIndex = qr_level_win<NGv, 2, COMPACT>(pa, fr, dim, ColIndex);                                            \
         else                                                                                                            \
-            ColIndex = qr_level_win<NGv, 3>(pa, fr, dim, ColIndex);                                                     \
+            ColIndex = qr_level_win<NGv, 3, COMPACT>(pa, fr, dim, ColIndex);                                            \
         return true;                                                                                                    \
     }
-    if (dim <= 12) LX_QR(3)
     if (dim <= 20) LX_QR(5)
     LX_QR(10)
 #undef LX_QR
 }
 
-// Gauss step over all lower rows, 32 at a time; false = rank too large for a compiled instance
+// Gauss step over all lower rows: COMPACT -> the small dynamic-loop routine; otherwise Left in registers, 32 rows at a time
+template <bool COMPACT>
 __device__ __forceinline__ bool gauss_step_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, const int fc,
                                                           const int rank, const int ColIndex)
 {
-    if (rank > 40) return false;
-    const int frn = fr + dim;
+    if (COMPACT || rank > 40)
+    {
+        gauss_rows_dyn(pa, fr + dim, fr, fc, rank, ColIndex);
+        return true;
+    }
+    const int frn  = fr + dim;
     const bool odd = fr & 1;
     for (int r0 = frn; r0 < pa.nCtr; r0 += 32)
     {
