@@ -127,8 +127,8 @@ def test_no_simple_bounds_and_degenerate_rows(oracle):
     compare_lsi(got, ref, 3)
 
 
-@pytest.mark.parametrize("env", [{"LEXLS_B200_WARPS": "2"}, {"LEXLS_B200_WARPS": "4"}, {"LEXLS_B200_DATA": "l2"},
-                                 {"LEXLS_B200_FORCE_LODGLOBAL": "1"}])
+@pytest.mark.parametrize("env", [{"LEXLS_B200_WARPS": "1"}, {"LEXLS_B200_WARPS": "1", "LEXLS_B200_DATA": "smem"},
+                                 {"LEXLS_B200_WARPS": "4"}, {"LEXLS_B200_DATA": "smem"}, {"LEXLS_B200_FORCE_LODGLOBAL": "1"}])
 def test_kernel_variants_match(oracle, env, monkeypatch):
     from lexls_b200 import problems
     for k, v in env.items():
