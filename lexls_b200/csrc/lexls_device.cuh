@@ -14,6 +14,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 namespace lexls_dev
 {

@@ -84,23 +84,23 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
     // pivot = first maximum of the down-dated norms over logical columns ColIndex .. n-1, lexlse.h:205-206
     int p;
     {
-        double best = 0.0;
-        int bpos    = 0x7fffffff;
+        // closed slots (finished columns, the RHS, padding) carry a norm of -inf and never win
+        double best = cn[0];
+        int bpos    = pos[0];
 #pragma unroll
-        for (int s = 0; s < S; s++)
+        for (int s = 1; s < S; s++)
         {
-            const bool open = pos[s] >= ColIndex && pos[s] < n;
-            const bool take = open && (bpos == 0x7fffffff || cn[s] > best || (cn[s] == best && pos[s] < bpos));
+            const bool take = cn[s] > best || (cn[s] == best && (unsigned)pos[s] < (unsigned)bpos);
             best            = take ? cn[s] : best;
             bpos            = take ? pos[s] : bpos;
         }
-        const unsigned long long key = (bpos == 0x7fffffff) ? 0ull : dkey(best);
+        const unsigned long long key = dkey(best);
         const unsigned hi = (unsigned)(key >> 32);
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
         const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
         const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
         const bool mine   = (hi == mh) && ((unsigned)key == ml);
-        p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)bpos : 0x7fffffffu);
+        p                 = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)bpos : 0xffffffffu);
     }
 
     // the owner lanes (one per parity) publish the pivot column's window rows (rows past the level are zeros)
@@ -133,12 +133,11 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
         t[2] = x[2] * x[2];
         t[3] = x[3] * x[3];
 #pragma unroll
-        for (int g = 2; g < NG; g++)
-            if (g < ng)
-            {
-                t[(2 * g) & 3]     = fma(x[2 * g], x[2 * g], t[(2 * g) & 3]);
-                t[(2 * g + 1) & 3] = fma(x[2 * g + 1], x[2 * g + 1], t[(2 * g + 1) & 3]);
-            }
+        for (int g = 2; g < NG; g++) // rows past the level were published as zeros: no guard needed
+        {
+            t[(2 * g) & 3]     = fma(x[2 * g], x[2 * g], t[(2 * g) & 3]);
+            t[(2 * g + 1) & 3] = fma(x[2 * g + 1], x[2 * g + 1], t[(2 * g + 1) & 3]);
+        }
         const double P = (t[0] + t[2]) + (t[1] + t[3]);
         acc2           = P + __shfl_xor_sync(0xffffffffu, P, 16);
     }
@@ -154,6 +153,7 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
             const bool isp = pos[s] == p, isc = pos[s] == ColIndex;
             pvar           = isp ? var[s] : pvar;
             pos[s]         = isp ? ColIndex : (isc ? p : pos[s]);
+            cn[s]          = isp ? -CUDART_INF : cn[s];
         }
         if (pvar >= 0 && par == 0) varofcol[ColIndex] = (unsigned short)pvar;
     }
@@ -170,21 +170,16 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
         __syncwarp();
     }
 
-    double tau = 0.0, beta = c0, rden = 0.0;
-    bool zero_tail = false;
-    if (rem > 1)
-    {
-        if (acc2 <= DBL_MIN)
-            zero_tail = true;
-        else
-        {
-            beta = sqrt(maxval);
-            if (c0 >= 0.0) beta = -beta;
-            rden = 1.0 / (c0 - beta);
-        }
-    }
-    const double inv = 1.0 / beta;
-    if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
+    // Householder scalars (makeHouseholderInPlace), branch-free: the square root and the two reciprocals overlap
+    const bool hhon      = (rem > 1) && !(acc2 <= DBL_MIN); // a non-trivial reflector exists
+    const bool zero_tail = (rem > 1) && !hhon;
+    const double sq      = sqrt(maxval);
+    const double bb      = (c0 >= 0.0) ? -sq : sq;
+    const double beta    = hhon ? bb : c0;
+    const double inv     = 1.0 / beta;
+    const double rdn     = 1.0 / (c0 - bb);
+    const double rden    = hhon ? rdn : 0.0;
+    const double tau     = hhon ? (bb - c0) * inv : 0.0;
 
     // the finished column: beta on the diagonal, essential part of the reflector below (lexlse.h:241-242)
     {
@@ -300,7 +295,8 @@ __device__ __noinline__ int qr_level_win(const PanelArgs pa, const int fr, const
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < RH; q++) acc = fma(a[q][s], a[q][s], acc);
-        cn[s] = acc + __shfl_xor_sync(0xffffffffu, acc, 16);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        cn[s] = (pos[s] >= 0 && pos[s] < n) ? acc : -CUDART_INF; // closed: the RHS and padding slots
     }
 
     int wb = 0;
