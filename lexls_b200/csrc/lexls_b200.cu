@@ -185,11 +185,12 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.x = take(lsi ? n * 8 : 8, 8);
     m.dx = take(lsi ? n * 8 : 8, 8);
     m.lx = take(n * 8, 8);
-    m.lxo = take(n * 8, 8);
+    const bool alias_tmp = !lsi && panel_only && n <= LX_PANEL_TMP_DOUBLES && M <= LX_PANEL_TMP_DOUBLES;
+    m.lxo = alias_tmp ? 0 : take(n * 8, 8);
     m.colnorm = take(panel_only ? 8 : n * 8, 8);
     m.invd = take(n * 8, 8);
     m.hh = take((M + 1) * 8, 8);
-    m.wsp = take((2 * m0 + M + n + 2) * 8, 8);
+    m.wsp = alias_tmp ? 0 : take((2 * m0 + M + n + 2) * 8, 8);
     const unsigned vecs = lsi ? Mall + 1 : 1;
     m.v = take(vecs * 8, 8);
     m.dv = take(vecs * 8, 8);
@@ -197,15 +198,16 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.Adx = take(vecs * 8, 8);
     m.vv = take(panel_only ? 16 : ((unsigned)sh.ld + 2) * 8, 16);
     m.ptmp = take(LX_PANEL_TMP_DOUBLES * 8, 16);
-    m.active = take((Mall + 1) * 2, 4);
-    m.inactive = take((Mall + 1) * 2, 4);
+    if (alias_tmp) m.lxo = m.wsp = m.ptmp; // LexLSE: un-permute buffer (solve) and residuals (get_v) reuse the panel's staging area
+    m.active = take(lsi ? (Mall + 1) * 2 : 4, 4);
+    m.inactive = take(lsi ? (Mall + 1) * 2 : 4, 4);
     m.fidx = take((std::max(m0, (unsigned)sh.nfix) + 1) * 2, 4);
     m.colperm = take((n + 1) * 2, 4);
     m.varofcol = take((n + 1) * 2, 4);
     m.sbidx = take((m0 + 1) * 2, 4);
-    m.atype = take(Mall + 1, 4);
-    m.alltype = take(Mall + 1, 4);
-    m.ctype = take(M + 1, 4);
+    m.atype = take(lsi ? Mall + 1 : 4, 4);
+    m.alltype = take(lsi ? Mall + 1 : 4, 4);
+    m.ctype = take(lsi ? M + 1 : 4, 4);
     m.ftype = take(std::max(m0, (unsigned)sh.nfix) + 1, 4);
     m.ldim = take((G + 1) * 4, 4);
     m.frow = take((G + 1) * 4, 4);
@@ -425,8 +427,15 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     s.Mall = s.m0 + s.M;
     if (s.Mall > 60000) { delete h; return fail(LEXLS_B200_ECAPACITY, "too many constraints"); }
     if (s.off && s.G == 0) { delete h; return fail(LEXLS_B200_EINVAL, "a problem of one simple-bounds level is not supported"); }
-    s.ld   = (std::max(s.M, 2) + 1) & ~1; // even, and ld/2 odd: 128-bit row-pair accesses are conflict-free both ways
-    if (((s.ld >> 1) & 1) == 0) s.ld += 2;
+    s.ld   = (std::max(s.M, 2) + 1) & ~1; // even: every column starts 16-byte aligned (128-bit row-pair accesses)
+    {
+        // the shared-memory QR also wants ld/2 odd (lanes over columns conflict-free); the register-window LexLSE path
+        // (<= 48 columns, <= 40 rows per level) does not read LOD that way and prefers the smaller footprint
+        bool panel = kind == LEXLS_B200_LSE && nVar + 1 <= 48;
+        for (int k = 0; k < s.P; k++)
+            if (s.dim[k] > 40) panel = false;
+        if (!panel && ((s.ld >> 1) & 1) == 0) s.ld += 2;
+    }
     s.nfix = 0;
     if (kind == LEXLS_B200_LSE)
     {

@@ -845,7 +845,7 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool LG>
-__global__ void __launch_bounds__(32 * W, W == 1 ? 9 : 1) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
