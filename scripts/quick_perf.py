@@ -62,3 +62,8 @@ if __name__ == "__main__":
     if "c3" in which:
         for r in run_lsi("c3", 16384):
             print(json.dumps(r))
+    if "c4" in which:
+        for r in run_lsi("c4", 1024, reps=3, warm=False):
+            print(json.dumps(r))
+    if "c2_60" in which and False:
+        pass
