@@ -20,6 +20,9 @@ namespace lexls_dev
 {
 
 #define LX_MAX_LEVELS 16
+#ifndef LX_LSE_COMPACT_QR
+#define LX_LSE_COMPACT_QR false
+#endif
 
 enum
 {
@@ -625,7 +628,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 //   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
-template <int W, bool CQ = false> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
+template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
                                               const int nCtr, const int nFixed, const double tol, FlopCount &fl)
 {
     const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol);
@@ -717,7 +720,7 @@ template <int W, bool CQ = false> __device__ int lse_factorize(const Ctx &c, con
         {
             const int Rows = nCtr - (fr + dim);
             if constexpr (W == 1)
-                gauss_step_panel_dispatch<CQ>(pa, fr, dim, fc, rank, ColIndex);
+                gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
                 gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
@@ -905,7 +908,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
         lse_solve<W>(c, n, ld, G);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v)
