@@ -48,7 +48,13 @@ public:
         }
         release();
         lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSE, nVar, nObj, dim.data(), 0, 1, 0, &h_));
+        lexls_b200_check(lexls_b200_request_outputs(h_, LEXLS_B200_OUT_LEXQR)); // get_lexqr() is part of the surface
         applyParameters();
+        data_.resize(nCtr > 0 ? nCtr : 1, nVar + 1);
+        lexqr_.resize(nCtr > 0 ? nCtr : 1, nVar + 1);
+        hh_.resize(nCtr > 0 ? nCtr : 1);
+        ctr_type_.assign(nCtr, static_cast<uint8_t>(CTR_INACTIVE));
+        dirty_ = true;
         nVarFixedInit = 0;
         TotalRank     = 0;
         ranks.assign(nObj, 0);
@@ -59,13 +65,26 @@ public:
         parameters = p;
         if (h_) applyParameters();
     }
-    void setData(Index ObjIndex, const dMatrixConstRef &data) // lexlse.h:1522
+    void setData(Index ObjIndex, const dMatrixConstRef &data) // lexlse.h:1522 (copies: the caller's buffer may go away)
     {
         if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
         if (static_cast<Index>(data.rows()) != dim[ObjIndex] || static_cast<Index>(data.cols()) != nVar + 1)
             throw Exception("Incorrect number of equations");
-        lexls_b200_check(lexls_b200_set_data(h_, ObjIndex, detail::data_of(data), detail::ld_of(data),
-                                             static_cast<uint64_t>(detail::ld_of(data)) * (nVar + 1)));
+        for (Index c = 0; c <= nVar; c++)
+            for (Index i = 0; i < dim[ObjIndex]; i++) data_(first_row[ObjIndex] + i, c) = data(i, c);
+        dirty_ = true;
+    }
+    void setCtr(Index CtrIndex, const dRowVectorType &row, RealScalar rhs) // lexlse.h:1539
+    {
+        if (CtrIndex >= nCtr) throw Exception("CtrIndex >= nCtr");
+        for (Index c = 0; c < nVar; c++) data_(CtrIndex, c) = row(c);
+        data_(CtrIndex, nVar) = rhs;
+        dirty_ = true;
+    }
+    void setCtrType(Index ObjIndex, Index CtrIndex, ConstraintActivationType type) // lexlse.h:1548 (used by the multipliers only)
+    {
+        if (ObjIndex >= nObj || CtrIndex >= dim[ObjIndex]) throw Exception("CtrIndex >= nCtr");
+        ctr_type_[first_row[ObjIndex] + CtrIndex] = static_cast<uint8_t>(type);
     }
     void setFixedVariablesCount(Index nVarFixed_) // lexlse.h:1449
     {
@@ -91,12 +110,21 @@ public:
     }
     void factorize() // lexlse.h:117 (+ :1015: the device kernel also back-substitutes)
     {
+        if (dirty_)
+        {
+            for (Index k = 0; k < nObj; k++)
+                if (dim[k])
+                    lexls_b200_check(lexls_b200_set_data(h_, k, data_.data() + first_row[k], data_.rows(),
+                                                         static_cast<uint64_t>(data_.rows()) * (nVar + 1)));
+            dirty_ = false;
+        }
         lexls_b200_check(lexls_b200_set_fixed_variables(h_, nVarFixed, fixed_index.data(), fixed_value.data(), fixed_type.data()));
         lexls_b200_check(lexls_b200_solve_batch_sync(h_));
         lexls_b200_check(lexls_b200_get_ranks(h_, ranks.data()));
         uint32_t cnt[LEXLS_B200_NCOUNTERS];
         lexls_b200_check(lexls_b200_get_counters(h_, cnt));
         TotalRank = cnt[LEXLS_B200_CNT_TOTAL_RANK];
+        if (nCtr) lexls_b200_check(lexls_b200_get_lexqr(h_, lexqr_.data(), hh_.data()));
     }
     void solve() { lexls_b200_check(lexls_b200_get_x(h_, x.data())); } // lexlse.h:1015
     const dVectorType &get_x() const { return x; }                      // lexlse.h:1587
@@ -106,6 +134,8 @@ public:
             if (dim[k]) lexls_b200_check(lexls_b200_get_v(h_, k, v.data() + first_row[k]));
         return v;
     }
+    const dMatrixType &get_lexqr() const { return lexqr_; } // lexlse.h:1626: nCtr x (nVar+1), R / Householder vectors / L
+    const dMatrixType &get_data() const { return data_; }   // lexlse.h:1631: the constraints as they were given
     Index getDim(Index k) const { return dim[k]; }
     Index getRank(Index k) const { return ranks[k]; }
     Index getTotalRank() const { return TotalRank; }
@@ -133,7 +163,10 @@ private:
     std::vector<RealScalar> fixed_value;
     std::vector<uint8_t> fixed_type;
     ParametersLexLSE parameters;
-    dVectorType x, v;
+    dVectorType x, v, hh_;
+    dMatrixType data_, lexqr_;
+    std::vector<uint8_t> ctr_type_;
+    bool dirty_;
 };
 } // namespace internal
 } // namespace LexLS

@@ -32,7 +32,13 @@ public:
         for (Index k = 0; k < nObj; k++) types[k] = static_cast<int32_t>(ObjType_[k]);
         release();
         lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSI, nVar, nObj, dim.data(), types.data(), 1, 0, &h_));
+        // getLambda() / get_lexqr() are part of the surface: a batch of one always asks the kernel for them
+        lexls_b200_check(lexls_b200_request_outputs(h_, LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA));
         applyParameters();
+        nGeneral = 0;
+        for (Index k = 0; k < nObj; k++)
+            if (ObjType_[k] != SIMPLE_BOUNDS_OBJECTIVE) nGeneral += dim[k];
+        lexqr_.resize(nGeneral > 0 ? nGeneral : 1, nVar + 1);
         guess.assign(nObj, std::vector<uint8_t>());
         for (Index k = 0; k < nObj; k++) guess[k].assign(dim[k], 0);
         guess_dirty = false;
@@ -95,8 +101,20 @@ public:
         lexls_b200_check(lexls_b200_get_x(h_, x.data()));
         for (Index k = 0; k < nObj; k++)
             if (dim[k]) lexls_b200_check(lexls_b200_get_v(h_, k, v[k].data()));
+        if (nGeneral) lexls_b200_check(lexls_b200_get_lexqr(h_, lexqr_.data(), 0));
         return status;
     }
+    // lexlsi.h:552-605: vec_lambda[k] is ObjDim[k] x nObj, rows in the order of the problem definition
+    void getLambda(std::vector<dMatrixType> &vec_lambda)
+    {
+        vec_lambda.resize(nObj);
+        for (Index k = 0; k < nObj; k++)
+        {
+            vec_lambda[k].resize(dim[k], nObj);
+            if (dim[k]) lexls_b200_check(lexls_b200_get_lambda(h_, k, vec_lambda[k].data()));
+        }
+    }
+    const dMatrixType &get_lexqr() const { return lexqr_; } // lexlsi.h:607: the last factorization (active rows)
     const dVectorType &get_x() const { return x; }                  // lexlsi.h:508
     const dVectorType &get_v(Index ObjIndex) const { return v[ObjIndex]; } // :528
     void getConstraintViolation(Index ObjIndex, dVectorType &out) const // :542
@@ -179,6 +197,8 @@ private:
     uint32_t cnt[LEXLS_B200_NCOUNTERS];
     dVectorType x;
     std::vector<dVectorType> v;
+    Index nGeneral;
+    dMatrixType lexqr_;
 };
 } // namespace internal
 } // namespace LexLS

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LEXLS_B200_ABI_VERSION 1
+#define LEXLS_B200_ABI_VERSION 2
 
 /* error codes */
 #define LEXLS_B200_OK 0
@@ -167,6 +167,21 @@ int lexls_b200_get_counters(lexls_b200_batch_t *h, uint32_t *counters);
 int lexls_b200_get_ranks(lexls_b200_batch_t *h, uint32_t *ranks);
 /* LSE only: column_permutations of factorize(), lexlse.h:222 -> [batch][nVar]; entries >= TotalRank are 0 */
 int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm);
+
+/* ---- optional outputs: requested BEFORE the solve, written by the solve kernel ------------------
+ * request_outputs: mask of LEXLS_B200_OUT_*; 0 switches them off again.
+ * get_lexqr: get_lexqr lexlse.h:1626 / lexlsi.h:607 — the factorized work matrix of the (last) factorization
+ *            -> lexqr [batch][(nVar+1) x M] column-major with leading dimension M = rows of all general levels (LSI: the
+ *            active rows in working-set order, zero rows below), hh [batch][M] Householder scalars (may be NULL).
+ * get_lambda: getLambda lexlsi.h:552-605 — Lagrange multipliers of every objective for the constraints of `level`
+ *            -> [batch][nObj][ObjDim[level]] (per problem the reference's ObjDim x nObj column-major matrix); rows of
+ *            inactive constraints are zero.  As in the reference, a problem that did not end PROBLEM_SOLVED is
+ *            re-factorized with its final working set first. */
+#define LEXLS_B200_OUT_LEXQR 1u
+#define LEXLS_B200_OUT_LAMBDA 2u
+int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask);
+int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh);
+int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda);
 
 /* device views of the result buffers (valid until destroy; contents valid after the solve completes on the stream):
  * x [batch][nVar]; status [batch]; counters [batch][NCOUNTERS] */

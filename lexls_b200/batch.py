@@ -116,6 +116,18 @@ class _Batch:
         check(lib().lexls_b200_get_ranks(self._h, r.ctypes.data_as(C.POINTER(C.c_uint32))))
         return r
 
+    def request_outputs(self, lexqr=False, multipliers=False):
+        """Optional outputs written by the next solves: the factorized work matrix (get_lexqr) / LexLSI multipliers."""
+        check(lib().lexls_b200_request_outputs(self._h, (capi.OUT_LEXQR if lexqr else 0) | (capi.OUT_LAMBDA if multipliers else 0)))
+
+    def get_lexqr(self):
+        """(lexqr [B, nVar+1, M] — i.e. per problem column-major M x (nVar+1) —, hh [B, M])."""
+        M = sum(d for k, d in enumerate(self.ObjDim) if not (self.ObjType and self.ObjType[k] == 1))
+        q = np.empty((self.batch, self.nVar + 1, M))
+        hh = np.empty((self.batch, M))
+        check(lib().lexls_b200_get_lexqr(self._h, q.ctypes.data_as(C.POINTER(C.c_double)), hh.ctypes.data_as(C.POINTER(C.c_double))))
+        return q, hh
+
     def device_results(self):
         x, s, c = C.POINTER(C.c_double)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_uint32)()
         check(lib().lexls_b200_device_results(self._h, C.byref(x), C.byref(s), C.byref(c)))
@@ -219,6 +231,13 @@ class LexLSIBatch(_Batch):
         t = np.empty((self.batch, self.ObjDim[level]), dtype=np.uint8)
         check(lib().lexls_b200_get_active_set(self._h, C.c_uint32(level), t.ctypes.data_as(C.POINTER(C.c_uint8))))
         return t
+
+    def getLambda(self, level):
+        """Multipliers of every objective for the constraints of `level` (getLambda, lexlsi.h:552-605): [B, nObj, m]
+        (per problem the reference's m x nObj column-major matrix).  Needs request_outputs(multipliers=True)."""
+        lam = np.empty((self.batch, self.nObj, self.ObjDim[level]))
+        check(lib().lexls_b200_get_lambda(self._h, C.c_uint32(level), _dp(lam)))
+        return lam
 
     def getActiveCtr_order(self, level):
         o = np.empty((self.batch, self.ObjDim[level]), dtype=np.uint32)

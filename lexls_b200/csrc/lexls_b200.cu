@@ -61,6 +61,8 @@ struct lexls_b200_batch
     double *x = nullptr, *v = nullptr, *viol = nullptr, *lod_scratch = nullptr;
     unsigned char *act = nullptr;
     unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
+    double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
+    unsigned want = 0;
     int *status = nullptr, *flag = nullptr;
     unsigned long long *queue = nullptr;
     uint64_t lod_stride = 0;
@@ -508,7 +510,8 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
-                    h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage};
+                    h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
+                    h->lexqr, h->hhout, h->lambda};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -846,6 +849,9 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.counters     = h->counters;
     b.ranks        = h->ranks;
     b.colperm      = (h->kind == LEXLS_B200_LSE) ? h->colperm : nullptr;
+    b.lexqr        = (h->want & LEXLS_B200_OUT_LEXQR) ? h->lexqr : nullptr;
+    b.hhout        = h->hhout;
+    b.lambda       = (h->want & LEXLS_B200_OUT_LAMBDA) ? h->lambda : nullptr;
     b.queue        = h->queue;
     b.batch        = h->batch;
     b.lod_scratch  = h->lod_scratch;
@@ -946,6 +952,50 @@ int lexls_b200_get_ranks(lexls_b200_batch_t *h, uint32_t *ranks)
 {
     if (!h || !ranks) return fail(LEXLS_B200_EINVAL, "NULL argument");
     return d2h(h, ranks, h->ranks, sizeof(unsigned) * h->sh.G * h->batch);
+}
+int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (mask & ~(uint32_t)(LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA)) return fail(LEXLS_B200_EINVAL, "unknown output bit");
+    if ((mask & LEXLS_B200_OUT_LAMBDA) && h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "Lagrange multipliers exist for LexLSI only");
+    CK(cudaSetDevice(h->device));
+    const Shape &s = h->sh;
+    const int M    = std::max(s.M, 1);
+    if ((mask & LEXLS_B200_OUT_LEXQR) && !h->lexqr)
+    {
+        CK(cudaMalloc(&h->lexqr, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(cudaMalloc(&h->hhout, sizeof(double) * (size_t)M * h->batch));
+    }
+    if ((mask & LEXLS_B200_OUT_LAMBDA) && !h->lambda)
+        CK(cudaMalloc(&h->lambda, sizeof(double) * (size_t)s.P * std::max(s.Mall, 1) * h->batch));
+    h->want = mask;
+    return 0;
+}
+int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh)
+{
+    if (!h || !lexqr) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (!(h->want & LEXLS_B200_OUT_LEXQR)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_LEXQR before the solve");
+    const Shape &s = h->sh;
+    if (int rc = d2h(h, lexqr, h->lexqr, sizeof(double) * (size_t)s.M * (s.n + 1) * h->batch)) return rc;
+    if (hh) return d2h(h, hh, h->hhout, sizeof(double) * (size_t)s.M * h->batch);
+    return 0;
+}
+int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
+{
+    if (!h || !lambda) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (!(h->want & LEXLS_B200_OUT_LAMBDA)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_LAMBDA before the solve");
+    const Shape &s = h->sh;
+    if ((int)level >= s.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    const int m = s.dim[level];
+    if (m == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const unsigned long long cols = (unsigned long long)h->batch * s.P; // one slice per (problem, objective column)
+    const size_t bytes            = sizeof(double) * m * cols;
+    if (int rc = ensure_stage(h, bytes)) return rc;
+    slice_level_kernel<double><<<blocks_for((unsigned long long)m * cols), 256, 0, h->stream>>>((double *)h->stage, h->lambda, s.Mall,
+                                                                                               s.uoff[level], m, cols);
+    CK(cudaGetLastError());
+    return d2h(h, lambda, h->stage, bytes);
 }
 int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
 {

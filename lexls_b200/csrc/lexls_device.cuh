@@ -110,6 +110,9 @@ struct Buffers
     unsigned *counters;        // [B][8]
     unsigned *ranks;           // [B][G]
     unsigned *colperm;         // [B][n] or null (debug)
+    double *lexqr;             // [B][(n+1) x M] factorized work matrix (column-major, ld = M) or null   (get_lexqr)
+    double *hhout;             // [B][M] Householder scalars, with lexqr
+    double *lambda;            // LSI: [B][P][Mall] Lagrange multipliers (getLambda, lexlsi.h:552-605) or null
     unsigned long long *queue; // work counter
     unsigned long long batch;
     double *lod_scratch;       // "LOD in global memory" variants: [grid][lod_stride] work matrices (L2 resident)
@@ -844,6 +847,20 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
     gsync<W>();
 }
 
+// get_lexqr (lexlse.h:1626): the factorized work matrix and the Householder scalars of problem p go to global memory
+template <int NT>
+__device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, const unsigned long long p, const int n, const int ld,
+                                           const int nCtr, const int M)
+{
+    double *dst = bf.lexqr + p * (unsigned long long)M * (n + 1);
+    for (int e = threadIdx.x; e < M * (n + 1); e += NT)
+    {
+        const int r = e % M, col = e / M;
+        dst[e]      = (r < nCtr) ? c.LOD[r + ld * col] : 0.0;
+    }
+    for (int k = threadIdx.x; k < M; k += NT) bf.hhout[p * M + k] = (k < nCtr) ? c.hh[k] : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
@@ -919,6 +936,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
         for (int g = tid; g < G; g += NT) bf.ranks[p * G + g] = c.rank[g];
         if (bf.colperm)
             for (int k = tid; k < n; k += NT) bf.colperm[p * n + k] = (k < totalRank) ? c.colperm[k] : 0u;
+        if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
         if (tid == 0)
         {
             bf.status[p]    = ST_SOLVED;
@@ -1607,6 +1625,40 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
             {
                 status = ST_MAX_FACT;
                 break;
+            }
+        }
+
+        // ---- optional outputs: get_lexqr (the last factorization) and getLambda, lexlsi.h:552-605 ------------------
+        if (bf.lexqr)
+        {
+            int nc = 0;
+            for (int g = 0; g < G; g++) nc += c.ldim[g];
+            dump_lexqr<NT>(c, bf, p, n, ld, nc, sh.M);
+            gsync<W>();
+        }
+        if (bf.lambda)
+        {
+            double *lam = bf.lambda + p * (unsigned long long)P * sh.Mall;
+            for (int e = tid; e < P * sh.Mall; e += NT) lam[e] = 0.0;
+            if (status != ST_SOLVED) factor_and_solve(); // lexlsi.h:566-571 (the working set changed after the last one)
+            gsync<W>();
+            for (int j = 0; j < G; j++)
+            {
+                if (tid < 32)
+                {
+                    int ctr2rem = 0, obj2rem = 0;
+                    lse_sensitivity(c, n, ld, j, nFixed, pr.tol_wrong, pr.tol_correct, ctr2rem, obj2rem, lane);
+                }
+                gsync<W>();
+                // workspace = [Lambda of the fixed variables | Lambda of LexLSE rows 0 .. frow[j] + ldim[j])
+                double *col = lam + (unsigned long long)(sh.off + j) * sh.Mall;
+                for (int a = tid; a < nFixed; a += NT) col[c.active[a]] = c.wsp[a];
+                for (int g = 0; g <= j; g++)
+                {
+                    const int o = sh.uoff[g + sh.off], fr = c.frow[g];
+                    for (int a = tid; a < c.ldim[g]; a += NT) col[o + c.active[o + a]] = c.wsp[nFixed + fr + a];
+                }
+                gsync<W>();
             }
         }
 

@@ -33,6 +33,20 @@ int main()
         std::vector<ConstraintActivationType> t;
         lsi.getActiveCtr(n, t);
         if (t[0] != CTR_ACTIVE_EQ) { std::printf("FAIL active type\n"); return 1; }
+        // multipliers of the last objective (sum(x) = 1): lambda_test.m — objective k < n carries
+        // -(1 - sum_j 1/j) / k in column n, the last objective's own entry is its residual sum_j 1/j - 1
+        {
+            std::vector<dMatrixType> lam;
+            lsi.getLambda(lam);
+            double hsum = 0.0;
+            for (Index k = 1; k <= n; k++) hsum += 1.0 / k;
+            const double r = hsum - 1.0;
+            if (lam.size() != n + 1 || lam[0].rows() != 1 || lam[0].cols() != n + 1) { std::printf("FAIL lambda shape\n"); return 1; }
+            if (std::fabs(lam[n](0, n) - r) > 1e-12) { std::printf("FAIL lambda own %g vs %g\n", lam[n](0, n), r); return 1; }
+            for (Index k = 0; k < n; k++)
+                if (std::fabs(std::fabs(lam[k](0, n)) - r / (k + 1)) > 1e-12) { std::printf("FAIL lambda[%u] %g\n", k, lam[k](0, n)); return 1; }
+            if (lsi.get_lexqr().rows() != n + 1 || lsi.get_lexqr().cols() != n + 1) { std::printf("FAIL lexqr shape\n"); return 1; }
+        }
 
         // LexLSE: x1 + x2 + x3 = 3 ; I x = 0  ->  minimum-norm solution (1,1,1); with x3 fixed to 2: (0.5, 0.5, 2)
         Index d2[2] = {1, 3};
@@ -48,6 +62,25 @@ int main()
         for (Index k = 0; k < 3; k++)
             if (std::fabs(lse.get_x()(k) - 1.0) > 1e-12) { std::printf("FAIL lse x\n"); return 1; }
         if (lse.getRank(0) != 1 || lse.getRank(1) != 2 || lse.getTotalRank() != 3) { std::printf("FAIL ranks\n"); return 1; }
+        // get_data() returns the constraints as given, get_lexqr() the factorization: a one-row level needs no reflector,
+        // so its R row is the row itself; level 2 (I x = 0 after eliminating x1) has |R(1,1)| = ||(-1, 1, 0)|| = sqrt(2)
+        if (lse.get_data()(0, 3) != 3.0 || lse.get_data()(3, 2) != 1.0) { std::printf("FAIL get_data\n"); return 1; }
+        if (lse.get_lexqr()(0, 0) != 1.0 || lse.get_lexqr()(0, 3) != 3.0 ||
+            std::fabs(std::fabs(lse.get_lexqr()(1, 1)) - std::sqrt(2.0)) > 1e-12)
+        {
+            std::printf("FAIL get_lexqr %g %g %g\n", lse.get_lexqr()(0, 0), lse.get_lexqr()(0, 3), lse.get_lexqr()(1, 1));
+            return 1;
+        }
+        // setCtr: replace the first equation by 2 x1 = 2 -> x = (1, 0, 0)
+        {
+            dRowVectorType row(3);
+            row(0) = 2.0; row(1) = 0.0; row(2) = 0.0;
+            lse.setCtr(0, row, 2.0);
+            lse.setCtrType(0, 0, CTR_ACTIVE_EQ);
+            lse.factorize();
+            lse.solve();
+            if (std::fabs(lse.get_x()(0) - 1.0) > 1e-12 || std::fabs(lse.get_x()(1)) > 1e-12) { std::printf("FAIL setCtr\n"); return 1; }
+        }
         lse.setObjDim(d2);
         lse.setFixedVariablesCount(1);
         lse.fixVariable(2, 2.0);

@@ -126,3 +126,21 @@ def test_solution_is_lexicographic_least_squares():
         r_gpu = np.linalg.norm(A1 @ x[p] - b1)
         r_opt = np.linalg.norm(A1 @ np.linalg.lstsq(A1, b1, rcond=None)[0] - b1)
         assert abs(r_gpu - r_opt) <= 1e-8 * max(1.0, r_opt)
+
+
+def test_get_lexqr_matches_the_oracle_factorization(oracle):
+    """get_lexqr (lexlse.h:1626): R, the Householder vectors, the eliminated blocks and the scalars — bit for bit."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    for name, batch in (("tiny_lse", None), ("c2", 128)):
+        w = problems.workload(name, batch)
+        data, _ = problems.generate(w)
+        ref = oracle.lse_solve_batch(w.nVar, w.ObjDim, data, threads=0, want_factors=True)
+        with lx.LexLSEBatch(w.nVar, w.ObjDim, batch=w.batch) as s:
+            s.request_outputs(lexqr=True)
+            for k, d in enumerate(data):
+                s.setData(k, d)
+            s.solve()
+            q, hh = s.get_lexqr()
+        assert np.array_equal(q, ref["lexqr"]), "factorized work matrix differs"
+        assert np.array_equal(hh, ref["hh"]), "Householder scalars differ"

@@ -170,3 +170,38 @@ def test_invalid_inputs_are_rejected():
         with pytest.raises(lx.LexLSError) as e:
             s.setParameters(lx.Params(regularization_type=1))
         assert e.value.code == 3
+
+
+@pytest.mark.parametrize("name,count,cap", [("tiny_lsi", 12, None), ("c3", 6, None), ("c3", 4, 3)])
+def test_get_lambda_matches_the_oracle(oracle, name, count, cap):
+    """getLambda (lexlsi.h:552-605): per-level multiplier matrices, also for problems stopped by the factorization cap
+    (the reference re-factorizes the final working set first)."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload(name, count)
+    data, vi = problems.generate(w)
+    par = dict(max_number_of_factorizations=cap) if cap else {}
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        if par:
+            s.setParameters(lx.Params(**par))
+        s.request_outputs(multipliers=True, lexqr=True)
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        lam = [s.getLambda(k) for k in range(len(w.ObjDim))]
+        status = s.get_status()
+        x = s.get_x()
+    nz = 0
+    for p in range(w.batch):
+        one = [d[p] for d in data]
+        r = oracle.lsi_solve_detail(w.nVar, w.ObjDim, w.ObjType, one, var_index=vi,
+                                    params=oracle.OracleParams(**par) if par else None)
+        assert r["status"] == status[p]
+        assert np.array_equal(r["x"], x[p])
+        for k in range(len(w.ObjDim)):
+            # oracle: [m_k, nObj]; device: [nObj, m_k]
+            assert np.array_equal(lam[k][p].T, r["lambdas"][k]), (p, k)
+            nz += int(np.count_nonzero(lam[k][p]))
+    assert nz > 0
+    if cap:
+        assert (status == 2).any()
