@@ -960,7 +960,7 @@ __device__ __forceinline__ void ws_activate(const Ctx &c, const Shape &sh, int k
 {
     const int o = sh.uoff[k];
     int ni      = c.ninact[k];
-    int q       = 0;
+    int q       = (i < ni && c.inactive[o + i] == i) ? i : 0; // usual case while the initial working set is built
     while (q < ni && c.inactive[o + q] != i) q++;
     c.inactive[o + q] = c.inactive[o + ni - 1];
     c.ninact[k]       = ni - 1;
@@ -1016,7 +1016,16 @@ __device__ __forceinline__ void obj_multiply(const Ctx &c, const Shape &sh, cons
     for (int r = tid; r < sh.M; r += NT)
     {
         double acc = 0.0;
-        for (int col = 0; col < sh.n; col++) acc = fma(ov.A(r, col), vec[col], acc);
+        int col    = 0;
+        for (; col + 8 <= sh.n; col += 8) // loads first (L2 latency), then the sequential chain (S)
+        {
+            double t8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t8[u] = ov.A(r, col + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fma(t8[u], vec[col + u], acc);
+        }
+        for (; col < sh.n; col++) acc = fma(ov.A(r, col), vec[col], acc);
         out[sh.m0 + r] = acc;
     }
 }
@@ -1088,7 +1097,16 @@ __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, co
             const int i = c.active[o + a], t = c.atype[o + a];
             c.ctype[fr + a] = (unsigned char)t;
             double *dst     = c.LOD + fr + a;
-            for (int col = 0; col < n; col++) dst[ld * col] = ov.A(go + i, col);
+            int col         = 0;
+            for (; col + 8 <= n; col += 8) // eight loads in flight (the objective record may live in L2)
+            {
+                double t8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) t8[u] = ov.A(go + i, col + u);
+#pragma unroll
+                for (int u = 0; u < 8; u++) dst[ld * (col + u)] = t8[u];
+            }
+            for (; col < n; col++) dst[ld * col] = ov.A(go + i, col);
             dst[ld * n] = (t == CTR_ACTIVE_LB) ? ov.A(go + i, n) : ov.A(go + i, n + 1);
         }
     }
@@ -1305,7 +1323,16 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                         // don't activate 0*x = b rows, lexlsi.h:377
                         const int r = sh.goff[k - sh.off] + i;
                         double s    = 0.0;
-                        for (int col = 0; col < n; col++) s = fma(ov.A(r, col), ov.A(r, col), s);
+                        int col     = 0;
+                        for (; col + 8 <= n; col += 8)
+                        {
+                            double t8[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) t8[u] = ov.A(r, col + u);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) s = fma(t8[u], t8[u], s);
+                        }
+                        for (; col < n; col++) s = fma(ov.A(r, col), ov.A(r, col), s);
                         eq = s > 0;
                     }
                     eqflag[o + i] = eq;
@@ -1313,19 +1340,20 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                 }
             }
             gsync<W>();
-            if (tid == 0)
+            if (tid < P)
             {
-                for (int k = 0; k < P; k++)
-                    for (int i = 0; i < sh.dim[k]; i++)
-                        if (eqflag[sh.uoff[k] + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
+                // the working sets of different levels do not interact: one thread per level replays its level's part
+                // of the reference's sequence (all equalities, then the guess)
+                const int k = tid;
+                for (int i = 0; i < sh.dim[k]; i++)
+                    if (eqflag[sh.uoff[k] + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
                 if (bf.guess)
-                    for (int k = 0; k < P; k++)
-                        for (int i = 0; i < sh.dim[k]; i++)
-                        {
-                            const int t = gs[sh.uoff[k] + i];
-                            if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[sh.uoff[k] + i] == CTR_INACTIVE)
-                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
-                        }
+                    for (int i = 0; i < sh.dim[k]; i++)
+                    {
+                        const int t = gs[sh.uoff[k] + i];
+                        if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[sh.uoff[k] + i] == CTR_INACTIVE)
+                            ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
+                    }
             }
             gsync<W>();
             for (int i = tid; i < sh.Mall; i += NT) c.dv[i] = 0.0;
