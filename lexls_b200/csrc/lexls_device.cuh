@@ -701,7 +701,12 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
 
         // warp-per-problem kernels are only planned for shapes that the register-window panel covers (plan() in
         // lexls_b200.cu), so they carry no shared-memory fallback code
-        if constexpr (W == 1)
+#ifdef LX_W1_SMEM_EXPERIMENT
+        constexpr bool PANEL = (W == 1) && !CQ; // experiment: the LexLSI warp-per-problem kernel on the shared-memory routines
+#else
+        constexpr bool PANEL = (W == 1);
+#endif
+        if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
             qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
@@ -722,7 +727,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
         if (g + 1 < G && rank > 0)
         {
             const int Rows = nCtr - (fr + dim);
-            if constexpr (W == 1)
+            if constexpr (PANEL)
                 gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
                 gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
