@@ -180,7 +180,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     // LOD first: it is the target of a TMA bulk copy (LSE) -> 128-byte alignment; size rounded to 16 bytes, followed by
     // 32 bytes of zeros (the register-window Gauss step reads row pairs that may end up to 3 rows past the matrix)
     m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16) + 32, 128);
-    m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, 128);
+    m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, (lsi && DS) ? 128 : 16);
     m.sb  = take((lsi && DS) ? 2 * m0 * 8 + 16 : 16, 16);
     // x / dx: LexLSI iterates; colnorm / vv: scratch of the shared-memory QR (not needed when every level runs in the
     // register-window panel)
@@ -199,7 +199,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.Ax = take(vecs * 8, 8);
     m.Adx = take(vecs * 8, 8);
     m.vv = take(panel_only ? 16 : ((unsigned)sh.ld + 2) * 8, 16);
-    m.ptmp = take(LX_PANEL_TMP_DOUBLES * 8, 16);
+    m.ptmp = take(panel_only ? LX_PANEL_TMP_DOUBLES * 8 : 16, 16); // staging area of the register-window panel only
     if (alias_tmp) m.lxo = m.wsp = m.ptmp; // LexLSE: un-permute buffer (solve) and residuals (get_v) reuse the panel's staging area
     m.active = take(lsi ? (Mall + 1) * 2 : 4, 4);
     m.inactive = take(lsi ? (Mall + 1) * 2 : 4, 4);
