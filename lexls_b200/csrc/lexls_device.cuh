@@ -352,17 +352,18 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         // integer max over order-preserving keys (REDUX), then the smallest column index holding the maximum
         int p;
         {
-            unsigned long long key = 0;
-            int col                = 0x7fffffff;
+            double best = 0.0;
+            int col     = 0x7fffffff;
             for (int k = ColIndex + lane; k < n; k += 32)
             {
-                const unsigned long long kk = dkey(c.colnorm[k]);
-                if (col == 0x7fffffff || kk > key)
+                const double v = c.colnorm[k];
+                if (col == 0x7fffffff || v > best)
                 {
-                    key = kk;
-                    col = k;
+                    best = v;
+                    col  = k;
                 }
             }
+            const unsigned long long key = (col == 0x7fffffff) ? 0ull : dkey(best);
             const unsigned hi = (unsigned)(key >> 32);
             const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
             const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
@@ -377,12 +378,15 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         const double *colp = LOD + ld * p + fr;
         double acc2        = 0.0;
         if (lane < 8)
-            for (int i = (counter & ~3) + lane; i < dim; i += 8)
-                if (i > counter)
-                {
-                    const double a = colp[i];
-                    acc2           = fma(a, a, acc2);
-                }
+        {
+            int i = (counter & ~3) + lane;
+            if (i <= counter) i += 8; // counter - (counter & ~3) < 4: one bump reaches the first row below the pivot
+            for (; i < dim; i += 8)
+            {
+                const double a = colp[i];
+                acc2           = fma(a, a, acc2);
+            }
+        }
         acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
         acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
         acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
@@ -391,21 +395,16 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         const double maxval = fma(c0, c0, acc2);
         if (maxval < tol) break; // rank found, lexlse.h:214-217
 
-        double tau = 0.0, beta = c0, rden = 0.0;
-        bool zero_tail = false;
-        if (rem > 1)
-        {
-            if (acc2 <= DBL_MIN)
-                zero_tail = true;
-            else
-            {
-                beta = sqrt(maxval);
-                if (c0 >= 0.0) beta = -beta;
-                rden = 1.0 / (c0 - beta);
-            }
-        }
-        const double inv = 1.0 / beta; // reciprocal of the diagonal entry R(c,c): Gauss step, solve, and tau
-        if (rem > 1 && !zero_tail) tau = (beta - c0) * inv;
+        // Householder scalars (makeHouseholderInPlace), branch-free: the square root and the two reciprocals overlap
+        const bool hhon      = (rem > 1) && !(acc2 <= DBL_MIN); // a non-trivial reflector exists
+        const bool zero_tail = (rem > 1) && !hhon;
+        const double sq      = sqrt(maxval);
+        const double bb      = (c0 >= 0.0) ? -sq : sq;
+        const double beta    = hhon ? bb : c0;
+        const double inv     = 1.0 / beta; // reciprocal of the diagonal entry R(c,c): Gauss step, solve, and tau
+        const double rdn     = 1.0 / (c0 - bb);
+        const double rden    = hhon ? rdn : 0.0;
+        const double tau     = hhon ? (bb - c0) * inv : 0.0;
 
         if constexpr (W > 1) gsync<W>(); // all warps finished reading colnorm / column p
 
@@ -476,6 +475,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                 if (apply)
                 {
                     double ae = 0.0, ao = 0.0;
+#pragma unroll 2
                     for (int q = 0; q < np; q++)
                     {
                         const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
@@ -483,6 +483,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                         ao = fma(v.y, a.y, ao);
                     }
                     const double w = tau * (ae + ao);
+#pragma unroll 2
                     for (int q = 0; q < np; q++)
                     {
                         const double2 v = ld2(vp + 2 * q);
