@@ -144,3 +144,31 @@ def test_get_lexqr_matches_the_oracle_factorization(oracle):
             q, hh = s.get_lexqr()
         assert np.array_equal(q, ref["lexqr"]), "factorized work matrix differs"
         assert np.array_equal(hh, ref["hh"]), "Householder scalars differ"
+
+
+@pytest.mark.parametrize("dims,n", [([40, 7], 47), ([33, 20, 5], 30), ([4, 4], 3), ([17, 3, 29], 15), ([21, 21], 47), ([40, 40], 16),
+                                    ([2, 38, 1], 31)])
+def test_register_window_shapes(oracle, dims, n):
+    """Shapes that exercise every instance of the register-window panel (1..3 column slots, 20- and 40-row windows, windows
+    that end inside a 4-row group, more rows than columns) with rank deficiency, zero columns and exact pivot ties."""
+    rng = np.random.default_rng(5)
+    B = 48
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    data[0][: B // 3, 1, :] = data[0][: B // 3, 0, :]           # duplicated column -> equal norms -> first-maximum rule
+    data[0][B // 3: B // 2, 2, :] = 0.0                          # zero column
+    if len(dims) > 1 and dims[1] >= 2:
+        data[1][: B // 2, :, 1] = 2.0 * data[1][: B // 2, :, 0]  # dependent rows -> rank found inside the level
+    data[-1][B - 4:, :, :] = 0.0                                 # an all-zero level (rank 0)
+    wx, exact, got = _check(oracle, n, dims, data)
+    assert exact
+    assert got["info"]["warps_per_problem"] == 1
+
+
+def test_register_window_with_fixed_variables(oracle):
+    rng = np.random.default_rng(9)
+    B, n, dims = 32, 20, [9, 14, 6]
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    idx = np.tile(np.array([3, 0, 17, 8], dtype=np.uint32), (B, 1))
+    val = rng.standard_normal((B, 4))
+    wx, exact, _ = _check(oracle, n, dims, data, fixed=(idx, val))
+    assert exact
