@@ -205,3 +205,39 @@ def test_get_lambda_matches_the_oracle(oracle, name, count, cap):
     assert nz > 0
     if cap:
         assert (status == 2).any()
+
+
+def test_full_size_c3_idempotence_and_feasibility():
+    """Size-independent properties at BASELINE's full C3 size (16,384 problems, no oracle): every problem ends
+    PROBLEM_SOLVED; the top-priority simple bounds hold; re-solving from the solution (x0 = x, guess = final active set)
+    takes exactly one factorization and reproduces x and the active set."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c3")
+    data, vi = problems.generate(w)
+    nl = len(w.ObjDim)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        x, st, cnt = s.get_x(), s.get_status(), s.get_counters()
+        act = [s.getActiveCtr(k) for k in range(nl)]
+        viol0 = s.getConstraintViolation(0)
+        assert (st == 0).all()
+        assert np.abs(viol0).max() <= 1e-9
+        lb, ub = data[0][:, 0, :], data[0][:, 1, :]
+        assert (x[:, vi] >= lb - 1e-9).all() and (x[:, vi] <= ub + 1e-9).all()
+        assert cnt[:, 0].mean() > 3
+        for k in range(nl):
+            s.set_active_guess(k, act[k])
+        s.set_x0(x)
+        s.solve()
+        x2, st2, cnt2 = s.get_x(), s.get_status(), s.get_counters()
+        act2 = [s.getActiveCtr(k) for k in range(nl)]
+    assert (st2 == 0).all()
+    assert (cnt2[:, 0] == 1).all(), "a converged active set must verify in one factorization"
+    for k in range(nl):
+        assert np.array_equal(act[k], act2[k])
+    num = np.linalg.norm(x2 - x, axis=1)
+    den = np.maximum(np.linalg.norm(x, axis=1), 1e-12)
+    assert (num / den).max() <= 1e-9
