@@ -102,8 +102,25 @@ public:
         for (Index k = 0; k < nObj; k++)
             if (dim[k]) lexls_b200_check(lexls_b200_get_v(h_, k, v[k].data()));
         if (nGeneral) lexls_b200_check(lexls_b200_get_lexqr(h_, lexqr_.data(), 0));
+        working_set_log.clear();
+        if (parameters.log_working_set_enabled)
+        {
+            const uint32_t cap = parameters.max_number_of_factorizations + 1;
+            std::vector<double> e(static_cast<size_t>(cap) * 6, 0.0);
+            uint32_t count = 0;
+            lexls_b200_check(lexls_b200_get_working_set_log(h_, cap, e.data(), &count));
+            for (uint32_t i = 0; i < count && i < cap; i++)
+            {
+                WorkingSetLogEntry w(static_cast<Index>(e[6 * i]), static_cast<Index>(e[6 * i + 1]),
+                                     static_cast<ConstraintActivationType>(static_cast<int>(e[6 * i + 2])), e[6 * i + 3],
+                                     static_cast<Index>(e[6 * i + 4]));
+                w.cycling_detected = e[6 * i + 5] != 0.0;
+                working_set_log.push_back(w);
+            }
+        }
         return status;
     }
+    std::vector<WorkingSetLogEntry> &getWorkingSetLog() { return working_set_log; } // lexlsi.h:739
     // lexlsi.h:552-605: vec_lambda[k] is ObjDim[k] x nObj, rows in the order of the problem definition
     void getLambda(std::vector<dMatrixType> &vec_lambda)
     {
@@ -199,6 +216,7 @@ private:
     std::vector<dVectorType> v;
     Index nGeneral;
     dMatrixType lexqr_;
+    std::vector<WorkingSetLogEntry> working_set_log;
 };
 } // namespace internal
 } // namespace LexLS

@@ -212,6 +212,24 @@ private:
     std::string msg_;
 };
 
+// one step of the active-set method (reference typedefs.h:380-432): the constraint that was added (ctr_type = its
+// activation type, alpha_or_lambda = step length) or removed (ctr_type = CTR_INACTIVE, alpha_or_lambda = the multiplier
+// with the wrong sign), the rank of the factorization at that step and whether the cycling handler fired
+class WorkingSetLogEntry
+{
+public:
+    WorkingSetLogEntry() : obj_index(0), ctr_index(0), ctr_type(CTR_INACTIVE), alpha_or_lambda(0), rank(0), cycling_detected(false) {}
+    WorkingSetLogEntry(Index o, Index c, ConstraintActivationType t, RealScalar a, Index r)
+    : obj_index(o), ctr_index(c), ctr_type(t), alpha_or_lambda(a), rank(r), cycling_detected(false)
+    {
+    }
+    Index obj_index, ctr_index;
+    ConstraintActivationType ctr_type;
+    RealScalar alpha_or_lambda;
+    Index rank;
+    bool cycling_detected;
+};
+
 class ConstraintIdentifier
 {
 public:

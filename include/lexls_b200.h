@@ -182,6 +182,10 @@ int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
 int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask);
 int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh);
 int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda);
+/* getWorkingSetLog lexlsi.h:739 (entries typedefs.h:380-432), written when params.log_working_set_enabled != 0:
+ * entries [batch][capacity][6] = {obj_index, ctr_index, ctr_type (0 = removed), alpha_or_lambda, rank, cycling_detected};
+ * count [batch] = entries the solve produced (<= max_number_of_factorizations + 1; more than `capacity` are cut). */
+int lexls_b200_get_working_set_log(lexls_b200_batch_t *h, uint32_t capacity, double *entries, uint32_t *count);
 
 /* device views of the result buffers (valid until destroy; contents valid after the solve completes on the stream):
  * x [batch][nVar]; status [batch]; counters [batch][NCOUNTERS] */

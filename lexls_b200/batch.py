@@ -239,6 +239,14 @@ class LexLSIBatch(_Batch):
         check(lib().lexls_b200_get_lambda(self._h, C.c_uint32(level), _dp(lam)))
         return lam
 
+    def getWorkingSetLog(self, capacity=64):
+        """(entries [B, capacity, 6] = {obj, ctr, type, alpha_or_lambda, rank, cycling_detected}, count [B]); needs
+        Params(log_working_set_enabled=1) at solve time (getWorkingSetLog, lexlsi.h:739)."""
+        e = np.zeros((self.batch, capacity, 6))
+        n = np.zeros(self.batch, dtype=np.uint32)
+        check(lib().lexls_b200_get_working_set_log(self._h, C.c_uint32(capacity), _dp(e), n.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return e, n
+
     def getActiveCtr_order(self, level):
         o = np.empty((self.batch, self.ObjDim[level]), dtype=np.uint32)
         check(lib().lexls_b200_get_active_order(self._h, C.c_uint32(level), o.ctypes.data_as(C.POINTER(C.c_uint32))))

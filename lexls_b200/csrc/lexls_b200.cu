@@ -62,6 +62,9 @@ struct lexls_b200_batch
     unsigned char *act = nullptr;
     unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
+    double *wslog = nullptr;                                      // working-set log (params.log_working_set_enabled)
+    unsigned *wslog_count = nullptr;
+    unsigned wslog_cap = 0;
     unsigned want = 0;
     int *status = nullptr, *flag = nullptr;
     unsigned long long *queue = nullptr;
@@ -512,7 +515,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -853,6 +856,24 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.lexqr        = (h->want & LEXLS_B200_OUT_LEXQR) ? h->lexqr : nullptr;
     b.hhout        = h->hhout;
     b.lambda       = (h->want & LEXLS_B200_OUT_LAMBDA) ? h->lambda : nullptr;
+    if (h->kind == LEXLS_B200_LSI && h->user_params.log_working_set_enabled)
+    {
+        // at most one entry per iteration, and every iteration but the first costs a factorization
+        const unsigned cap = h->user_params.max_number_of_factorizations + 1;
+        if (!h->wslog || h->wslog_cap < cap)
+        {
+            if (h->wslog) cudaFree(h->wslog);
+            if (h->wslog_count) cudaFree(h->wslog_count);
+            h->wslog = nullptr;
+            h->wslog_count = nullptr;
+            CK(cudaMalloc(&h->wslog, sizeof(double) * 6 * (size_t)cap * h->batch));
+            CK(cudaMalloc(&h->wslog_count, sizeof(unsigned) * h->batch));
+            h->wslog_cap = cap;
+        }
+        b.wslog       = h->wslog;
+        b.wslog_count = h->wslog_count;
+        b.wslog_cap   = h->wslog_cap;
+    }
     b.queue        = h->queue;
     b.batch        = h->batch;
     b.lod_scratch  = h->lod_scratch;
@@ -997,6 +1018,19 @@ int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
                                                                                                s.uoff[level], m, cols);
     CK(cudaGetLastError());
     return d2h(h, lambda, h->stage, bytes);
+}
+int lexls_b200_get_working_set_log(lexls_b200_batch_t *h, uint32_t capacity, double *entries, uint32_t *count)
+{
+    if (!h || !entries || !count) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (!h->wslog) return fail(LEXLS_B200_EINVAL, "set log_working_set_enabled before the solve");
+    CK(cudaSetDevice(h->device));
+    if (int rc = d2h(h, count, h->wslog_count, sizeof(unsigned) * h->batch)) return rc;
+    const uint32_t take = std::min(capacity, h->wslog_cap);
+    if (take == 0) return 0;
+    CK(cudaMemcpy2DAsync(entries, sizeof(double) * 6 * capacity, h->wslog, sizeof(double) * 6 * h->wslog_cap, sizeof(double) * 6 * take,
+                         h->batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
 {

@@ -113,6 +113,9 @@ struct Buffers
     double *lexqr;             // [B][(n+1) x M] factorized work matrix (column-major, ld = M) or null   (get_lexqr)
     double *hhout;             // [B][M] Householder scalars, with lexqr
     double *lambda;            // LSI: [B][P][Mall] Lagrange multipliers (getLambda, lexlsi.h:552-605) or null
+    double *wslog;             // LSI: [B][wslog_cap][6] working-set log {obj, ctr, type, alpha_or_lambda, rank, cycling} or null
+    unsigned *wslog_count;     // LSI: [B] entries written (capped by wslog_cap)
+    unsigned wslog_cap;
     unsigned long long *queue; // work counter
     unsigned long long batch;
     double *lod_scratch;       // "LOD in global memory" variants: [grid][lod_stride] work matrices (L2 resident)
@@ -1124,7 +1127,7 @@ __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, co
 // returns true when a constraint to drop was found; obj2rem = LexLSE level (or -1 for the fixed variables)
 __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const int ld, const int j, const int nFixed,
                                                 const double tol_wrong, const double tol_correct, int &ctr2rem, int &obj2rem,
-                                                const int lane)
+                                                const int lane, double *lam2rem = nullptr)
 {
     int nLambda = 0, nRank = 0;
     for (int k = 0; k < j; k++)
@@ -1215,6 +1218,7 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
     best = bfly_argmin(best);
     __syncwarp();
     if (best.pos == 0x7fffffff) return false;
+    if (lam2rem) *lam2rem = best.v; // lambda_wrong_sign of the working-set log
     const int order = best.pos >> 16;
     ctr2rem         = best.pos & 0xffff;
     obj2rem         = (order == j + 1) ? -1 : (j - order);
@@ -1372,6 +1376,24 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
         FlopCount fl;
         fl.f = 0;
 
+        // working-set log, lexlsi.h:1187-1222 (typedefs.h:380-432): one entry per ADD / REMOVE
+        unsigned nLog  = 0;
+        auto log_entry = [&](int obj, int ctr, int type, double alpha_or_lambda) {
+            if (bf.wslog)
+            {
+                if (tid == 0 && nLog < bf.wslog_cap)
+                {
+                    double *e = bf.wslog + (p * bf.wslog_cap + nLog) * 6;
+                    e[0]      = (double)obj;
+                    e[1]      = (double)ctr;
+                    e[2]      = (double)type;
+                    e[3]      = alpha_or_lambda;
+                    e[4]      = (double)totalRank;
+                    e[5]      = 0.0;
+                }
+                nLog++;
+            }
+        };
         auto factor_and_solve = [&]() {
             lsi_factor_and_solve<W, DS>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl);
         };
@@ -1568,6 +1590,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                 idType = (bl.pos & 1) ? CTR_ACTIVE_UB : CTR_ACTIVE_LB;
                 gsync<W>();
                 if (tid == 0) ws_activate(c, sh, idObj, idCtr, idType);
+                log_entry(idObj, idCtr, idType, alpha);
                 nAct++;
                 operation = OP_ADD;
             }
@@ -1578,8 +1601,9 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                 if (tid < 32)
                 {
                     int found = 0, ctr2rem = 0, obj2rem = 0;
+                    double lam2rem = 0.0;
                     for (int j = 0; j < G; j++)
-                        if (lse_sensitivity(c, n, ld, j, nFixed, pr.tol_wrong, pr.tol_correct, ctr2rem, obj2rem, lane))
+                        if (lse_sensitivity(c, n, ld, j, nFixed, pr.tol_wrong, pr.tol_correct, ctr2rem, obj2rem, lane, &lam2rem))
                         {
                             found = 1;
                             break;
@@ -1589,6 +1613,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                         c.scal[2] = found;
                         c.scal[3] = ctr2rem;
                         c.scal[4] = obj2rem + sh.off;
+                        *(double *)(c.scal + 6) = lam2rem;
                     }
                 }
                 gsync<W>();
@@ -1597,6 +1622,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                     idObj  = c.scal[4];
                     idCtr  = c.active[sh.uoff[idObj] + c.scal[3]];
                     idType = c.atype[sh.uoff[idObj] + c.scal[3]];
+                    log_entry(idObj, idCtr, CTR_INACTIVE, *(const double *)(c.scal + 6));
                     gsync<W>();
                     if (tid == 0) ws_deactivate(c, sh, idObj, c.scal[3]);
                     nDeact++;
@@ -1640,6 +1666,8 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                                 ov.ub(cycPrevObj, cycPrevCtr) += pr.cyc_step;
                         }
                         cycCounter++;
+                        if (bf.wslog && tid == 0 && nLog >= 1 && nLog <= bf.wslog_cap)
+                            bf.wslog[(p * bf.wslog_cap + (nLog - 1)) * 6 + 5] = 1.0; // cycling_detected of this entry
                     }
                 }
                 if (!early)
@@ -1733,6 +1761,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
         }
         if (tid == 0)
         {
+            if (bf.wslog_count) bf.wslog_count[p] = nLog;
             bf.status[p]  = status;
             unsigned *cnt = bf.counters + p * 8;
             cnt[0]        = nFact;

@@ -241,3 +241,31 @@ def test_full_size_c3_idempotence_and_feasibility():
     num = np.linalg.norm(x2 - x, axis=1)
     den = np.maximum(np.linalg.norm(x, axis=1), 1e-12)
     assert (num / den).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name,count,par", [("tiny_lsi", 10, {}), ("c3", 6, {}),
+                                             ("c3", 4, dict(cycling_handling_enabled=1, cycling_max_counter=3)),
+                                             ("c3", 3, dict(max_number_of_factorizations=4))])
+def test_working_set_log_matches_the_oracle(oracle, name, count, par):
+    """getWorkingSetLog (lexlsi.h:739): the sequence of added / removed constraints with step lengths, multipliers, ranks."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload(name, count)
+    data, vi = problems.generate(w)
+    par = dict(par, log_working_set_enabled=1)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        s.setParameters(lx.Params(**par))
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        entries, n = s.getWorkingSetLog(capacity=256)
+        status = s.get_status()
+    total = 0
+    for p in range(w.batch):
+        r = oracle.lsi_solve_detail(w.nVar, w.ObjDim, w.ObjType, [d[p] for d in data], var_index=vi,
+                                    params=oracle.OracleParams(**par))
+        assert r["status"] == status[p]
+        assert n[p] == len(r["log"]), (p, n[p], len(r["log"]))
+        assert np.array_equal(entries[p, :n[p]], r["log"]), p
+        total += int(n[p])
+    assert total > 0
