@@ -140,14 +140,6 @@ __device__ __forceinline__ double bfly_sum(double a)
     return a;
 }
 
-// (T) dot of two contiguous vectors, result uniform over the warp
-__device__ __forceinline__ double tree32_dot(int count, const double *a, const double *b, int lane)
-{
-    double acc = 0.0;
-    for (int i = lane; i < count; i += 32) acc = fma(a[i], b[i], acc);
-    return bfly_sum(acc);
-}
-
 struct ArgMin
 {
     double v;
@@ -819,22 +811,52 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
 }
 
 // Q_g * y for LexLSE level g (householderSequence::applyOnTheLeft); y has ldim[g] entries; one warp, all lanes.
+// Dots in the (T) order: level row r -> slot (lane) r % 32.  Levels of up to 64 rows keep y in registers (rows lane and
+// lane + 32), so one reflector costs two loads, two FMAs, one butterfly and one broadcast.
 __device__ __forceinline__ void apply_Q(const Ctx &c, const int ld, const int g, double *y, const int lane)
 {
     const int fr = c.frow[g], fc = c.fcol[g], dim = c.ldim[g], rank = c.rank[g];
+    if (rank == 0) return;
+    if (dim <= 64)
+    {
+        const int r0 = lane, r1 = lane + 32;
+        double y0 = (r0 < dim) ? y[r0] : 0.0, y1 = (r1 < dim) ? y[r1] : 0.0;
+        for (int i = rank; i--;)
+        {
+            const double tau = c.hh[fr + i];
+            if (dim - i == 1 || tau == 0.0) continue;
+            const double *col = c.LOD + fr + ld * (fc + i);
+            const double e0 = (r0 > i && r0 < dim) ? col[r0] : 0.0;
+            const double e1 = (r1 > i && r1 < dim) ? col[r1] : 0.0;
+            double acc      = fma(e0, y0, 0.0);
+            acc             = fma(e1, y1, acc);
+            acc             = bfly_sum(acc);
+            const double yi = __shfl_sync(0xffffffffu, (i < 32) ? y0 : y1, i & 31);
+            const double w  = tau * (acc + yi);
+            y0              = fma(-e0, w, y0);
+            y1              = fma(-e1, w, y1);
+            if (r0 == i) y0 = yi - w;
+            if (r1 == i) y1 = yi - w;
+        }
+        if (r0 < dim) y[r0] = y0;
+        if (r1 < dim) y[r1] = y1;
+        __syncwarp();
+        return;
+    }
     for (int i = rank; i--;)
     {
         const int len    = dim - i;
         const double tau = c.hh[fr + i];
         if (len == 1 || tau == 0.0) continue;
-        const double *ess = c.LOD + fr + i + 1 + ld * (fc + i);
-        double *yt        = y + i + 1;
-        const double acc  = tree32_dot(len - 1, ess, yt, lane);
-        const double y0   = y[i];
-        const double w    = tau * (acc + y0);
+        const double *col = c.LOD + fr + ld * (fc + i);
+        double acc        = 0.0;
+        for (int r = i + 1 + ((lane - (i + 1)) & 31); r < dim; r += 32) acc = fma(col[r], y[r], acc);
+        acc             = bfly_sum(acc);
+        const double yi = y[i];
+        const double w  = tau * (acc + yi);
         __syncwarp();
-        if (lane == 0) y[i] = y0 - w;
-        for (int t = lane; t < len - 1; t += 32) yt[t] = fma(-ess[t], w, yt[t]);
+        if (lane == 0) y[i] = yi - w;
+        for (int r = i + 1 + lane; r < dim; r += 32) y[r] = fma(-col[r], w, y[r]);
         __syncwarp();
     }
 }

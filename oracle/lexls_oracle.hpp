@@ -22,9 +22,9 @@
 //       accumulators, one for even and one for odd absolute row indices (each sequential, fma,
 //       ascending), combined as even + odd.  Used for the initial column norms and for the dot
 //       product of a Householder application (the kernel reads rows in aligned pairs).
-//   (T) "tree32": the terms are dealt round-robin to 32 partial accumulators (term i -> slot i%32,
-//       fma, ascending i), which are then combined by an xor-butterfly of width
-//       min(32, nextpow2(count)).  Used for Householder-sequence dots on a single vector.
+//   (T) "tree32": a dot product over level rows i+1 .. dim-1 (Householder-sequence application): the
+//       term of level row r goes to slot r % 32 (fma, ascending r), the 32 slots are combined by an
+//       xor-butterfly 16, 8, 4, 2, 1.  (A warp keeps level row r in lane r % 32.)
 //   (W8) "window tree8": the squared norm of the pivot column's tail at pivot step `counter` of a
 //       level.  With wb = counter & ~3 (the base of the 4-row group holding the pivot row), the
 //       term of in-level row i > counter goes to slot (i - wb) % 8 (fma, ascending i); the 8 slots
@@ -110,19 +110,17 @@ static inline double fmad(double a, double b, double c)
     return __builtin_fma(a, b, c);
 }
 
-// (T) tree32 dot product of a[i*sa] and b[i*sb], i = 0..count-1
-static inline double tree32_dot(Index count, const double *a, long sa, const double *b, long sb)
+// (T) tree32 dot product of a[i*sa] and b[i*sb], i = 0..count-1; term i belongs to level row first + i
+static inline double tree32_dot(Index count, const double *a, long sa, const double *b, long sb, Index first)
 {
     double p[32];
     for (int l = 0; l < 32; l++) p[l] = 0.0;
-    for (Index i = 0; i < count; i++) p[i & 31] = fmad(a[(long)i * sa], b[(long)i * sb], p[i & 31]);
-    Index width = 1;
-    while (width < count && width < 32) width <<= 1;
-    for (Index off = width >> 1; off >= 1; off >>= 1)
+    for (Index i = 0; i < count; i++) p[(first + i) & 31] = fmad(a[(long)i * sa], b[(long)i * sb], p[(first + i) & 31]);
+    for (Index off = 16; off >= 1; off >>= 1)
     {
         double q[32];
-        for (Index l = 0; l < width; l++) q[l] = p[l] + p[l ^ off];
-        for (Index l = 0; l < width; l++) p[l] = q[l];
+        for (Index l = 0; l < 32; l++) q[l] = p[l] + p[l ^ off];
+        for (Index l = 0; l < 32; l++) p[l] = q[l];
     }
     return p[0];
 }
@@ -503,7 +501,7 @@ public:
             const double tau = hh_scalars[fr + i];
             if (len == 1 || tau == 0.0) continue; // 1-row block scales by (1 - tau) with tau == 0
             const double *ess = &Lc(fr + i + 1, fc + i);
-            double acc = tree32_dot(len - 1, ess, 1, y + i + 1, 1); // (T)
+            double acc = tree32_dot(len - 1, ess, 1, y + i + 1, 1, i + 1); // (T)
             double tmp = acc + y[i];
             double w   = tau * tmp;
             y[i]       = y[i] - w;
