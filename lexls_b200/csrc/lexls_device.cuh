@@ -991,8 +991,15 @@ __device__ __forceinline__ void ws_activate(const Ctx &c, const Shape &sh, int k
 {
     const int o = sh.uoff[k];
     int ni      = c.ninact[k];
-    int q       = (i < ni && c.inactive[o + i] == i) ? i : 0; // usual case while the initial working set is built
-    while (q < ni && c.inactive[o + q] != i) q++;
+    // the position is unique; the two guesses cover the sequences the initial working set produces (ascending
+    // activations with swap-with-last: an element is still at its own index, or it was the last one moved forward)
+    int q = 0;
+    if (i < ni && c.inactive[o + i] == i)
+        q = i;
+    else if (ni > 0 && c.inactive[o + ni - 1] == i)
+        q = ni - 1;
+    else
+        while (q < ni && c.inactive[o + q] != i) q++;
     c.inactive[o + q] = c.inactive[o + ni - 1];
     c.ninact[k]       = ni - 1;
     c.alltype[o + i]  = (unsigned char)type;
@@ -1164,6 +1171,9 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
     double *Lambda      = c.wsp + nFixed;
     double *rhs         = c.wsp + nFixed + nLambda;
     __syncwarp();
+    // an objective with full row rank has a zero residual: its multipliers are Q * 0 = 0 for every constraint, nothing has a
+    // wrong sign and no type is re-marked (the workspace, all zeros, is what getLambda reads)
+    if (c.rank[j] == c.ldim[j]) return false;
 
     ArgMin best;
     best.v   = 0.0;        // maxAbsValue starts at 0 (lexlse.h:618); candidates are strictly below -tol_wrong
