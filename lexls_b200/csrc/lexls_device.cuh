@@ -920,24 +920,31 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
         if (tid < 4) c.LOD[ld * (n + 1) + tid] = 0.0; // zero pad behind LOD (see build_map)
     gsync<W>();
 
+    // The record of the NEXT problem is requested (TMA bulk copy) as soon as the work matrix of the current one is dead, so
+    // the copy overlaps the output stores and the queue round trip.
+    auto fetch_and_load = [&]() {
+        if (tid == 0)
+        {
+            const unsigned long long q       = atomicAdd(bf.queue, 1ull);
+            *(unsigned long long *)c.scal = q;
+            if constexpr (!LG)
+                if (q < bf.batch)
+                {
+                    fence_proxy_async();
+                    tma_load_record(c.LOD, bf.rec + q * bf.rec_stride, (unsigned)(bf.rec_stride * sizeof(double)), c.mbar);
+                }
+        }
+    };
     unsigned parity = 0;
-    for (;;)
+    fetch_and_load();
+    gsync<W>();
+    unsigned long long p = *(unsigned long long *)c.scal;
+    while (p < bf.batch)
     {
-        if (tid == 0) *(unsigned long long *)c.scal = atomicAdd(bf.queue, 1ull);
-        gsync<W>();
-        const unsigned long long p = *(unsigned long long *)c.scal;
-        if (p >= bf.batch) break;
-
-        // stage [A|b] (already in the shared-memory layout) with one bulk copy
         if constexpr (LG)
         {
             const double *src = bf.rec + p * bf.rec_stride;
             for (unsigned long long e = tid; e < bf.rec_stride; e += NT) c.LOD[e] = src[e];
-        }
-        else if (tid == 0)
-        {
-            fence_proxy_async();
-            tma_load_record(c.LOD, bf.rec + p * bf.rec_stride, (unsigned)(bf.rec_stride * sizeof(double)), c.mbar);
         }
         for (int k = tid; k < nCtr; k += NT) c.hh[k] = 0.0;
         for (int k = tid; k < n; k += NT) c.lx[k] = 0.0;
@@ -959,15 +966,15 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
         const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
         lse_solve<W>(c, n, ld, G);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
+        if (bf.v) lse_get_v<W>(c, n, ld, G);
+        if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
+        gsync<W>(); // the work matrix is dead: every thread is done with it
+        fetch_and_load();
         if (bf.v)
-        {
-            lse_get_v<W>(c, n, ld, G);
             for (int k = tid; k < nCtr; k += NT) bf.v[p * nCtr + k] = c.wsp[k];
-        }
         for (int g = tid; g < G; g += NT) bf.ranks[p * G + g] = c.rank[g];
         if (bf.colperm)
             for (int k = tid; k < n; k += NT) bf.colperm[p * n + k] = (k < totalRank) ? c.colperm[k] : 0u;
-        if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
         if (tid == 0)
         {
             bf.status[p]    = ST_SOLVED;
@@ -979,6 +986,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
             cnt[7]                            = (unsigned)((fl.f + 500) / 1000);
         }
         gsync<W>();
+        p = *(unsigned long long *)c.scal;
     }
 }
 
