@@ -182,7 +182,13 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     const unsigned n = sh.n, M = sh.M, Mall = sh.Mall, m0 = sh.m0, G = sh.G, P = sh.P;
     // LOD first: it is the target of a TMA bulk copy (LSE) -> 128-byte alignment; size rounded to 16 bytes, followed by
     // 32 bytes of zeros (the register-window Gauss step reads row pairs that may end up to 3 rows past the matrix)
-    m.lod = take(LG ? 16 : align_up((unsigned)sh.ld * (n + 1) * 8, 16) + 32, 128);
+    // (the "work matrix in global memory" variants keep a view of the level being factorized here instead: row pairs of the
+    //  largest level + one pair of slack, leading dimension 2 * odd so that lanes over columns spread over the banks)
+    unsigned maxdim = 0;
+    for (int g = 0; g < sh.G; g++) maxdim = std::max(maxdim, (unsigned)sh.dim[g + sh.off]);
+    const unsigned vpairs = ((maxdim + 3) / 2) | 1u;
+    m.ldv = (int)(2 * vpairs);
+    m.lod = take(LG ? 2 * vpairs * (n + 1) * 8 : align_up((unsigned)sh.ld * (n + 1) * 8, 16) + 32, 128);
     m.obj = take((lsi && DS) ? align_up((unsigned)sh.ldo * (n + 2) * 8, 16) : 16, (lsi && DS) ? 128 : 16);
     m.sb  = take((lsi && DS) ? 2 * m0 * 8 + 16 : 16, 16);
     // x / dx: LexLSI iterates; colnorm / vv: scratch of the shared-memory QR (not needed when every level runs in the

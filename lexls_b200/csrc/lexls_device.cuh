@@ -83,6 +83,7 @@ struct SmemMap
     unsigned lod, obj, sb, x, dx, lx, lxo, colnorm, invd, hh, wsp, v, dv, Ax, Adx, vv, ptmp;
     unsigned active, inactive, atype, alltype, ctype, fidx, ftype, colperm, varofcol, sbidx;
     unsigned ldim, frow, fcol, rank, nact, ninact, scal, mbar, total;
+    int ldv; // leading dimension of the level view of the global-memory variants
 };
 
 struct Buffers
@@ -183,7 +184,7 @@ __device__ __forceinline__ ArgMin bfly_argmax(ArgMin a)
 // ---------------------------------------------------------------------------------------------------------------
 struct Ctx
 {
-    double *LOD, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx, *vv, *ptmp;
+    double *LOD, *LVIEW, *obj, *sb, *x, *dx, *lx, *lxo, *colnorm, *invd, *hh, *wsp, *v, *dv, *Ax, *Adx, *vv, *ptmp;
     unsigned short *active, *inactive, *fidx, *colperm, *varofcol, *sbidx;
     unsigned char *atype, *alltype, *ctype, *ftype;
     int *ldim, *frow, *fcol, *rank, *nact, *ninact, *scal;
@@ -194,6 +195,7 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char *base, const SmemMap &m)
 {
     Ctx c;
     c.LOD      = (double *)(base + m.lod);
+    c.LVIEW    = c.LOD; // the global-memory variants re-point LOD; this stays the shared-memory level view
     c.obj      = (double *)(base + m.obj);
     c.sb       = (double *)(base + m.sb);
     c.x        = (double *)(base + m.x);
@@ -321,18 +323,42 @@ namespace lexls_dev
 // ---------------------------------------------------------------------------------------------------------------
 // column-pivoted Householder QR of one level in shared memory, lexlse.h:182-272 (any shape, W warps)
 // ---------------------------------------------------------------------------------------------------------------
-template <int W>
+// LGV (the "work matrix in global memory" kernels): the rows of the level being factorized — the aligned row pairs
+// [fr & ~1, fr + dim rounded up) of columns ColIndex .. n — are staged in a shared-memory view `lv` (leading dimension ldv)
+// for the duration of the level, so that only the column swaps of the other rows go to global memory (L2).
+template <int W, bool LGV>
 __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const int ld, const int fr, const int dim, int &ColIndex,
-                                              const double tol)
+                                              const double tol, double *const lv = nullptr, const int ldv = 0)
 {
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
     double *const LOD = c.LOD;
     const int hp      = ld >> 1; // row pairs per column
+    const int vt0 = fr >> 1, vt1 = (fr + dim + 1) >> 1; // row pairs of the level
+    // pair t of column col / element of level row r
+    auto P = [&](int col, int t) -> double * {
+        if (LGV && t >= vt0 && t < vt1) return lv + ldv * col + 2 * (t - vt0);
+        return LOD + ld * col + 2 * t;
+    };
+    auto E = [&](int col, int r) -> double * {
+        if (LGV) return lv + ldv * col + (r - 2 * vt0);
+        return LOD + ld * col + r;
+    };
+    const int fc0 = ColIndex;
+    if constexpr (LGV)
+    {
+        const int npv = vt1 - vt0, ncv = n + 1 - fc0;
+        for (int e = tid; e < npv * ncv; e += NT)
+        {
+            const int t = e % npv, col = fc0 + e / npv;
+            st2(lv + ldv * col + 2 * t, ld2(LOD + ld * col + 2 * (vt0 + t)));
+        }
+        gsync<W>();
+    }
     // initial squared column norms over this level's rows, lexlse.h:193-196   (S2)
     for (int k = ColIndex + tid; k < n; k += NT)
     {
-        const double *col = LOD + ld * k;
+        const double *col = E(k, 0);
         double acc[2]     = {0.0, 0.0};
         for (int r = fr; r < fr + dim; r++) acc[r & 1] = fma(col[r], col[r], acc[r & 1]);
         c.colnorm[k] = acc[0] + acc[1];
@@ -370,7 +396,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
 
         // ||tail||^2 by (W8): row i > counter -> slot (i - wb) % 8 with wb = counter & ~3, butterfly 4, 2, 1;
         // ||col||^2 = c0^2 + ||tail||^2 (lexlse.h:210 and makeHouseholderInPlace)
-        const double *colp = LOD + ld * p + fr;
+        const double *colp = E(p, fr);
         double acc2        = 0.0;
         if (lane < 8)
         {
@@ -423,8 +449,9 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         const int pb = row >> 1, pe = (row + rem + 1) >> 1; // pairs touched by the reflector
         for (int t = tid; t < hp; t += NT)
         {
-            double2 a = ld2(LOD + ld * p + 2 * t);
-            if (p != ColIndex) st2(LOD + ld * p + 2 * t, ld2(LOD + ld * ColIndex + 2 * t));
+            double *const pp = P(p, t), *const pc = P(ColIndex, t);
+            double2 a        = ld2(pp);
+            if (p != ColIndex) st2(pp, ld2(pc));
             if (rem > 1 && t >= pb && t < pe)
             {
                 const int r0 = 2 * t, r1 = r0 + 1;
@@ -455,7 +482,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                     v.y = 0.0;
                 st2(c.vv + 2 * t, v);
             }
-            st2(LOD + ld * ColIndex + 2 * t, a);
+            st2(pc, a);
         }
         gsync<W>();
 
@@ -466,7 +493,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const int np      = pe - pb;
             for (int j = ColIndex + 1 + tid; j <= n; j += NT)
             {
-                double *cp = LOD + ld * j + 2 * pb;
+                double *cp = P(j, pb);
                 if (apply)
                 {
                     double ae = 0.0, ao = 0.0;
@@ -490,7 +517,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                 }
                 if (j < n)
                 {
-                    const double a0 = LOD[ld * j + row];
+                    const double a0 = *E(j, row);
                     c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
                 }
             }
@@ -498,6 +525,18 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         ColIndex++;
         gsync<W>();
         if (ColIndex == n) break; // lexlse.h:255-258
+    }
+    if constexpr (LGV)
+    {
+        // the level's rows (R, the reflectors, the not eliminated rest) go back to the work matrix
+        gsync<W>();
+        const int npv = vt1 - vt0, ncv = n + 1 - fc0;
+        for (int e = tid; e < npv * ncv; e += NT)
+        {
+            const int t = e % npv, col = fc0 + e / npv;
+            st2(LOD + ld * col + 2 * (vt0 + t), ld2(lv + ldv * col + 2 * t));
+        }
+        gsync<W>();
     }
 }
 
@@ -705,7 +744,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
         if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
-            qr_level_smem<W>(c, n, ld, fr, dim, ColIndex, tol);
+            qr_level_smem<W, (W == 16)>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
