@@ -545,11 +545,15 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
 // ---------------------------------------------------------------------------------------------------------------
 template <int W>
 __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const int ld, const int nCtr, const int fr, const int dim,
-                                                const int fc, const int rank, const int ColIndex)
+                                                const int fc, const int rank, const int ColIndex, const int ldv = 0)
 {
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x;
     double *const LOD = c.LOD;
+    // R(k, col) / Up(k, col) = RB[k + rl * col].  Global-memory variants (W == 16): the level's rows are still in the
+    // shared-memory view that qr_level_smem staged (columns >= fc), so only the lower rows stream from global memory.
+    const double *const RB = (W == 16) ? c.LVIEW + (fr - 2 * (fr >> 1)) : LOD + fr;
+    const int rl           = (W == 16) ? ldv : ld;
     const int frn = fr + dim, Rows = nCtr - frn;
     const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
     // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
@@ -571,11 +575,11 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
             for (int k = 0; k < cb; k++)
             {
                 const double2 x  = ld2(rp + ld * (fc + k));
-                const double *Rk = LOD + fr + k;
+                const double *Rk = RB + k;
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                 {
-                    const double rr = Rk[ld * col[q]];
+                    const double rr = Rk[rl * col[q]];
                     acc[q].x        = fma(-x.x, rr, acc[q].x);
                     acc[q].y        = fma(-x.y, rr, acc[q].y);
                 }
@@ -588,7 +592,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 #pragma unroll
                     for (int q2 = 0; q2 < q; q2++)
                     {
-                        const double rr = LOD[fr + cb + q2 + ld * col[q]];
+                        const double rr = RB[cb + q2 + rl * col[q]];
                         acc[q].x        = fma(-acc[q2].x, rr, acc[q].x);
                         acc[q].y        = fma(-acc[q2].y, rr, acc[q].y);
                     }
@@ -629,11 +633,11 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
             for (int k = 0; k < rank; k++)
             {
                 const double2 l  = ld2(rp + ld * (fc + k));
-                const double *up = LOD + fr + k;
+                const double *up = RB + k;
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                 {
-                    const double u = up[ld * col[q]];
+                    const double u = up[rl * col[q]];
                     acc[q].x       = fma(-l.x, u, acc[q].x);
                     acc[q].y       = fma(-l.y, u, acc[q].y);
                 }
@@ -765,7 +769,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
             if constexpr (PANEL)
                 gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
-                gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex);
+                gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
         }
 
@@ -784,27 +788,44 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
 // ---------------------------------------------------------------------------------------------------------------
 // back-substitution, lexlse.h:1015-1045; result (already un-permuted, x = P*x) in c.lx and c.lxo
 // ---------------------------------------------------------------------------------------------------------------
-template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int ld, const int G)
+template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int ld, const int G, const int ldv = 0)
 {
-    constexpr int NT = 32 * W;
+    constexpr int NT  = 32 * W;
+    constexpr bool LGV = (W == 16); // work matrix in global memory: each level's R rows are staged in the shared-memory view
     const int tid = threadIdx.x, lane = tid & 31;
     const double *LOD = c.LOD;
-    if (tid < 32)
+    int accr = 0;
+    for (int g = G; g--;)
     {
-        int accr = 0;
-        for (int g = G; g--;)
+        const int r = c.rank[g];
+        if (r == 0) continue;
+        const int fr = c.frow[g], fc = c.fcol[g];
+        const int fc1 = (accr > 0) ? c.fcol[g + 1] : 0;
+        // element (i, col) of the level's first r rows = B[ro + i + lb * col]
+        const double *B = LOD;
+        int lb = ld, ro = fr;
+        if constexpr (LGV)
         {
-            const int r = c.rank[g];
-            if (r == 0) continue;
-            const int fr = c.frow[g], fc = c.fcol[g];
-            const int fc1 = (accr > 0) ? c.fcol[g + 1] : 0;
+            const int ncv = n + 1 - fc;
+            for (int e = tid; e < r * ncv; e += NT)
+            {
+                const int i = e % r, col = fc + e / r;
+                c.LVIEW[i + ldv * col] = LOD[fr + i + ld * col];
+            }
+            gsync<W>();
+            B  = c.LVIEW;
+            lb = ldv;
+            ro = 0;
+        }
+        if (tid < 32)
+        {
             if (r <= 32)
             {
                 double xi = 0.0, inv = 0.0;
                 if (lane < r)
                 {
-                    double acc = LOD[fr + lane + ld * n];
-                    for (int j = 0; j < accr; j++) acc = fma(-LOD[fr + lane + ld * (fc1 + j)], c.lx[fc1 + j], acc);
+                    double acc = B[ro + lane + lb * n];
+                    for (int j = 0; j < accr; j++) acc = fma(-B[ro + lane + lb * (fc1 + j)], c.lx[fc1 + j], acc);
                     xi  = acc;
                     inv = c.invd[fc + lane];
                 }
@@ -815,7 +836,7 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
                     if (lane == j)
                         xi = xj;
                     else if (lane < j)
-                        xi = fma(-LOD[fr + lane + ld * (fc + j)], xj, xi);
+                        xi = fma(-B[ro + lane + lb * (fc + j)], xj, xi);
                 }
                 if (lane < r) c.lx[fc + lane] = xi;
             }
@@ -823,8 +844,8 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
             {
                 for (int i = lane; i < r; i += 32)
                 {
-                    double acc = LOD[fr + i + ld * n];
-                    for (int j = 0; j < accr; j++) acc = fma(-LOD[fr + i + ld * (fc1 + j)], c.lx[fc1 + j], acc);
+                    double acc = B[ro + i + lb * n];
+                    for (int j = 0; j < accr; j++) acc = fma(-B[ro + i + lb * (fc1 + j)], c.lx[fc1 + j], acc);
                     c.lx[fc + i] = acc;
                 }
                 __syncwarp();
@@ -833,13 +854,14 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
                     const double xj = c.lx[fc + j] * c.invd[fc + j];
                     __syncwarp();
                     if (lane == 0) c.lx[fc + j] = xj;
-                    for (int i = lane; i < j; i += 32) c.lx[fc + i] = fma(-LOD[fr + i + ld * (fc + j)], xj, c.lx[fc + i]);
+                    for (int i = lane; i < j; i += 32) c.lx[fc + i] = fma(-B[ro + i + lb * (fc + j)], xj, c.lx[fc + i]);
                     __syncwarp();
                 }
             }
-            accr += r;
             __syncwarp();
         }
+        accr += r;
+        if constexpr (LGV) gsync<W>(); // the view is reused by the next level
     }
     gsync<W>();
     // x = P*x (lexlse.h:1044): column c of the factorization belongs to variable varofcol[c]
@@ -1003,7 +1025,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
         FlopCount fl;
         fl.f                = 0;
         const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
-        lse_solve<W>(c, n, ld, G);
+        lse_solve<W>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v) lse_get_v<W>(c, n, ld, G);
         if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
@@ -1318,7 +1340,7 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
     nFixedPrev     = nFixed;
     totalRank      = lse_factorize<W, true>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
-    lse_solve<W>(c, sh.n, sh.ld, sh.G);
+    lse_solve<W>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
 template <int W, bool DS, bool LG>
