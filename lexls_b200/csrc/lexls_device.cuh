@@ -1451,20 +1451,52 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
                 }
             }
             gsync<W>();
-            if (tid < P)
+            // The working sets of different levels do not interact: one warp per level replays its level's part of the
+            // reference's sequence (all equalities in ascending order, then the guess).  A level of equalities only — the
+            // usual case — ends with active = 0, 1, 2, ... and nothing inactive: filled in parallel.  Mixed levels replay.
+            for (int k = tid >> 5; k < P; k += W)
             {
-                // the working sets of different levels do not interact: one thread per level replays its level's part
-                // of the reference's sequence (all equalities, then the guess)
-                const int k = tid;
-                for (int i = 0; i < sh.dim[k]; i++)
-                    if (eqflag[sh.uoff[k] + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
-                if (bf.guess)
-                    for (int i = 0; i < sh.dim[k]; i++)
+                const int o = sh.uoff[k], m = sh.dim[k];
+                bool alleq = true, anyeq = false, anyguess = false;
+                for (int i = lane; i < m; i += 32)
+                {
+                    const bool e = eqflag[o + i] != 0;
+                    alleq        = alleq && e;
+                    anyeq        = anyeq || e;
+                    const int t  = gs[o + i];
+                    anyguess     = anyguess || t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB;
+                }
+                alleq    = __all_sync(0xffffffffu, alleq);
+                anyeq    = __any_sync(0xffffffffu, anyeq);
+                anyguess = __any_sync(0xffffffffu, anyguess) && bf.guess != nullptr;
+                if (alleq && m > 0)
+                {
+                    for (int i = lane; i < m; i += 32)
                     {
-                        const int t = gs[sh.uoff[k] + i];
-                        if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[sh.uoff[k] + i] == CTR_INACTIVE)
-                            ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
+                        c.active[o + i]  = (unsigned short)i;
+                        c.atype[o + i]   = CTR_ACTIVE_EQ;
+                        c.alltype[o + i] = CTR_ACTIVE_EQ;
                     }
+                    if (lane == 0)
+                    {
+                        c.nact[k]   = m;
+                        c.ninact[k] = 0;
+                    }
+                }
+                else if (lane == 0)
+                {
+                    if (anyeq)
+                        for (int i = 0; i < m; i++)
+                            if (eqflag[o + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
+                    if (anyguess)
+                        for (int i = 0; i < m; i++)
+                        {
+                            const int t = gs[o + i];
+                            if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[o + i] == CTR_INACTIVE)
+                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
+                        }
+                }
+                __syncwarp();
             }
             gsync<W>();
             for (int i = tid; i < sh.Mall; i += NT) c.dv[i] = 0.0;
