@@ -2,6 +2,10 @@
 #include "lexls_device.cuh"
 namespace lexls_dev
 {
+kernel_fn pick_lse_pair_kernel()
+{
+    return (kernel_fn)lse_pair_kernel<0>;
+}
 kernel_fn pick_lse_kernel(int W, bool LG)
 {
     if (LG) return (kernel_fn)lse_kernel<16, true>;

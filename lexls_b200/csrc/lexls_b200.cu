@@ -41,7 +41,7 @@ struct lexls_b200_batch
     lexls_b200_params_t user_params{};
     SmemMap sm{};
     int W = 1;
-    bool DS = false, LG = false;
+    bool DS = false, LG = false, pair = false;
     unsigned grid = 0, smem = 0, per_sm = 0;
     std::string kname;
     bool planned = false;
@@ -244,6 +244,7 @@ template <typename K> static int occupancy_of(K kernel, int threads, unsigned sm
 namespace lexls_dev
 {
 kernel_fn pick_lse_kernel(int W, bool LG);
+kernel_fn pick_lse_pair_kernel();
 kernel_fn pick_lsi_w1_kernel(bool DS);
 kernel_fn pick_lsi_wn_kernel(int W, bool DS, bool LG);
 } // namespace lexls_dev
@@ -312,7 +313,21 @@ static int plan(lexls_b200_batch *h)
     h->LG = LG;
     h->sm = m;
     h->smem = m.total;
+    // two LexLSE problems per warp (lexls_pair.cuh): no fixed variables, register-window shapes with <= 20 rows per level
+    h->pair = false;
+    if (!lsi && !LG && W == 1 && panel_only && h->sh.nfix == 0 && getenv("LEXLS_B200_PAIR"))
+    {
+        h->pair = true;
+        for (int k = 0; k < h->sh.P; k++)
+            if (h->sh.dim[k] > 20) h->pair = false;
+    }
     kernel_fn k = pick_kernel(h->kind, W, DS, LG, h->kname);
+    if (h->pair)
+    {
+        k        = pick_lse_pair_kernel();
+        h->kname = "lse_pair";
+        h->smem  = 2 * m.total;
+    }
     int per_sm  = 0;
     if (int rc = occupancy_of(k, 32 * W, h->smem, &per_sm)) return rc;
     if (per_sm < 1) return fail(LEXLS_B200_ECAPACITY, "kernel does not fit on an SM");
@@ -886,7 +901,7 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.lod_stride   = h->lod_stride;
 
     std::string name;
-    kernel_fn k = pick_kernel(h->kind, h->W, h->DS, h->LG, name);
+    kernel_fn k = h->pair ? pick_lse_pair_kernel() : pick_kernel(h->kind, h->W, h->DS, h->LG, name);
     CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     void *args[] = {(void *)&h->sh, (void *)&h->pr, (void *)&h->sm, (void *)&b};
@@ -1063,7 +1078,7 @@ int lexls_b200_kernel_info(lexls_b200_batch_t *h, lexls_b200_kernel_info_t *info
     info->grid               = h->grid;
     info->block              = 32 * h->W;
     info->smem_bytes         = h->smem;
-    info->problems_per_sm    = h->per_sm;
+    info->problems_per_sm    = h->pair ? 2 * h->per_sm : h->per_sm;
     info->launches_per_solve = 1;
     info->warps_per_problem  = h->W;
     return 0;

@@ -317,6 +317,7 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 
 } // namespace lexls_dev
 #include "lexls_panel.cuh"
+#include "lexls_pair.cuh"
 namespace lexls_dev
 {
 
@@ -1048,6 +1049,176 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
         }
         gsync<W>();
         p = *(unsigned long long *)c.scal;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LexLSE, two problems per warp (lexls_pair.cuh): each half warp factorizes its own problem in its own shared-memory
+// slice; solve / residuals / outputs then run per problem on the full warp with the ordinary routines.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lse_factorize_pair(unsigned char *smem, const SmemMap &smap, const unsigned slice, const int n,
+                                                  const int ld, const int G, const int nCtr, const double tol, const bool on,
+                                                  FlopCount &fl)
+{
+    PairArgs pa;
+    pa.lod = smap.lod; pa.ptmp = smap.ptmp; pa.invd = smap.invd; pa.hh = smap.hh; pa.colperm = smap.colperm;
+    pa.varofcol = smap.varofcol; pa.slice = slice; pa.n = n; pa.ld = ld; pa.nCtr = nCtr; pa.tol = tol;
+    const int lane = threadIdx.x & 31, hb = lane >> 4, cl = lane & 15;
+    const Ctx c = make_ctx(smem + hb * slice, smap);
+    for (int k = cl; k < n; k += 16) c.varofcol[k] = (unsigned short)k;
+    for (int g = cl; g < G; g += 16)
+    {
+        c.rank[g] = 0;
+        c.fcol[g] = 0;
+    }
+    __syncwarp();
+    int ColIndex = 0, sumRank = 0;
+    for (int g = 0; g < G; g++)
+    {
+        const int fr = c.frow[g], dim = c.ldim[g], fc = ColIndex;
+        if (cl == 0) c.fcol[g] = fc;
+        const bool go = on && ColIndex < n && dim > 0;
+        if (__any_sync(0xffffffffu, go))
+        {
+            const int ncmax = (int)__reduce_max_sync(0xffffffffu, go ? (unsigned)(n + 1 - ColIndex) : 0u);
+            const int S     = (ncmax + 15) >> 4;
+#define LX_PQR(NGv)                                                                                                     \
+    {                                                                                                                   \
+        if (S == 1)                                                                                                     \
+            ColIndex = qr_level_pair<NGv, 1>(pa, fr, dim, ColIndex, go);                                                \
+        else if (S == 2)                                                                                                \
+            ColIndex = qr_level_pair<NGv, 2>(pa, fr, dim, ColIndex, go);                                                \
+        else                                                                                                            \
+            ColIndex = qr_level_pair<NGv, 3>(pa, fr, dim, ColIndex, go);                                                \
+    }
+            if (dim <= 12) LX_PQR(3) else LX_PQR(5)
+#undef LX_PQR
+        }
+        const int rank = ColIndex - fc;
+        sumRank += rank;
+        if (cl == 0) c.rank[g] = rank;
+        {
+            // algorithmic flops of this level's QR in closed form
+            const long long m = dim, cc = n - fc, r = rank, rp = (r < m) ? r : m - 1;
+            const long long T1 = rp * (rp - 1) / 2, T2 = (rp - 1) * rp * (2 * rp - 1) / 6, R1 = r * (r - 1) / 2;
+            long long f = 2 * m * cc + 2 * (r * m - R1) + 2 * (r * (cc - 1) - R1);
+            if (rp > 0) f += 3 * (rp * m - T1) + 4 * rp + 4 * (rp * m * cc - (m + cc) * T1 + T2);
+            if (go) fl.f += (unsigned long long)f;
+        }
+        if (g + 1 < G && __any_sync(0xffffffffu, on && rank > 0) && fr + dim < nCtr)
+        {
+            const int rk    = on ? rank : 0;
+            const int rkmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)rk);
+            const bool odd  = fr & 1;
+#define LX_PGS(NBv)                                                                                                     \
+    {                                                                                                                   \
+        if (odd)                                                                                                        \
+            gauss_rows_pair<NBv, true>(pa, fr + dim, fr, fc, rk, ColIndex);                                             \
+        else                                                                                                            \
+            gauss_rows_pair<NBv, false>(pa, fr + dim, fr, fc, rk, ColIndex);                                            \
+    }
+            if (rkmax <= 12) LX_PGS(3) else LX_PGS(5)
+#undef LX_PGS
+            const int Rows = nCtr - (fr + dim);
+            if (on && rank > 0) fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
+        }
+    }
+    __syncwarp();
+    fl.f += (unsigned long long)sumRank * sumRank;
+    return sumRank;
+}
+
+template <int UNUSED>
+__global__ void __launch_bounds__(32, 5) lse_pair_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+                                                         const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned slice = sm.total;
+    const int tid = threadIdx.x, hb = tid >> 4, cl = tid & 15;
+    const int n = sh.n, ld = sh.ld, G = sh.G, nCtr = sh.M;
+    const Ctx c0 = make_ctx(smem_raw, sm);
+    {
+        const Ctx ch = make_ctx(smem_raw + hb * slice, sm);
+        if (tid == 0)
+        {
+            mbar_init(c0.mbar, 1);
+            fence_mbar_init();
+        }
+        for (int g = cl; g < G; g += 16)
+        {
+            ch.ldim[g] = sh.dim[g];
+            ch.frow[g] = sh.goff[g];
+        }
+        if (cl < 4) ch.LOD[ld * (n + 1) + cl] = 0.0; // zero pad behind LOD (see build_map)
+        for (int k = cl; k < LX_PANEL_TMP_DOUBLES; k += 16) ch.ptmp[k] = 0.0; // an idle half multiplies stale staging data by 0
+    }
+    __syncwarp();
+
+    unsigned parity = 0;
+    for (;;)
+    {
+        if (tid == 0) *(unsigned long long *)c0.scal = atomicAdd(bf.queue, 2ull);
+        __syncwarp();
+        const unsigned long long q = *(unsigned long long *)c0.scal;
+        if (q >= bf.batch) break;
+        const bool two             = q + 1 < bf.batch;
+        const unsigned long long p = q + hb;
+        const bool on              = hb == 0 || two;
+        const Ctx ch               = make_ctx(smem_raw + hb * slice, sm);
+        if (tid == 0)
+        {
+            const unsigned bytes = (unsigned)(bf.rec_stride * sizeof(double));
+            fence_proxy_async();
+            mbar_expect_tx(c0.mbar, two ? 2 * bytes : bytes);
+            tma_bulk_g2s(c0.LOD, bf.rec + q * bf.rec_stride, bytes, c0.mbar);
+            if (two) tma_bulk_g2s(smem_raw + slice + sm.lod, bf.rec + (q + 1) * bf.rec_stride, bytes, c0.mbar);
+        }
+        for (int k = cl; k < nCtr; k += 16) ch.hh[k] = 0.0;
+        for (int k = cl; k < n; k += 16) ch.lx[k] = 0.0;
+        __syncwarp();
+        mbar_wait(c0.mbar, parity);
+        parity ^= 1;
+        __syncwarp();
+
+        FlopCount fl;
+        fl.f               = 0;
+        const int totalRank = lse_factorize_pair(smem_raw, sm, slice, n, ld, G, nCtr, pr.tol_lindep, on, fl);
+        if (cl == 0)
+        {
+            ch.scal[4]                        = totalRank;
+            *(unsigned long long *)(ch.scal + 6) = fl.f;
+        }
+        __syncwarp();
+        (void)p;
+        // back-substitution, residuals and outputs: one problem at a time on the whole warp
+        for (int h = 0; h < (two ? 2 : 1); h++)
+        {
+            const Ctx c                = make_ctx(smem_raw + h * slice, sm);
+            const unsigned long long pp = q + h;
+            lse_solve<1>(c, n, ld, G);
+            for (int k = tid; k < n; k += 32) bf.x[pp * n + k] = c.lx[k];
+            if (bf.v)
+            {
+                lse_get_v<1>(c, n, ld, G);
+                for (int k = tid; k < nCtr; k += 32) bf.v[pp * nCtr + k] = c.wsp[k];
+            }
+            for (int g = tid; g < G; g += 32) bf.ranks[pp * G + g] = c.rank[g];
+            const int tr = c.scal[4];
+            if (bf.colperm)
+                for (int k = tid; k < n; k += 32) bf.colperm[pp * n + k] = (k < tr) ? c.colperm[k] : 0u;
+            if (bf.lexqr) dump_lexqr<32>(c, bf, pp, n, ld, nCtr, nCtr);
+            if (tid == 0)
+            {
+                bf.status[pp]   = ST_SOLVED;
+                unsigned *cnt   = bf.counters + pp * 8;
+                cnt[0]          = 1;
+                cnt[1] = cnt[2] = cnt[3] = cnt[4] = 0;
+                cnt[5]                            = (unsigned)tr;
+                cnt[6]                            = (unsigned)nCtr;
+                cnt[7]                            = (unsigned)((*(unsigned long long *)(c.scal + 6) + 500) / 1000);
+            }
+            __syncwarp();
+        }
     }
 }
 
