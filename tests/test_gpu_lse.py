@@ -172,3 +172,25 @@ def test_register_window_with_fixed_variables(oracle):
     val = rng.standard_normal((B, 4))
     wx, exact, _ = _check(oracle, n, dims, data, fixed=(idx, val))
     assert exact
+
+
+def test_two_problems_per_warp_kernel(oracle, monkeypatch):
+    """The experimental half-warp-per-problem kernel (LEXLS_B200_PAIR=1): odd batch (a last warp with one problem), pairs whose
+    two problems leave a level at different steps (rank deficiency, zero levels) — same bits as the oracle."""
+    from lexls_b200 import problems
+    monkeypatch.setenv("LEXLS_B200_PAIR", "1")
+    w = problems.workload("c2", 257)
+    data, _ = problems.generate(w)
+    wx, exact, got = _check(oracle, w.nVar, w.ObjDim, data)
+    assert got["info"]["name"] == "lse_pair" and exact
+    rng = np.random.default_rng(21)
+    for dims, n in (([17, 3, 20], 15), ([20, 20], 47), ([9, 12, 5], 30)):
+        B = 37
+        data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+        data[0][::2, 1, :] = data[0][::2, 0, :]            # every other problem: duplicated column (ties, lower rank)
+        data[0][1::3, 2, :] = 0.0                           # zero column in every third
+        if dims[1] >= 2:
+            data[1][::4, :, 1] = -data[1][::4, :, 0]        # dependent rows: the level ends early for one half only
+        data[-1][B - 3:, :, :] = 0.0
+        wx, exact, got = _check(oracle, n, dims, data)
+        assert got["info"]["name"] == "lse_pair" and exact
