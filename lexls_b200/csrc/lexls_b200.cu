@@ -291,8 +291,7 @@ static int plan(lexls_b200_batch *h)
     bool panel_only = (W == 1) && cols <= 48;
     for (int k = 0; k < h->sh.P; k++)
         if (h->sh.dim[k] > 40 && !(lsi && h->sh.off && k == 0)) panel_only = false;
-    if (getenv("LEXLS_B200_W1_SMEM") && lsi) panel_only = false; // experiment (needs -DLX_W1_SMEM_EXPERIMENT)
-    else if (W == 1 && !panel_only) W = 2; // the W = 1 kernels have no shared-memory QR (see lse_factorize)
+    if (W == 1 && !panel_only) W = 2; // the W = 1 kernels have no shared-memory QR (see lse_factorize)
     SmemMap m = build_map(h->sh, lsi, DS, LG, panel_only);
     // keep the objective data in shared memory only while at least 3 problems stay resident per SM
     if (lsi && DS && m.total * 3 > max_smem)

@@ -741,11 +741,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
 
         // warp-per-problem kernels are only planned for shapes that the register-window panel covers (plan() in
         // lexls_b200.cu), so they carry no shared-memory fallback code
-#ifdef LX_W1_SMEM_EXPERIMENT
-        constexpr bool PANEL = (W == 1) && !CQ; // experiment: the LexLSI warp-per-problem kernel on the shared-memory routines
-#else
         constexpr bool PANEL = (W == 1);
-#endif
         if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else

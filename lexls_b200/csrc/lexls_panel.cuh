@@ -635,10 +635,7 @@ template <bool COMPACT>
 __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, int &ColIndex)
 {
     const int ncols = pa.n + 1 - ColIndex;
-    int S           = (ncols + 15) >> 4;
-#ifdef LX_QR_MERGE_S23
-    if (!COMPACT && S == 2) S = 3; // experiment: one instance for both widths (instruction-cache footprint)
-#endif
+    const int S     = (ncols + 15) >> 4;
     if (dim < 1) return true; // empty level: rank 0
     if (S > 3 || dim > 40) return false;
 #define LX_QR(NGv)                                                                                                      \
