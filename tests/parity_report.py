@@ -1,7 +1,7 @@
 """Full-size parity report: the CUDA path vs the CPU oracle on the complete BASELINE batches (C2: 65,536 LexLSE problems;
 C3: 16,384 LexLSI problems cold and warm-started).  Counts bit-identical results and discrete mismatches, and lists the
 near-tie margins the oracle measures (pivot gap, rank margin, ratio-test gap, multiplier gap) — the cases a different
-summation order (e.g. Eigen's) could decide differently.   usage: python scripts/parity_report.py > profiles/rN_parity_report.json"""
+summation order (e.g. Eigen's) could decide differently.   usage: python tests/parity_report.py > profiles/rN_parity_report.json"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
