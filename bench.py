@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2_60"])
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's batch)")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--e2e-chunks", type=int, default=4,
+                    help="end-to-end leg: sub-batches whose host->device copies overlap the previous chunk's solve (1 = plain calls)")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload line items")
     return ap.parse_args()
@@ -179,6 +181,19 @@ class Runner:
     def step(self):
         self.s.solve(sync=False)
 
+    def make_pipeline(self, chunks, device):
+        """The end-to-end leg through lexls_b200.PipelinedBatch (public API): same inputs, `chunks` sub-batches."""
+        lx = self.lx
+        cls = lx.LexLSEBatch if self.w.kind == "lse" else lx.LexLSIBatch
+        self.pipe = lx.PipelinedBatch(cls, self.w.nVar, self.w.ObjDim, self.w.ObjType if self.w.kind == "lsi" else None,
+                                      batch=self.w.batch, device=device, chunks=chunks)
+        self.pipe_host = [t.numpy() for t in self.pinned]
+        self.pipe_guess = [g.numpy() for g in self.guess_pinned] if self.w.kind == "lsi" else None
+        self.pipe_x0 = self.x0_pinned.numpy() if self.w.kind == "lsi" else None
+
+    def e2e_step_pipelined(self):
+        self.pipe.solve_host(self.pipe_host, self.x_pinned.numpy(), var_index=self.vi, guess=self.pipe_guess, x0=self.pipe_x0)
+
     def e2e_step(self):
         """What a caller does per batch: host data in (pinned), solve, x out (pinned)."""
         for k, t in enumerate(self.pinned):
@@ -274,7 +289,17 @@ def run_ours(args):
     for _ in range(2):
         r.e2e_step()
     ms_e2e = timed(torch, dist, world, r.e2e_step, e2e_steps)
-    e2e_value = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
+    e2e_plain = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value, e2e_api = e2e_plain, "LexLSEBatch/LexLSIBatch: setData, solve, get_x"
+    if args.e2e_chunks > 1:
+        # the same step through PipelinedBatch: sub-batches whose copies overlap the previous chunk's solve
+        r.make_pipeline(args.e2e_chunks, local)
+        for _ in range(2):
+            r.e2e_step_pipelined()
+        ms_e2e = timed(torch, dist, world, r.e2e_step_pipelined, e2e_steps)
+        e2e_value = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
+        e2e_api = "PipelinedBatch.solve_host, %d chunks" % args.e2e_chunks
+        r.pipe.close()
 
     out = None
     if rank == 0:
@@ -296,7 +321,7 @@ def run_ours(args):
                        "kernel": info},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes, "d2h_bytes_per_step": r.d2h_bytes,
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "api": e2e_api, "plain_calls_value": e2e_plain},
             "gpu_launches": args.steps * info["launches_per_solve"],
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp["dfma_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / fp["dfma_tflops"], "traffic": load_traffic(info["name"], w.name),
@@ -338,6 +363,7 @@ def run_ours(args):
             for _ in range(2):
                 r3.e2e_step()
             e3 = timed(torch, dist, 1, r3.e2e_step, 5)
+            # (plain calls: with 16k problems per batch the eleven small set_* calls per chunk cost what the overlap gains)
             out["also"] = {"c3_lexlsi_warm": {
                 "workload": w3.name, "value": w3.batch * k3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / k3,
                 "mean_factorizations": float(c3[:, 0].mean()), "kernel": r3.s.kernel_info()["name"],

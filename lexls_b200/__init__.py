@@ -7,5 +7,6 @@ call sequence, synthetic workload generators and the `.dat` fixture reader.  The
 from .capi import LexLSError, Params, SO_PATH  # noqa: F401
 from .batch import LexLSEBatch, LexLSIBatch, measure_fp64_peak  # noqa: F401
 from . import datfile, problems  # noqa: F401
+from .shard import PipelinedBatch, ShardedBatch  # noqa: F401
 
-__all__ = ["LexLSEBatch", "LexLSIBatch", "Params", "LexLSError", "measure_fp64_peak", "datfile", "problems", "SO_PATH"]
+__all__ = ["LexLSEBatch", "LexLSIBatch", "PipelinedBatch", "ShardedBatch", "Params", "LexLSError", "measure_fp64_peak", "datfile", "problems", "SO_PATH"]

@@ -92,3 +92,68 @@ class ShardedBatch:
 
     def gather(self, name, *args):
         return np.concatenate([getattr(s, name)(*args) for _, _, s in self.parts], axis=0)
+
+
+class PipelinedBatch:
+    """One logical batch on ONE GPU, split into `chunks` sub-batches with their own handle and CUDA stream, each driven by
+    its own host thread: the host->device copy of one chunk overlaps the solve and the result read of the previous ones.
+    The copy phases are serialised by a lock (the PCIe link is the shared resource; interleaved copies would all finish
+    late), the solves and reads are not.  For callers whose problem data lives in host memory (pinned for full speed)."""
+
+    def __init__(self, cls, nVar, ObjDim, ObjType=None, batch=1, device=0, chunks=4):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.ObjType = list(ObjType) if ObjType is not None else None
+        self.nObj = len(ObjDim)
+        chunks = max(1, min(int(chunks), int(batch)))
+        self.ranges = shard_ranges(batch, chunks)
+        self.parts = []
+        for lo, hi in self.ranges:
+            kw = dict(batch=hi - lo, device=device)
+            self.parts.append((lo, hi, cls(nVar, ObjDim, ObjType, **kw) if ObjType is not None else cls(nVar, ObjDim, **kw)))
+        self._lock = threading.Lock()
+        self._pool = ThreadPoolExecutor(max_workers=len(self.parts))
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        for _, _, s in self.parts:
+            s.close()
+        self.parts = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def setParameters(self, p):
+        for _, _, s in self.parts:
+            s.setParameters(p)
+
+    def solve_host(self, data, x_out, var_index=None, guess=None, x0=None):
+        """data[k]: host arrays of the whole batch ([B, cols, m_k]); x_out: [B, nVar] host array that receives x.
+        LexLSI warm start: guess[k] [B, m_k] uint8 and x0 [B, nVar].  Returns when every chunk is done."""
+
+        def work(part):
+            lo, hi, s = part
+            with self._lock:  # one chunk's inputs at a time over the link
+                for k, d in enumerate(data):
+                    if self.ObjType is not None and self.ObjType[k] == 1:
+                        s.setData(k, d[lo:hi], var_index=var_index)
+                    else:
+                        s.setData(k, d[lo:hi])
+                if guess is not None:
+                    for k, g in enumerate(guess):
+                        s.set_active_guess(k, g[lo:hi])
+                if x0 is not None:
+                    s.set_x0(x0[lo:hi])
+            s.solve(sync=False)
+            s.get_x(out=x_out[lo:hi])
+
+        for f in [self._pool.submit(work, p) for p in self.parts]:
+            f.result()
+
+    def gather(self, name, *args):
+        return np.concatenate([getattr(s, name)(*args) for _, _, s in self.parts], axis=0)

@@ -269,3 +269,43 @@ def test_working_set_log_matches_the_oracle(oracle, name, count, par):
         assert np.array_equal(entries[p, :n[p]], r["log"]), p
         total += int(n[p])
     assert total > 0
+
+
+def test_pipelined_batch_matches_plain_calls():
+    """PipelinedBatch (chunks with overlapped copies) returns the same bits as one plain batch: LexLSE and warm-started LexLSI."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c2", 1000)
+    data, _ = problems.generate(w)
+    with lx.LexLSEBatch(w.nVar, w.ObjDim, batch=w.batch) as s:
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        x_ref = s.get_x()
+    x = np.empty_like(x_ref)
+    with lx.PipelinedBatch(lx.LexLSEBatch, w.nVar, w.ObjDim, batch=w.batch, chunks=3) as pb:
+        pb.solve_host(data, x)
+        assert np.array_equal(pb.gather("get_ranks").shape, (w.batch, 3))
+    assert np.array_equal(x, x_ref)
+
+    w = problems.workload("c3", 500)
+    data, vi = problems.generate(w)
+    nl = len(w.ObjDim)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        guess, x0 = [s.getActiveCtr(k) for k in range(nl)], s.get_x()
+        d2 = problems.perturb(w, data)
+        for k, d in enumerate(d2):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        for k, g in enumerate(guess):
+            s.set_active_guess(k, g)
+        s.set_x0(x0)
+        s.solve()
+        x_ref, st_ref = s.get_x(), s.get_status()
+    x = np.empty_like(x_ref)
+    with lx.PipelinedBatch(lx.LexLSIBatch, w.nVar, w.ObjDim, w.ObjType, batch=w.batch, chunks=4) as pb:
+        pb.solve_host(d2, x, var_index=vi, guess=guess, x0=x0)
+        st = pb.gather("get_status")
+    assert np.array_equal(x, x_ref) and np.array_equal(st, st_ref)
