@@ -826,14 +826,18 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
                     xi  = acc;
                     inv = c.invd[fc + lane];
                 }
+                // column-oriented back-substitution: the entry of the next column is loaded one step ahead, the update is
+                // computed by every lane and kept by the lanes above the pivot (no divergent branch in the chain)
+                const double *Bl = B + ro + ((lane < r) ? lane : 0) + lb * fc;
+                double anext     = Bl[lb * (r - 1)];
                 for (int j = r; j--;)
                 {
+                    const double a  = anext;
+                    if (j > 0) anext = Bl[lb * (j - 1)];
                     const double t  = xi * inv;
                     const double xj = __shfl_sync(0xffffffffu, t, j);
-                    if (lane == j)
-                        xi = xj;
-                    else if (lane < j)
-                        xi = fma(-B[ro + lane + lb * (fc + j)], xj, xi);
+                    const double u  = fma(-a, xj, xi);
+                    xi              = (lane == j) ? xj : ((lane < j) ? u : xi);
                 }
                 if (lane < r) c.lx[fc + lane] = xi;
             }
