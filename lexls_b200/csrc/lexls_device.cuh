@@ -821,8 +821,24 @@ template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int 
                 double xi = 0.0, inv = 0.0;
                 if (lane < r)
                 {
-                    double acc = B[ro + lane + lb * n];
-                    for (int j = 0; j < accr; j++) acc = fma(-B[ro + lane + lb * (fc1 + j)], c.lx[fc1 + j], acc);
+                    double acc       = B[ro + lane + lb * n];
+                    const double *bp = B + ro + lane + lb * fc1;
+                    const double *xp = c.lx + fc1;
+                    int j            = 0;
+                    if constexpr (W == 1) // (measured: helps the LexLSE kernel, hurts the two-warp LexLSI kernel)
+                    for (; j + 4 <= accr; j += 4) // loads first, then the sequential chain (S)
+                    {
+                        double b4[4], x4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                        {
+                            b4[u] = bp[lb * (j + u)];
+                            x4[u] = xp[j + u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) acc = fma(-b4[u], x4[u], acc);
+                    }
+                    for (; j < accr; j++) acc = fma(-bp[lb * j], xp[j], acc);
                     xi  = acc;
                     inv = c.invd[fc + lane];
                 }
