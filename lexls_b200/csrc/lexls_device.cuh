@@ -366,6 +366,15 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
     }
     gsync<W>();
 
+    // LGV: the column swaps of the row pairs outside the level go to global memory (L2).  Each thread owns one such pair
+    // (from the top of the group: the warps without a staged pair) and stores the swap of a step during the NEXT step,
+    // so that no barrier waits for the round trip; same thread, same addresses: program order keeps the swaps in sequence
+    const int npv_ = vt1 - vt0, nout = LGV ? hp - npv_ : 0;
+    const int og = NT - 1 - tid, tg = (og < vt0) ? og : og + npv_;
+    const bool outside = LGV && og < nout;
+    double2 pend_c = make_double2(0.0, 0.0), pend_p = make_double2(0.0, 0.0);
+    int pendp = -1, pendc = 0;
+
     for (int counter = 0; counter < dim; counter++)
     {
         const int row = fr + counter, rem = dim - counter;
@@ -448,7 +457,34 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
         // column swap over ALL rows (lexlse.h:222-227) fused with the Householder scaling (:241-242); the reflector
         // v = [1; essential], zero outside its rows, is also written to c.vv for the broadcast reads of the apply
         const int pb = row >> 1, pe = (row + rem + 1) >> 1; // pairs touched by the reflector
-        for (int t = tid; t < hp; t += NT)
+        if constexpr (LGV)
+        {
+            if (outside)
+            {
+                if (pendp >= 0)
+                {
+                    st2(LOD + ld * pendp + 2 * tg, pend_c);
+                    st2(LOD + ld * pendc + 2 * tg, pend_p);
+                }
+                pendp = -1;
+                if (p != ColIndex)
+                {
+                    pend_p = ld2(LOD + ld * p + 2 * tg);
+                    pend_c = ld2(LOD + ld * ColIndex + 2 * tg);
+                    pendp  = p;
+                    pendc  = ColIndex;
+                }
+            }
+            if (p != ColIndex)
+                for (int o = NT + tid; o < nout; o += NT) // more outside pairs than threads: swapped at once
+                {
+                    const int t     = (o < vt0) ? o : o + npv_;
+                    const double2 a = ld2(LOD + ld * p + 2 * t);
+                    st2(LOD + ld * p + 2 * t, ld2(LOD + ld * ColIndex + 2 * t));
+                    st2(LOD + ld * ColIndex + 2 * t, a);
+                }
+        }
+        for (int t = (LGV ? vt0 : 0) + tid; t < (LGV ? vt1 : hp); t += NT)
         {
             double *const pp = P(p, t), *const pc = P(ColIndex, t);
             double2 a        = ld2(pp);
@@ -492,6 +528,36 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const bool apply  = tau != 0.0;
             const double *vp  = c.vv + 2 * pb;
             const int np      = pe - pb;
+            if constexpr (W == 16)
+            {
+                // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
+                const int par = tid & 1;
+                for (int jb = ColIndex + 1 + ((tid & ~31) >> 1); jb <= n; jb += NT / 2) // warp-uniform trip count
+                {
+                    const int j      = jb + (lane >> 1);
+                    const bool valid = j <= n;
+                    double *cp       = P(valid ? j : n, pb) + par;
+                    const double *vq = vp + par;
+                    double acc       = 0.0;
+                    if (apply && valid)
+                    {
+#pragma unroll 4
+                        for (int q = 0; q < np; q++) acc = fma(vq[2 * q], cp[2 * q], acc);
+                    }
+                    const double w = tau * (acc + __shfl_xor_sync(0xffffffffu, acc, 1));
+                    if (apply && valid)
+                    {
+#pragma unroll 4
+                        for (int q = 0; q < np; q++) cp[2 * q] = fma(-vq[2 * q], w, cp[2 * q]);
+                    }
+                    if (valid && j < n && par == (row & 1))
+                    {
+                        const double a0 = *E(j, row);
+                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
+                    }
+                }
+            }
+            else
             for (int j = ColIndex + 1 + tid; j <= n; j += NT)
             {
                 double *cp = P(j, pb);
@@ -529,6 +595,11 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
     }
     if constexpr (LGV)
     {
+        if (outside && pendp >= 0)
+        {
+            st2(LOD + ld * pendp + 2 * tg, pend_c);
+            st2(LOD + ld * pendc + 2 * tg, pend_p);
+        }
         // the level's rows (R, the reflectors, the not eliminated rest) go back to the work matrix
         gsync<W>();
         const int npv = vt1 - vt0, ncv = n + 1 - fc0;
