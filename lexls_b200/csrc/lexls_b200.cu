@@ -452,7 +452,6 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     s.M    = s.goff[s.G];
     s.Mall = s.m0 + s.M;
     if (s.Mall > 60000) { delete h; return fail(LEXLS_B200_ECAPACITY, "too many constraints"); }
-    if (s.off && s.G == 0) { delete h; return fail(LEXLS_B200_EINVAL, "a problem of one simple-bounds level is not supported"); }
     s.ld   = (std::max(s.M, 2) + 1) & ~1; // even: every column starts 16-byte aligned (128-bit row-pair accesses)
     {
         // the shared-memory QR also wants ld/2 odd (lanes over columns conflict-free); the register-window LexLSE path

@@ -1,0 +1,96 @@
+"""GPU parity on randomly drawn SHAPES (seeded): every kernel family is crossed — the register-window panel (<= 48 columns,
+<= 40 rows per level), the two-warp and the 4 / 8-warp shared-memory routines, levels of one row, empty levels, more rows
+than columns, rank-deficient and duplicated rows, with and without a simple-bounds level.  Discrete outcomes (ranks, pivot
+sequence, status, counters, active sets, working-set order) must be identical to the oracle's; x and ||v_k|| within 1e-9."""
+import numpy as np
+import pytest
+
+from helpers import compare_lsi
+from test_gpu_lse import _check
+from test_gpu_lsi import _both
+
+pytestmark = pytest.mark.gpu
+
+
+def _lse_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 100))
+    P = int(rng.integers(1, 7))
+    dims = [int(rng.integers(0, 46)) if rng.random() < 0.8 else int(rng.integers(0, 3)) for _ in range(P)]
+    if sum(dims) == 0:
+        dims[0] = 2
+    B = 24
+    data = []
+    for m in dims:
+        d = rng.standard_normal((B, n + 1, m))
+        if m >= 2 and rng.random() < 0.5:
+            d[: B // 2, :, m - 1] = d[: B // 2, :, 0]                      # duplicated row
+        if m >= 3 and rng.random() < 0.3:
+            d[: B // 3, :n, 1] = 0.0                                       # zero normal
+        if m >= 4 and rng.random() < 0.3:
+            d[:, :, 2] = 0.5 * d[:, :, 0] - 2.0 * d[:, :, 3]               # dependent row
+        data.append(np.ascontiguousarray(d))
+    nfix = int(rng.integers(0, min(n, 4))) if rng.random() < 0.4 else 0
+    fixed = None
+    if nfix:
+        idx = np.stack([rng.permutation(n)[:nfix] for _ in range(B)]).astype(np.uint32)
+        fixed = (idx, rng.standard_normal((B, nfix)))
+    return n, dims, data, fixed
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_lse_shapes(oracle, seed):
+    n, dims, data, fixed = _lse_case(seed)
+    wx, exact, _ = _check(oracle, n, dims, data, fixed=fixed)
+    assert exact, "n=%d dims=%s fixed=%s: not bit-identical (worst rel err %.3e)" % (n, dims, fixed is not None, wx)
+
+
+def _lsi_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.integers(2, 80))
+    P = int(rng.integers(1, 6))
+    B = 16
+    sb = rng.random() < 0.5
+
+    class W:
+        pass
+    W.nVar, W.ObjDim, W.ObjType = n, [], []
+    data, vi = [], None
+    for k in range(P):
+        if k == 0 and sb:
+            m = int(rng.integers(1, n + 1))
+            vi = np.sort(rng.permutation(n)[:m]).astype(np.uint32)
+            ub = 0.3 + rng.random((B, m))
+            lb = -0.3 - rng.random((B, m))
+            if rng.random() < 0.5:
+                lb[:, 0] = ub[:, 0]                                        # a fixed variable (equality bound)
+            data.append(np.ascontiguousarray(np.stack([lb, ub], axis=1)))
+            W.ObjDim.append(m)
+            W.ObjType.append(1)
+            continue
+        m = int(rng.integers(1, 31))
+        A = rng.standard_normal((B, m, n))
+        ub = rng.standard_normal((B, m)) + 0.5
+        lb = ub - rng.random((B, m)) * 2.0
+        eq = rng.random(m) < rng.random()
+        lb[:, eq] = ub[:, eq]
+        if m >= 2 and rng.random() < 0.4:
+            A[:, m - 1, :] = A[:, 0, :]                                    # parallel constraints
+        if m >= 3 and rng.random() < 0.2:
+            A[:, 1, :] = 0.0                                               # 0 * x in [lb, ub]
+        data.append(np.ascontiguousarray(np.concatenate([A, lb[:, :, None], ub[:, :, None]], axis=2).transpose(0, 2, 1)))
+        W.ObjDim.append(m)
+        W.ObjType.append(0)
+    return W, data, vi
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_lsi_shapes(oracle, seed):
+    W, data, vi = _lsi_case(seed)
+    got, ref = _both(oracle, W, data, vi, max_number_of_factorizations=60)
+    compare_lsi(got, ref, len(W.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]), "n=%d dims=%s types=%s: x not bit-identical" % (W.nVar, W.ObjDim, W.ObjType)
+    # warm start from the result (previous active set and x as the guess)
+    got2, ref2 = _both(oracle, W, data, vi, guess=got["active"], x0=got["x"], max_number_of_factorizations=60)
+    compare_lsi(got2, ref2, len(W.ObjDim))
+    assert np.array_equal(got2["x"], ref2["x"])
