@@ -8,7 +8,7 @@ kernel_fn pick_lse_pair_kernel()
 }
 kernel_fn pick_lse_kernel(int W, bool LG)
 {
-    if (LG) return (kernel_fn)lse_kernel<16, true>;
+    if (LG) return W == 8 ? (kernel_fn)lse_kernel<8, true> : (kernel_fn)lse_kernel<16, true>;
     switch (W)
     {
     case 1: return (kernel_fn)lse_kernel<1, false>;

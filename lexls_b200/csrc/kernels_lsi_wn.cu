@@ -4,7 +4,7 @@ namespace lexls_dev
 {
 kernel_fn pick_lsi_wn_kernel(int W, bool DS, bool LG)
 {
-    if (LG) return (kernel_fn)lsi_kernel<16, false, true>;
+    if (LG) return W == 8 ? (kernel_fn)lsi_kernel<8, false, true> : (kernel_fn)lsi_kernel<16, false, true>;
     if (DS) switch (W)
         {
         case 2: return (kernel_fn)lsi_kernel<2, true, false>;

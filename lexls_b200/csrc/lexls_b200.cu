@@ -306,6 +306,14 @@ static int plan(lexls_b200_batch *h)
         W  = 16;
         m  = build_map(h->sh, lsi, DS, LG);
         if (m.total > max_smem) return fail(LEXLS_B200_ECAPACITY, "problem shape exceeds the shared memory of every kernel variant");
+        // the pivot chain is latency bound: two 8-warp groups per SM (two problems in flight) beat one 16-warp group
+        // whenever two copies of the level view fit (1 KB per CTA is reserved by the system)
+        if (2ull * (m.total + 1024) <= (unsigned long long)prop.sharedMemPerMultiprocessor) W = 8;
+        if (const char *e = getenv("LEXLS_B200_LG_WARPS"))
+        {
+            const int w = atoi(e);
+            if (w == 8 || w == 16) W = w;
+        }
     }
     h->W  = W;
     h->DS = DS;

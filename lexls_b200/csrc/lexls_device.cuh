@@ -528,7 +528,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const bool apply  = tau != 0.0;
             const double *vp  = c.vv + 2 * pb;
             const int np      = pe - pb;
-            if constexpr (W == 16)
+            if constexpr (LGV)
             {
                 // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
                 const int par = tid & 1;
@@ -615,17 +615,17 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
 // ---------------------------------------------------------------------------------------------------------------
 // Gauss step of one level in shared memory, lexlse.h:431-471: Left := Left * inv(R), Trailing -= Left * Up
 // ---------------------------------------------------------------------------------------------------------------
-template <int W>
+template <int W, bool LGV = (W == 16)>
 __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const int ld, const int nCtr, const int fr, const int dim,
                                                 const int fc, const int rank, const int ColIndex, const int ldv = 0)
 {
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x;
     double *const LOD = c.LOD;
-    // R(k, col) / Up(k, col) = RB[k + rl * col].  Global-memory variants (W == 16): the level's rows are still in the
+    // R(k, col) / Up(k, col) = RB[k + rl * col].  Global-memory variants (LGV): the level's rows are still in the
     // shared-memory view that qr_level_smem staged (columns >= fc), so only the lower rows stream from global memory.
-    const double *const RB = (W == 16) ? c.LVIEW + (fr - 2 * (fr >> 1)) : LOD + fr;
-    const int rl           = (W == 16) ? ldv : ld;
+    const double *const RB = LGV ? c.LVIEW + (fr - 2 * (fr >> 1)) : LOD + fr;
+    const int rl           = LGV ? ldv : ld;
     const int frn = fr + dim, Rows = nCtr - frn;
     const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
     // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
@@ -742,7 +742,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 //   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
-template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
+template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
                                               const int nCtr, const int nFixed, const double tol, FlopCount &fl)
 {
     const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol);
@@ -816,7 +816,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
         if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
-            qr_level_smem<W, (W == 16)>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv);
+            qr_level_smem<W, LGV>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
@@ -837,7 +837,7 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
             if constexpr (PANEL)
                 gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
-                gauss_step_smem<W>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv);
+                gauss_step_smem<W, LGV>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
         }
 
@@ -856,10 +856,10 @@ template <int W, bool CQ = false, bool CG = CQ> __device__ int lse_factorize(con
 // ---------------------------------------------------------------------------------------------------------------
 // back-substitution, lexlse.h:1015-1045; result (already un-permuted, x = P*x) in c.lx and c.lxo
 // ---------------------------------------------------------------------------------------------------------------
-template <int W> __device__ void lse_solve(const Ctx &c, const int n, const int ld, const int G, const int ldv = 0)
+template <int W, bool LGV = (W == 16)> __device__ void lse_solve(const Ctx &c, const int n, const int ld, const int G, const int ldv = 0)
 {
     constexpr int NT  = 32 * W;
-    constexpr bool LGV = (W == 16); // work matrix in global memory: each level's R rows are staged in the shared-memory view
+    // LGV: work matrix in global memory: each level's R rows are staged in the shared-memory view
     const int tid = threadIdx.x, lane = tid & 31;
     const double *LOD = c.LOD;
     int accr = 0;
@@ -1045,7 +1045,7 @@ __device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, cons
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool LG>
-__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : ((LG && W == 8) ? 2 : 1)) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
@@ -1112,8 +1112,8 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : 1) lse_kernel(const __gr
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
-        lse_solve<W>(c, n, ld, G, sm.ldv);
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
+        lse_solve<W, LG>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v) lse_get_v<W>(c, n, ld, G);
         if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
@@ -1587,7 +1587,7 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
 // formLexLSE + factorize + solve of one active-set iteration as ONE real call: the LexLSI kernel needs it at three places
 // (phase 1, the first step from a user guess, the loop), and three inlined copies do not fit the instruction cache.
 // The context is rebuilt from the shared-memory map (kernel parameter, __grid_constant__: its address may be taken).
-template <int W, bool DS>
+template <int W, bool DS, bool LG>
 __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap &sm, const double tol, double *lod, double *objp,
                                                   double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl)
 {
@@ -1597,12 +1597,12 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     ObjView<DS> ov{c, sh, objp, sbp};
     const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
     nFixedPrev     = nFixed;
-    totalRank      = lse_factorize<W, true>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
-    lse_solve<W>(c, sh.n, sh.ld, sh.G, sm.ldv);
+    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
+    lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
 template <int W, bool DS, bool LG>
-__global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 1) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
@@ -1786,7 +1786,7 @@ __global__ void __launch_bounds__(32 * W) lsi_kernel(const __grid_constant__ Sha
             }
         };
         auto factor_and_solve = [&]() {
-            lsi_factor_and_solve<W, DS>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl);
+            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl);
         };
 
         // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------

@@ -12,14 +12,14 @@ from test_gpu_lsi import _both
 pytestmark = pytest.mark.gpu
 
 
-def _lse_case(seed):
-    rng = np.random.default_rng(1000 + seed)
-    n = int(rng.integers(1, 100))
-    P = int(rng.integers(1, 7))
-    dims = [int(rng.integers(0, 46)) if rng.random() < 0.8 else int(rng.integers(0, 3)) for _ in range(P)]
+def _lse_case(seed, wide=False):
+    rng = np.random.default_rng(1000 + seed + (500 if wide else 0))
+    n = int(rng.integers(100, 400)) if wide else int(rng.integers(1, 100))
+    P = int(rng.integers(1, 5 if wide else 7))
+    dims = [int(rng.integers(0, 90 if wide else 46)) if rng.random() < 0.8 else int(rng.integers(0, 3)) for _ in range(P)]
     if sum(dims) == 0:
         dims[0] = 2
-    B = 24
+    B = 8 if wide else 24
     data = []
     for m in dims:
         d = rng.standard_normal((B, n + 1, m))
@@ -45,11 +45,11 @@ def test_random_lse_shapes(oracle, seed):
     assert exact, "n=%d dims=%s fixed=%s: not bit-identical (worst rel err %.3e)" % (n, dims, fixed is not None, wx)
 
 
-def _lsi_case(seed):
-    rng = np.random.default_rng(5000 + seed)
-    n = int(rng.integers(2, 80))
-    P = int(rng.integers(1, 6))
-    B = 16
+def _lsi_case(seed, wide=False):
+    rng = np.random.default_rng(5000 + seed + (500 if wide else 0))
+    n = int(rng.integers(65, 260)) if wide else int(rng.integers(2, 80))
+    P = int(rng.integers(1, 5 if wide else 6))
+    B = 6 if wide else 16
     sb = rng.random() < 0.5
 
     class W:
@@ -68,7 +68,7 @@ def _lsi_case(seed):
             W.ObjDim.append(m)
             W.ObjType.append(1)
             continue
-        m = int(rng.integers(1, 31))
+        m = int(rng.integers(1, 60 if wide else 31))
         A = rng.standard_normal((B, m, n))
         ub = rng.standard_normal((B, m)) + 0.5
         lb = ub - rng.random((B, m)) * 2.0
@@ -94,3 +94,19 @@ def test_random_lsi_shapes(oracle, seed):
     got2, ref2 = _both(oracle, W, data, vi, guess=got["active"], x0=got["x"], max_number_of_factorizations=60)
     compare_lsi(got2, ref2, len(W.ObjDim))
     assert np.array_equal(got2["x"], ref2["x"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_wide_lse_shapes(oracle, seed):
+    """100-400 columns, up to 90 rows per level: the 4 / 8-warp shared-memory kernels and the global-work-matrix kernel."""
+    n, dims, data, fixed = _lse_case(seed, wide=True)
+    wx, exact, got = _check(oracle, n, dims, data, fixed=fixed)
+    assert exact, "n=%d dims=%s (%s): not bit-identical (worst rel err %.3e)" % (n, dims, got["info"]["name"], wx)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_wide_lsi_shapes(oracle, seed):
+    W, data, vi = _lsi_case(seed, wide=True)
+    got, ref = _both(oracle, W, data, vi, max_number_of_factorizations=25)
+    compare_lsi(got, ref, len(W.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]), "n=%d dims=%s (%s): x not bit-identical" % (W.nVar, W.ObjDim, got["info"]["name"])
