@@ -110,3 +110,21 @@ def test_random_wide_lsi_shapes(oracle, seed):
     got, ref = _both(oracle, W, data, vi, max_number_of_factorizations=25)
     compare_lsi(got, ref, len(W.ObjDim))
     assert np.array_equal(got["x"], ref["x"]), "n=%d dims=%s (%s): x not bit-identical" % (W.nVar, W.ObjDim, got["info"]["name"])
+
+
+@pytest.mark.parametrize("lg_warps", ["8", "16"])
+@pytest.mark.parametrize("seed", range(5))
+def test_random_shapes_with_the_work_matrix_in_global_memory(oracle, monkeypatch, seed, lg_warps):
+    """The same random shapes forced through the global-work-matrix kernels (level view in shared memory, odd first rows,
+    deferred column swaps of the rows outside the level), 8 and 16 warps per problem."""
+    monkeypatch.setenv("LEXLS_B200_FORCE_LODGLOBAL", "1")
+    monkeypatch.setenv("LEXLS_B200_LG_WARPS", lg_warps)
+    n, dims, data, fixed = _lse_case(seed)
+    wx, exact, got = _check(oracle, n, dims, data, fixed=fixed)
+    assert got["info"]["name"] == "lse_w%s_lodglobal" % lg_warps
+    assert exact, "LexLSE n=%d dims=%s: not bit-identical (worst rel err %.3e)" % (n, dims, wx)
+    W, data, vi = _lsi_case(seed + 1)
+    got, ref = _both(oracle, W, data, vi, max_number_of_factorizations=40)
+    assert got["info"]["name"] == "lsi_w%s_lodglobal" % lg_warps
+    compare_lsi(got, ref, len(W.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]), "LexLSI n=%d dims=%s types=%s: x not bit-identical" % (W.nVar, W.ObjDim, W.ObjType)

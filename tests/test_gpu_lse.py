@@ -87,13 +87,15 @@ def test_multi_warp_groups_match(oracle, warps, monkeypatch):
     assert exact
 
 
-def test_lod_in_global_memory_variant(oracle, monkeypatch):
+@pytest.mark.parametrize("lg_warps", ["8", "16"])
+def test_lod_in_global_memory_variant(oracle, monkeypatch, lg_warps):
     monkeypatch.setenv("LEXLS_B200_FORCE_LODGLOBAL", "1")
+    monkeypatch.setenv("LEXLS_B200_LG_WARPS", lg_warps)
     from lexls_b200 import problems
     w = problems.workload("tiny_lse")
     data, _ = problems.generate(w)
     wx, exact, got = _check(oracle, w.nVar, w.ObjDim, data)
-    assert "lodglobal" in got["info"]["name"]
+    assert got["info"]["name"] == "lse_w%s_lodglobal" % lg_warps
     assert exact
 
 

@@ -46,14 +46,17 @@ def test_c3_cold_and_warm(oracle):
     assert got2["counters"][:, 0].mean() < got["counters"][:, 0].mean()
 
 
-def test_c4_shape_work_matrix_in_global_memory(oracle):
+@pytest.mark.parametrize("lg_warps", ["8", "16"])
+def test_c4_shape_work_matrix_in_global_memory(oracle, monkeypatch, lg_warps):
     """BASELINE configs[3] shape (10 levels, n = 200, 40 rows each): the work matrix (401 x 201 doubles) exceeds one SM's
-    shared memory, so the 16-warp kernel keeps it in an L2-resident scratch buffer.  Bounded by the factorization cap."""
+    shared memory, so the kernel keeps it in an L2-resident scratch buffer (8 warps per problem and two problems per SM by
+    default, 16 warps when two level views do not fit).  Bounded by the factorization cap."""
+    monkeypatch.setenv("LEXLS_B200_LG_WARPS", lg_warps)
     from lexls_b200 import problems
     w = problems.workload("c4", 6)
     data, vi = problems.generate(w)
     got, ref = _both(oracle, w, data, vi, max_number_of_factorizations=10)
-    assert "lodglobal" in got["info"]["name"]
+    assert got["info"]["name"] == "lsi_w%s_lodglobal" % lg_warps
     compare_lsi(got, ref, len(w.ObjDim))
     assert np.array_equal(got["x"], ref["x"])
     assert (got["status"] == 2).all() and (got["counters"][:, 0] == 10).all()
