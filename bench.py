@@ -379,7 +379,7 @@ def run_ours(args):
             out["also"] = {"error": repr(e)}
         try:
             # BASELINE configs[3]: LexLSI 10 levels, n = 200, 40 rows each, 1,024 problems, cold start (one timed solve; the
-            # 401 x 201 work matrix lives in an L2-resident scratch buffer, 16 warps per problem)
+            # 401 x 201 work matrix lives in an L2-resident scratch buffer, 8 warps per problem and two problems per SM)
             import lexls_b200 as lx
             w4, d4, v4 = make_workload("c4", None, 0)
             with lx.LexLSIBatch(w4.nVar, w4.ObjDim, w4.ObjType, batch=w4.batch, device=local) as s4:

@@ -1602,7 +1602,7 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
 }
 
 template <int W, bool DS, bool LG>
-__global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 1) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
