@@ -1,0 +1,337 @@
+// lexls/batch.h — the batch entry point in C++: LexLS::LexLSIBatch / LexLS::LexLSEBatch (RAII over the C-ABI handle of
+// include/lexls_b200.h) and the free functions LexLS::solveBatch.  One object owns `batch` problems of ONE shape
+// (nVar, nObj, ObjDim, ObjType) and solves them with one kernel launch; the members mirror the single-problem classes
+// (reference include/lexls/lexlsi.h:51, :325, :350, :444, :120, :306, :205, :508, :688 and lexlse.h:50, :1522, :1381,
+// :117, :1015, :1587) with a leading problem index where a result of one problem is read.  The reference has no such
+// entry point: this is the header a maintainer would add next to lexlsi.h.
+#pragma once
+
+#include <algorithm>
+
+#include <lexls/lexlsi.h>
+
+namespace LexLS
+{
+namespace internal
+{
+// [batch][m x cols] column-major image of per-problem matrices (what lexls_b200_set_data takes)
+inline void pack_level(const std::vector<dMatrixType> &per_problem, Index rows, Index cols, std::vector<RealScalar> &packed)
+{
+    packed.resize(per_problem.size() * static_cast<size_t>(rows) * cols);
+    for (size_t q = 0; q < per_problem.size(); q++)
+    {
+        const dMatrixType &m = per_problem[q];
+        if (static_cast<Index>(m.rows()) != rows || static_cast<Index>(m.cols()) != cols)
+            throw Exception("solveBatch: a problem's matrix has the wrong size");
+        std::copy(m.data(), m.data() + static_cast<size_t>(rows) * cols, packed.begin() + q * static_cast<size_t>(rows) * cols);
+    }
+}
+} // namespace internal
+
+class LexLSIBatch
+{
+public:
+    LexLSIBatch(Index nVar_, Index nObj_, Index *ObjDim_, ObjectiveType *ObjType_, uint64_t batch_, int device = 0)
+    : h_(0), nVar(nVar_), nObj(nObj_), batch(batch_), dim(ObjDim_, ObjDim_ + nObj_), solved(false)
+    {
+        type.resize(nObj);
+        for (Index k = 0; k < nObj; k++) type[k] = static_cast<int32_t>(ObjType_[k]);
+        internal::lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSI, nVar, nObj, dim.data(), type.data(), batch, device, &h_));
+    }
+    ~LexLSIBatch()
+    {
+        if (h_) lexls_b200_destroy(h_);
+    }
+    LexLSIBatch(const LexLSIBatch &) = delete;
+    LexLSIBatch &operator=(const LexLSIBatch &) = delete;
+
+    uint64_t size() const { return batch; }
+    lexls_b200_batch_t *handle() { return h_; } // for the *_dev entry points and lexls_b200_set_stream
+
+    void setParameters(const ParametersLexLSI &par) // lexlsi.h:325
+    {
+        if (par.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
+        lexls_b200_params_t p;
+        lexls_b200_default_params(&p);
+        p.max_number_of_factorizations = par.max_number_of_factorizations;
+        p.tol_linear_dependence        = par.tol_linear_dependence;
+        p.tol_wrong_sign_lambda        = par.tol_wrong_sign_lambda;
+        p.tol_correct_sign_lambda      = par.tol_correct_sign_lambda;
+        p.tol_feasibility              = par.tol_feasibility;
+        p.cycling_handling_enabled     = par.cycling_handling_enabled;
+        p.cycling_max_counter          = par.cycling_max_counter;
+        p.cycling_relax_step           = par.cycling_relax_step;
+        p.modify_x_guess_enabled       = par.modify_x_guess_enabled;
+        p.modify_type_active_enabled   = par.modify_type_active_enabled;
+        p.modify_type_inactive_enabled = par.modify_type_inactive_enabled;
+        p.set_min_init_ctr_violation   = par.set_min_init_ctr_violation;
+        p.use_phase1_v0                = par.use_phase1_v0;
+        p.log_working_set_enabled      = par.log_working_set_enabled;
+        p.deactivate_first_wrong_sign  = par.deactivate_first_wrong_sign;
+        internal::lexls_b200_check(lexls_b200_set_params(h_, &p));
+    }
+
+    // general level: [A | lb | ub] of every problem, m_k x (nVar + 2) each (lexlsi.h:350)
+    void setData(Index ObjIndex, const std::vector<dMatrixType> &per_problem)
+    {
+        check_level(ObjIndex, per_problem.size());
+        if (type[ObjIndex] == static_cast<int32_t>(SIMPLE_BOUNDS_OBJECTIVE)) throw Exception("setData: use the VarIndex overload for simple bounds");
+        internal::pack_level(per_problem, dim[ObjIndex], nVar + 2, scratch);
+        setDataPacked(ObjIndex, scratch.data(), dim[ObjIndex], static_cast<uint64_t>(dim[ObjIndex]) * (nVar + 2));
+    }
+    // already packed host data: problem q at data + q * problem_stride, column-major with leading dimension ld
+    void setDataPacked(Index ObjIndex, const RealScalar *data, Index ld, uint64_t problem_stride)
+    {
+        internal::lexls_b200_check(lexls_b200_set_data(h_, ObjIndex, data, ld > 0 ? ld : 1, problem_stride));
+        solved = false;
+    }
+    // simple bounds (level 0): one VarIndex (0-based) shared by the batch, [lb | ub] m_0 x 2 per problem (lexlsi.h:444)
+    void setData(Index ObjIndex, Index *VarIndex, const std::vector<dMatrixType> &per_problem)
+    {
+        check_level(ObjIndex, per_problem.size());
+        if (ObjIndex != 0 || type[0] != static_cast<int32_t>(SIMPLE_BOUNDS_OBJECTIVE)) throw Exception("setData: level 0 is not SIMPLE_BOUNDS_OBJECTIVE");
+        internal::pack_level(per_problem, dim[0], 2, scratch);
+        internal::lexls_b200_check(lexls_b200_set_simple_bounds(h_, VarIndex, 0, scratch.data(), dim[0] > 0 ? dim[0] : 1,
+                                                                static_cast<uint64_t>(dim[0]) * 2));
+        solved = false;
+    }
+    // warm start: the api_activate calls of problem q as one type per row (CTR_INACTIVE = no call), lexlsi.h:120
+    void setActiveGuess(Index ObjIndex, const std::vector<std::vector<ConstraintActivationType>> &per_problem)
+    {
+        check_level(ObjIndex, per_problem.size());
+        std::vector<uint8_t> t(batch * static_cast<size_t>(dim[ObjIndex]));
+        for (uint64_t q = 0; q < batch; q++)
+        {
+            if (per_problem[q].size() != dim[ObjIndex]) throw Exception("setActiveGuess: wrong number of constraints");
+            for (Index i = 0; i < dim[ObjIndex]; i++) t[q * dim[ObjIndex] + i] = static_cast<uint8_t>(per_problem[q][i]);
+        }
+        internal::lexls_b200_check(lexls_b200_set_active_guess(h_, ObjIndex, t.data()));
+        solved = false;
+    }
+    void set_x0(const std::vector<dVectorType> &x0) // lexlsi.h:306
+    {
+        if (x0.size() != batch) throw Exception("set_x0: one vector per problem");
+        std::vector<RealScalar> p(batch * static_cast<size_t>(nVar));
+        for (uint64_t q = 0; q < batch; q++)
+        {
+            if (static_cast<Index>(x0[q].size()) != nVar) throw Exception("set_x0: wrong size");
+            std::copy(x0[q].data(), x0[q].data() + nVar, p.begin() + q * nVar);
+        }
+        internal::lexls_b200_check(lexls_b200_set_x0(h_, p.data()));
+        solved = false;
+    }
+    void reset() // lexlsi.h:88 (keeps data and parameters)
+    {
+        internal::lexls_b200_check(lexls_b200_reset(h_));
+        solved = false;
+    }
+
+    // one launch: the active-set loop of every problem runs on the device (lexlsi.h:205)
+    void solve()
+    {
+        internal::lexls_b200_check(lexls_b200_solve_batch_sync(h_));
+        x.resize(batch * static_cast<size_t>(nVar));
+        status.resize(batch);
+        counters.resize(batch * static_cast<size_t>(LEXLS_B200_NCOUNTERS));
+        internal::lexls_b200_check(lexls_b200_get_x(h_, x.data()));
+        internal::lexls_b200_check(lexls_b200_get_status(h_, status.data()));
+        internal::lexls_b200_check(lexls_b200_get_counters(h_, counters.data()));
+        active.assign(nObj, std::vector<uint8_t>());
+        solved = true;
+    }
+
+    TerminationStatus getStatus(uint64_t q) const { need(q); return static_cast<TerminationStatus>(status[q]); }
+    dVectorType get_x(uint64_t q) const // lexlsi.h:508
+    {
+        need(q);
+        dVectorType r(nVar);
+        std::copy(x.begin() + q * nVar, x.begin() + (q + 1) * nVar, r.data());
+        return r;
+    }
+    const RealScalar *get_x_packed() const { need(0); return x.data(); } // [batch][nVar]
+    Index getFactorizationsCount(uint64_t q) const { need(q); return counters[q * LEXLS_B200_NCOUNTERS + LEXLS_B200_CNT_FACTORIZATIONS]; }
+    Index getActivationsCount(uint64_t q) const { need(q); return counters[q * LEXLS_B200_NCOUNTERS + LEXLS_B200_CNT_ACTIVATIONS]; }
+    Index getDeactivationsCount(uint64_t q) const { need(q); return counters[q * LEXLS_B200_NCOUNTERS + LEXLS_B200_CNT_DEACTIVATIONS]; }
+    Index getTotalRank(uint64_t q) const { need(q); return counters[q * LEXLS_B200_NCOUNTERS + LEXLS_B200_CNT_TOTAL_RANK]; }
+    dVectorType get_v(uint64_t q, Index ObjIndex) // lexlsi.h:528
+    {
+        need(q);
+        std::vector<RealScalar> t(batch * static_cast<size_t>(dim[ObjIndex]));
+        internal::lexls_b200_check(lexls_b200_get_v(h_, ObjIndex, t.data()));
+        dVectorType r(dim[ObjIndex]);
+        std::copy(t.begin() + q * dim[ObjIndex], t.begin() + (q + 1) * dim[ObjIndex], r.data());
+        return r;
+    }
+    void getActiveCtr(uint64_t q, Index ObjIndex, std::vector<ConstraintActivationType> &out) // lexlsi.h:688
+    {
+        need(q);
+        if (active[ObjIndex].empty() && dim[ObjIndex])
+        {
+            active[ObjIndex].resize(batch * static_cast<size_t>(dim[ObjIndex]));
+            internal::lexls_b200_check(lexls_b200_get_active_set(h_, ObjIndex, active[ObjIndex].data()));
+        }
+        out.resize(dim[ObjIndex]);
+        for (Index i = 0; i < dim[ObjIndex]; i++) out[i] = static_cast<ConstraintActivationType>(active[ObjIndex][q * dim[ObjIndex] + i]);
+    }
+
+private:
+    void check_level(Index ObjIndex, size_t count) const
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        if (count != batch) throw Exception("one matrix per problem of the batch is expected");
+    }
+    void need(uint64_t q) const
+    {
+        if (!solved) throw Exception("solve() has not been called");
+        if (q >= batch) throw Exception("problem index >= batch");
+    }
+    lexls_b200_batch_t *h_;
+    Index nVar, nObj;
+    uint64_t batch;
+    std::vector<Index> dim;
+    std::vector<int32_t> type;
+    std::vector<RealScalar> scratch, x;
+    std::vector<int32_t> status;
+    std::vector<uint32_t> counters;
+    std::vector<std::vector<uint8_t>> active;
+    bool solved;
+};
+
+class LexLSEBatch
+{
+public:
+    LexLSEBatch(Index nVar_, Index nObj_, Index *ObjDim_, uint64_t batch_, int device = 0)
+    : h_(0), nVar(nVar_), nObj(nObj_), batch(batch_), dim(ObjDim_, ObjDim_ + nObj_), solved(false)
+    {
+        internal::lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSE, nVar, nObj, dim.data(), 0, batch, device, &h_));
+    }
+    ~LexLSEBatch()
+    {
+        if (h_) lexls_b200_destroy(h_);
+    }
+    LexLSEBatch(const LexLSEBatch &) = delete;
+    LexLSEBatch &operator=(const LexLSEBatch &) = delete;
+
+    uint64_t size() const { return batch; }
+    lexls_b200_batch_t *handle() { return h_; }
+    void setParameters(const ParametersLexLSE &par) // lexlse.h:1467
+    {
+        if (par.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
+        lexls_b200_params_t p;
+        lexls_b200_default_params(&p);
+        p.tol_linear_dependence = par.tol_linear_dependence;
+        internal::lexls_b200_check(lexls_b200_set_params(h_, &p));
+    }
+    void setData(Index ObjIndex, const std::vector<dMatrixType> &per_problem) // [A | b], m_k x (nVar + 1) each, lexlse.h:1522
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        if (per_problem.size() != batch) throw Exception("one matrix per problem of the batch is expected");
+        internal::pack_level(per_problem, dim[ObjIndex], nVar + 1, scratch);
+        setDataPacked(ObjIndex, scratch.data(), dim[ObjIndex], static_cast<uint64_t>(dim[ObjIndex]) * (nVar + 1));
+    }
+    void setDataPacked(Index ObjIndex, const RealScalar *data, Index ld, uint64_t problem_stride)
+    {
+        internal::lexls_b200_check(lexls_b200_set_data(h_, ObjIndex, data, ld > 0 ? ld : 1, problem_stride));
+        solved = false;
+    }
+    // the same `count` variables fixed in every problem slot order: var_index / value are [batch][count] (lexlse.h:1381, :1449)
+    void fixVariables(Index count, const Index *var_index, const RealScalar *value)
+    {
+        internal::lexls_b200_check(lexls_b200_set_fixed_variables(h_, count, var_index, value, 0));
+        solved = false;
+    }
+    void solve() // factorize + solve of every problem, one launch (lexlse.h:117, :1015)
+    {
+        internal::lexls_b200_check(lexls_b200_solve_batch_sync(h_));
+        x.resize(batch * static_cast<size_t>(nVar));
+        ranks.resize(batch * static_cast<size_t>(nObj));
+        internal::lexls_b200_check(lexls_b200_get_x(h_, x.data()));
+        internal::lexls_b200_check(lexls_b200_get_ranks(h_, ranks.data()));
+        solved = true;
+    }
+    dVectorType get_x(uint64_t q) const // lexlse.h:1587
+    {
+        need(q);
+        dVectorType r(nVar);
+        std::copy(x.begin() + q * nVar, x.begin() + (q + 1) * nVar, r.data());
+        return r;
+    }
+    const RealScalar *get_x_packed() const { need(0); return x.data(); }
+    Index getRank(uint64_t q, Index ObjIndex) const { need(q); return ranks[q * nObj + ObjIndex]; } // lexlse.h:1603
+
+private:
+    void need(uint64_t q) const
+    {
+        if (!solved) throw Exception("solve() has not been called");
+        if (q >= batch) throw Exception("problem index >= batch");
+    }
+    lexls_b200_batch_t *h_;
+    Index nVar, nObj;
+    uint64_t batch;
+    std::vector<Index> dim;
+    std::vector<RealScalar> scratch, x;
+    std::vector<uint32_t> ranks;
+    bool solved;
+};
+
+struct BatchResult
+{
+    std::vector<dVectorType> x;
+    std::vector<TerminationStatus> status; // LexLSE: PROBLEM_SOLVED for every problem
+};
+
+// LexLSI: data[q][k] = [A | lb | ub] of level k of problem q (level 0 of a SIMPLE_BOUNDS hierarchy: [lb | ub], with VarIndex)
+inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, ObjectiveType *ObjType, const ParametersLexLSI &par,
+                              const std::vector<std::vector<dMatrixType>> &data, Index *VarIndex = 0, int device = 0)
+{
+    LexLSIBatch b(nVar, nObj, ObjDim, ObjType, data.size(), device);
+    b.setParameters(par);
+    std::vector<dMatrixType> level(data.size());
+    for (Index k = 0; k < nObj; k++)
+    {
+        for (size_t q = 0; q < data.size(); q++)
+        {
+            if (data[q].size() != nObj) throw Exception("solveBatch: every problem needs nObj matrices");
+            level[q] = data[q][k];
+        }
+        if (ObjType[k] == SIMPLE_BOUNDS_OBJECTIVE)
+            b.setData(k, VarIndex, level);
+        else
+            b.setData(k, level);
+    }
+    b.solve();
+    BatchResult r;
+    for (uint64_t q = 0; q < b.size(); q++)
+    {
+        r.x.push_back(b.get_x(q));
+        r.status.push_back(b.getStatus(q));
+    }
+    return r;
+}
+
+// LexLSE: data[q][k] = [A | b] of level k of problem q
+inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, const ParametersLexLSE &par,
+                              const std::vector<std::vector<dMatrixType>> &data, int device = 0)
+{
+    LexLSEBatch b(nVar, nObj, ObjDim, data.size(), device);
+    b.setParameters(par);
+    std::vector<dMatrixType> level(data.size());
+    for (Index k = 0; k < nObj; k++)
+    {
+        for (size_t q = 0; q < data.size(); q++)
+        {
+            if (data[q].size() != nObj) throw Exception("solveBatch: every problem needs nObj matrices");
+            level[q] = data[q][k];
+        }
+        b.setData(k, level);
+    }
+    b.solve();
+    BatchResult r;
+    for (uint64_t q = 0; q < b.size(); q++)
+    {
+        r.x.push_back(b.get_x(q));
+        r.status.push_back(PROBLEM_SOLVED);
+    }
+    return r;
+}
+} // namespace LexLS

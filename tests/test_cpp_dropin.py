@@ -7,11 +7,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
+def _build(tmp_path, name="test_dropin"):
     from lexls_b200 import build
     so = build.build()
-    exe = os.path.join(str(tmp_path), "test_dropin")
-    cmd = ["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"),
+    exe = os.path.join(str(tmp_path), name)
+    cmd = ["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-o", exe, so, "-Wl,-rpath," + os.path.dirname(so)]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return exe
@@ -29,5 +29,21 @@ def test_dropin_headers_compile_as_cxx11(tmp_path):
 @pytest.mark.gpu
 def test_dropin_known_answers_on_gpu(tmp_path):
     exe = _build(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_batch_header_compiles_as_cxx11(tmp_path):
+    """include/lexls/batch.h (LexLS::solveBatch, LexLSIBatch, LexLSEBatch) builds against the C-ABI; no GPU -> loud failure."""
+    exe = _build(tmp_path, "test_batch")
+    import torch
+    if not torch.cuda.is_available():
+        res = subprocess.run([exe], capture_output=True, text=True)
+        assert res.returncode == 2 and "no CPU fallback" in res.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_solve_batch_equals_single_problem_solves(tmp_path):
+    exe = _build(tmp_path, "test_batch")
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
