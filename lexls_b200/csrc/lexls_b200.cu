@@ -198,10 +198,15 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.lx = take(n * 8, 8);
     const bool alias_tmp = !lsi && panel_only && n <= LX_PANEL_TMP_DOUBLES && M <= LX_PANEL_TMP_DOUBLES;
     m.lxo = alias_tmp ? 0 : take(n * 8, 8);
-    m.colnorm = take(panel_only ? 8 : n * 8, 8);
+    // LexLSI: the column norms of the QR live in the multiplier workspace (wsp is dead while a level is factorized).  The
+    // 300 bytes matter: with them C3 fills all 228 KB of an SM (8 x (28,160 + 1,024)) and the repack kernels of the next
+    // sub-batch (PipelinedBatch) cannot become resident beside the solve — no copy/solve overlap
+    const bool alias_cn = lsi && !panel_only;
+    m.colnorm = alias_cn ? 0 : take(panel_only ? 8 : n * 8, 8);
     m.invd = take(n * 8, 8);
     m.hh = take((M + 1) * 8, 8);
     m.wsp = alias_tmp ? 0 : take((2 * m0 + M + n + 2) * 8, 8);
+    if (alias_cn) m.colnorm = m.wsp;
     const unsigned vecs = lsi ? Mall + 1 : 1;
     m.v = take(vecs * 8, 8);
     m.dv = take(vecs * 8, 8);
