@@ -1,5 +1,6 @@
 """Full-size parity report: the CUDA path vs the CPU oracle on the complete BASELINE batches (C2: 65,536 LexLSE problems;
-C3: 16,384 LexLSI problems cold and warm-started).  Counts bit-identical results and discrete mismatches, and lists the
+C3: 16,384 LexLSI problems cold and warm-started; with the argument `c4` also C4: 1,024 LexLSI problems of 10 levels, n = 200,
+cold start up to the 200-factorization cap — minutes of oracle time).  Counts bit-identical results and discrete mismatches, and lists the
 near-tie margins the oracle measures (pivot gap, rank margin, ratio-test gap, multiplier gap) — the cases a different
 summation order (e.g. Eigen's) could decide differently.   usage: python tests/parity_report.py > profiles/rN_parity_report.json"""
 import json, os, sys, time
@@ -53,7 +54,8 @@ data, vi = problems.generate(w)
 vib = np.tile(vi, (w.batch, 1))
 nl = len(w.ObjDim)
 
-def run_gpu(data, guess=None, x0=None):
+def run_gpu(data, guess=None, x0=None, w=w, vi=vi):
+    nl = len(w.ObjDim)
     with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
         for k, d in enumerate(data):
             s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
@@ -65,7 +67,8 @@ def run_gpu(data, guess=None, x0=None):
         return dict(x=s.get_x(), status=s.get_status(), counters=s.get_counters(), active=[s.getActiveCtr(k) for k in range(nl)],
                     v=[s.get_v(k) for k in range(nl)], info=s.kernel_info())
 
-def compare(tag, got, ref):
+def compare(tag, got, ref, w=w):
+    nl = len(w.ObjDim)
     act_same = np.ones(w.batch, dtype=bool)
     v_same = np.ones(w.batch, dtype=bool)
     for k in range(nl):
@@ -93,4 +96,15 @@ d2 = problems.perturb(w, data)
 ref2 = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, d2, var_index=vib, guess=got["active"], x0=got["x"], threads=0)
 got2 = run_gpu(d2, guess=got["active"], x0=got["x"])
 compare("c3_warm", got2, ref2)
+
+# ---- C4 (optional: the oracle needs minutes) --------------------------------------------------------------------------
+if "c4" in sys.argv[1:]:
+    w4 = problems.workload("c4")
+    d4, v4 = problems.generate(w4)
+    t0 = time.time()
+    ref4 = oracle.lsi_solve_batch(w4.nVar, w4.ObjDim, w4.ObjType, d4, var_index=None, threads=0)
+    t_or = time.time() - t0
+    got4 = run_gpu(d4, w=w4, vi=v4)
+    compare("c4_cold", got4, ref4, w=w4)
+    out["c4_cold"]["oracle_seconds"] = t_or
 print(json.dumps(out, indent=1))
