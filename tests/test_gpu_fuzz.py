@@ -41,8 +41,9 @@ def _lse_case(seed, wide=False):
 @pytest.mark.parametrize("seed", range(24))
 def test_random_lse_shapes(oracle, seed):
     n, dims, data, fixed = _lse_case(seed)
-    wx, exact, _ = _check(oracle, n, dims, data, fixed=fixed)
-    assert exact, "n=%d dims=%s fixed=%s: not bit-identical (worst rel err %.3e)" % (n, dims, fixed is not None, wx)
+    tol = [None, 1e-9, 1e-6, 1e-3][seed % 4]  # tol_linear_dependence decides the ranks of the dependent rows
+    wx, exact, _ = _check(oracle, n, dims, data, fixed=fixed, tol=tol)
+    assert exact, "n=%d dims=%s fixed=%s tol=%s: not bit-identical (worst rel err %.3e)" % (n, dims, fixed is not None, tol, wx)
 
 
 def _lsi_case(seed, wide=False):
@@ -128,3 +129,34 @@ def test_random_shapes_with_the_work_matrix_in_global_memory(oracle, monkeypatch
     assert got["info"]["name"] == "lsi_w%s_lodglobal" % lg_warps
     compare_lsi(got, ref, len(W.ObjDim))
     assert np.array_equal(got["x"], ref["x"]), "LexLSI n=%d dims=%s types=%s: x not bit-identical" % (W.nVar, W.ObjDim, W.ObjType)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_parameters_and_guesses(oracle, seed):
+    """Random ParametersLexLSI (tolerances, cycling guard, iteration cap, hot-start flags) with random active-set guesses, x0 and
+    (sometimes) v0 on random shapes: every option of the path against the oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    W, data, vi = _lsi_case(100 + seed)
+    B = data[0].shape[0]
+    par = dict(max_number_of_factorizations=int(rng.choice([1, 2, 5, 40])),
+               tol_linear_dependence=float(rng.choice([1e-12, 1e-9, 1e-6])),
+               tol_wrong_sign_lambda=float(rng.choice([1e-8, 1e-6, 1e-10])),
+               tol_correct_sign_lambda=float(rng.choice([1e-12, 1e-9, 0.0])),
+               tol_feasibility=float(rng.choice([1e-13, 1e-10, 1e-8])),
+               cycling_handling_enabled=int(rng.integers(0, 2)), cycling_max_counter=int(rng.integers(1, 6)),
+               cycling_relax_step=float(rng.choice([1e-8, 1e-6])),
+               modify_x_guess_enabled=int(rng.integers(0, 2)), modify_type_active_enabled=int(rng.integers(0, 2)),
+               modify_type_inactive_enabled=int(rng.integers(0, 2)), set_min_init_ctr_violation=int(rng.integers(0, 2)))
+    guess = x0 = v0 = None
+    mode = int(rng.integers(0, 4))
+    if mode >= 1:
+        guess = [rng.choice([0, 0, 1, 2], size=(B, m)).astype(np.uint8) for m in W.ObjDim]
+    if mode >= 2:
+        x0 = 0.5 * rng.standard_normal((B, W.nVar))
+        if rng.random() < 0.5:
+            par["use_phase1_v0"] = 1
+    if mode == 3:
+        v0 = [0.1 * rng.standard_normal((B, m)) for m in W.ObjDim]
+    got, ref = _both(oracle, W, data, vi, guess=guess, x0=x0, v0=v0, **par)
+    compare_lsi(got, ref, len(W.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]), "n=%d dims=%s types=%s par=%s" % (W.nVar, W.ObjDim, W.ObjType, par)
