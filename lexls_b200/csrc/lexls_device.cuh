@@ -630,6 +630,44 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
     const int t0 = frn >> 1, t1 = (nCtr + 1) >> 1; // row pairs of the lower levels (the first may straddle)
     // Left := Left * inv(R): one thread per row pair, 4 columns at a time (left-looking across blocks of 4 columns,
     // then the 4x4 triangle); per entry the update order is k = 0,1,2,... as in the column-by-column solve
+    if constexpr (LGV)
+    {
+        // global work matrix: one thread per ROW and 8 columns at a time — every re-read of an L entry is a round trip to L2,
+        // and blocks of 8 need 80 of them per row of a 40-row level where blocks of 4 need 180.  Same updates per entry,
+        // in the same order (k ascending, then the triangle of the block, then the scaling).
+        for (int r = frn + tid; r < nCtr; r += NT)
+        {
+            double *rp = LOD + r;
+            for (int cb = 0; cb < rank; cb += 8)
+            {
+                int col[8];
+                double acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                {
+                    col[q] = fc + ((cb + q < rank) ? cb + q : rank - 1);
+                    acc[q] = rp[ld * col[q]];
+                }
+                for (int k = 0; k < cb; k++)
+                {
+                    const double x   = rp[ld * (fc + k)];
+                    const double *Rk = RB + k;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc[q] = fma(-x, Rk[rl * col[q]], acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (cb + q < rank)
+                    {
+#pragma unroll
+                        for (int q2 = 0; q2 < q; q2++) acc[q] = fma(-acc[q2], RB[cb + q2 + rl * col[q]], acc[q]);
+                        acc[q] *= c.invd[col[q]];
+                        rp[ld * col[q]] = acc[q];
+                    }
+            }
+        }
+    }
+    else
     for (int t = t0 + tid; t < t1; t += NT)
     {
         double *rp       = LOD + 2 * t;
