@@ -718,9 +718,11 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
         }
     }
     gsync<W>();
-    // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of 4 columns)
+    // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of SW columns); the global-work-matrix
+    // kernels use strips of 8: every L entry is an L2 round trip there, and wider strips halve them
     {
-        const int ncols = n - ColIndex + 1, nstrips = (ncols + 3) >> 2, npairs = t1 - t0;
+        constexpr int SW = LGV ? 8 : 4;
+        const int ncols = n - ColIndex + 1, nstrips = (ncols + SW - 1) / SW, npairs = t1 - t0;
         int s = 0, tt = tid;
         while (tt >= npairs && s < nstrips)
         {
@@ -729,13 +731,13 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
         }
         while (s < nstrips)
         {
-            const int t = t0 + tt, j0 = ColIndex + 4 * s;
+            const int t = t0 + tt, j0 = ColIndex + SW * s;
             double *rp      = LOD + 2 * t;
             const bool full = (2 * t >= frn);
-            int col[4];
-            double2 acc[4];
+            int col[SW];
+            double2 acc[SW];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < SW; q++)
             {
                 col[q] = (j0 + q <= n) ? j0 + q : n;
                 acc[q] = ld2(rp + ld * col[q]);
@@ -745,7 +747,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
                 const double2 l  = ld2(rp + ld * (fc + k));
                 const double *up = RB + k;
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int q = 0; q < SW; q++)
                 {
                     const double u = up[rl * col[q]];
                     acc[q].x       = fma(-l.x, u, acc[q].x);
@@ -753,7 +755,7 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < SW; q++)
                 if (j0 + q <= n)
                 {
                     if (full)
