@@ -281,7 +281,9 @@ static int plan(lexls_b200_batch *h)
     // LexLSE: one warp per problem (register-window panel).  LexLSI: the active-set loop is latency bound and its code
     // has to stay small (32 KB instruction cache), so two warps per problem on the compact shared-memory routines with
     // the objective data read through L2 keep more warps resident (measured on C3: 18.5 ms vs 29.8 ms, profiles/).
-    int W = cols <= 64 ? (lsi ? 2 : 1) : (cols <= 128 ? 2 : (cols <= 256 ? 4 : 8));
+    // Wider problems: the reflector is applied with one thread per column, so the group gets a thread for every column
+    // (residency is set by the work matrix in shared memory, not by the warps: test_01.dat, 89 columns, 84 -> 76 ms with 4)
+    int W = cols <= 64 ? (lsi ? 2 : 1) : (cols <= 128 ? 4 : 8);
     if (const char *e = getenv("LEXLS_B200_WARPS"))
     {
         int w = atoi(e);
