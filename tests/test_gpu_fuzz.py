@@ -160,3 +160,18 @@ def test_random_parameters_and_guesses(oracle, seed):
     got, ref = _both(oracle, W, data, vi, guess=guess, x0=x0, v0=v0, **par)
     compare_lsi(got, ref, len(W.ObjDim))
     assert np.array_equal(got["x"], ref["x"]), "n=%d dims=%s types=%s par=%s" % (W.nVar, W.ObjDim, W.ObjType, par)
+
+
+@pytest.mark.parametrize("lg_warps", ["8", "16"])
+def test_global_work_matrix_with_more_row_pairs_than_threads(oracle, monkeypatch, lg_warps):
+    """1,100 rows = 550 row pairs per column: more pairs outside a level than the group has threads (256 / 512), so the column
+    swaps of the rows outside the level run both the pipelined path (one pair per thread) and the immediate loop."""
+    monkeypatch.setenv("LEXLS_B200_FORCE_LODGLOBAL", "1")
+    monkeypatch.setenv("LEXLS_B200_LG_WARPS", lg_warps)
+    rng = np.random.default_rng(77)
+    n, dims, B = 60, [20, 20, 20] + [80] * 13, 3   # 1,100 rows; the first three levels eliminate all 60 columns
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    data[1][:, :, 5] = data[1][:, :, 4]      # a dependent row: level 3 gets a column to eliminate as well
+    wx, exact, got = _check(oracle, n, dims, data)
+    assert got["info"]["name"] == "lse_w%s_lodglobal" % lg_warps
+    assert exact, "not bit-identical (worst rel err %.3e)" % wx
