@@ -111,6 +111,62 @@ int main()
             for (Index j = 0; j < ne; j++)
                 if (one.get_x()(j) != re.x[q](j)) { std::printf("FAIL LexLSE x of problem %u\n", unsigned(q)); return 1; }
         }
+        // the handle classes: ranks, packed data, fixed variables, residuals
+        {
+            LexLSEBatch b(ne, Pe, de, B);
+            std::vector<double> packed;
+            for (Index k = 0; k < Pe; k++)
+            {
+                packed.assign(B * de[k] * (ne + 1), 0.0);
+                for (uint64_t q = 0; q < B; q++)
+                    for (Index j = 0; j <= ne; j++)
+                        for (Index i = 0; i < de[k]; i++) packed[q * de[k] * (ne + 1) + j * de[k] + i] = eq[q][k](i, j);
+                b.setDataPacked(k, packed.data(), de[k], uint64_t(de[k]) * (ne + 1));
+            }
+            std::vector<Index> fi(B, 3);         // x4 = 0.25 in every problem
+            std::vector<double> fv(B, 0.25);
+            b.fixVariables(1, fi.data(), fv.data());
+            b.solve();
+            for (uint64_t q = 0; q < B; q++)
+            {
+                internal::LexLSE one(ne, Pe, de);
+                one.setFixedVariablesCount(1);
+                one.fixVariable(3, 0.25);
+                for (Index k = 0; k < Pe; k++) one.setData(k, eq[q][k]);
+                one.factorize();
+                one.solve();
+                for (Index j = 0; j < ne; j++)
+                    if (one.get_x()(j) != b.get_x(q)(j)) { std::printf("FAIL LexLSEBatch x (fixed variable) of problem %u\n", unsigned(q)); return 1; }
+                for (Index k = 0; k < Pe; k++)
+                    if (one.getRank(k) != b.getRank(q, k)) { std::printf("FAIL LexLSEBatch rank\n"); return 1; }
+                if (b.get_x(q)(3) != 0.25) { std::printf("FAIL fixed value\n"); return 1; }
+            }
+        }
+        {
+            LexLSIBatch b(n, P, dims, types, B);
+            std::vector<dMatrixType> level(B);
+            for (Index k = 0; k < P; k++)
+            {
+                for (uint64_t q = 0; q < B; q++) level[q] = data[q][k];
+                if (k == 0) b.setData(0, var_index, level); else b.setData(k, level);
+            }
+            b.solve();
+            internal::LexLSI one(n, P, dims, types);
+            one.setData(0, var_index, data[5][0]);
+            for (Index k = 1; k < P; k++) one.setData(k, data[5][k]);
+            one.solve();
+            for (Index k = 0; k < P; k++)
+            {
+                const dVectorType vb = b.get_v(5, k);
+                for (Index i = 0; i < dims[k]; i++)
+                    if (vb(i) != one.get_v(k)(i)) { std::printf("FAIL LexLSIBatch get_v level %u\n", k); return 1; }
+            }
+            if (b.getTotalRank(5) != one.getTotalRank() || b.getActivationsCount(5) != one.getActivationsCount()) { std::printf("FAIL counters\n"); return 1; }
+            b.reset();
+            bool threw = false;
+            try { b.get_x(0); } catch (Exception &) { threw = true; }
+            if (!threw) { std::printf("FAIL get_x before solve must throw\n"); return 1; }
+        }
         std::printf("OK\n");
         return 0;
     }
