@@ -306,7 +306,23 @@ static int plan(lexls_b200_batch *h)
         DS = false;
         m  = build_map(h->sh, lsi, DS, LG, panel_only);
     }
-    if (m.total > max_smem || getenv("LEXLS_B200_FORCE_LODGLOBAL"))
+    // residency decides (every variant is latency bound: measured with scripts/shape_perf.py):
+    //  * <= 64 columns but a work matrix that leaves <= 4 problems per SM: 4 warps (two threads per column in the reflector
+    //    apply) — LexLSE 60/60/60 x 41: 4.44 -> 4.04 ms, LexLSI 60/60/60 x 41: 68 -> 62 ms;
+    //  * a work matrix that leaves ONE problem per SM while two level views fit: the global-work-matrix kernel, two
+    //    problems per SM — LexLSE 120 x 201: 4.23 -> 3.45 ms, LexLSI 240 x 101: 400 -> 287 ms.
+    const unsigned sm_smem = (unsigned)prop.sharedMemPerMultiprocessor;
+    auto fit = [&](const SmemMap &mm) { return sm_smem / (mm.total + 1024u); };
+    const bool w_forced = getenv("LEXLS_B200_WARPS") != nullptr;
+    if (!w_forced && !panel_only && cols <= 64 && m.total <= max_smem && fit(m) <= 4) W = 4;
+    bool auto_lg = false;
+    // (a batch that fits one wave of the shared-memory kernel stays there: 2.7 vs 3.0 ms for one test_01.dat problem)
+    if (m.total <= max_smem && fit(m) <= 1 && h->batch > (uint64_t)prop.multiProcessorCount && !getenv("LEXLS_B200_NO_AUTO_LODGLOBAL"))
+    {
+        const SmemMap mlg = build_map(h->sh, lsi, false, true);
+        auto_lg           = mlg.total <= max_smem && fit(mlg) >= 2;
+    }
+    if (m.total > max_smem || auto_lg || getenv("LEXLS_B200_FORCE_LODGLOBAL"))
     {
         LG = true;
         DS = false;

@@ -528,7 +528,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const bool apply  = tau != 0.0;
             const double *vp  = c.vv + 2 * pb;
             const int np      = pe - pb;
-            if constexpr (LGV)
+            if constexpr (LGV || W >= 4)
             {
                 // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
                 const int par = tid & 1;
@@ -1086,7 +1086,7 @@ __device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, cons
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool LG>
-__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : ((LG && W == 8) ? 2 : 1)) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : 1)) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
