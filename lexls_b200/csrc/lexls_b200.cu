@@ -315,6 +315,9 @@ static int plan(lexls_b200_batch *h)
     auto fit = [&](const SmemMap &mm) { return sm_smem / (mm.total + 1024u); };
     const bool w_forced = getenv("LEXLS_B200_WARPS") != nullptr;
     if (!w_forced && !panel_only && cols <= 64 && m.total <= max_smem && fit(m) <= 4) W = 4;
+    //  * > 128 columns but a small work matrix (>= 3 problems per SM by shared memory): 4 warps keep 3 problems per SM where
+    //    8 warps keep 2 (registers) — LexLSE 30 x 151: 1.02 -> 0.85 ms
+    if (!w_forced && cols > 128 && m.total <= max_smem && fit(m) >= 3) W = 4;
     bool auto_lg = false;
     // (a batch that fits one wave of the shared-memory kernel stays there: 2.7 vs 3.0 ms for one test_01.dat problem)
     if (m.total <= max_smem && fit(m) <= 1 && h->batch > (uint64_t)prop.multiProcessorCount && !getenv("LEXLS_B200_NO_AUTO_LODGLOBAL"))

@@ -1085,8 +1085,11 @@ __device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, cons
 // ---------------------------------------------------------------------------------------------------------------
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef LX_LSE_W2_MINB
+#define LX_LSE_W2_MINB 8
+#endif
 template <int W, bool LG>
-__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : 1)) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 4 : (W == 2 ? LX_LSE_W2_MINB : 1)))) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
