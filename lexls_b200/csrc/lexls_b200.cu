@@ -306,18 +306,33 @@ static int plan(lexls_b200_batch *h)
         DS = false;
         m  = build_map(h->sh, lsi, DS, LG, panel_only);
     }
-    // residency decides (every variant is latency bound: measured with scripts/shape_perf.py):
-    //  * <= 64 columns but a work matrix that leaves <= 4 problems per SM: 4 warps (two threads per column in the reflector
-    //    apply) — LexLSE 60/60/60 x 41: 4.44 -> 4.04 ms, LexLSI 60/60/60 x 41: 68 -> 62 ms;
-    //  * a work matrix that leaves ONE problem per SM while two level views fit: the global-work-matrix kernel, two
-    //    problems per SM — LexLSE 120 x 201: 4.23 -> 3.45 ms, LexLSI 240 x 101: 400 -> 287 ms.
+    // Residency decides: every variant is latency bound (one serial pivot chain per problem), so the warps per problem are
+    // chosen to keep the most problems resident per SM — shared memory (the work matrix) and registers (<= 128 per thread
+    // for the LexLSE kernels, 96 for the LexLSI kernels) bound that; on a tie more warps win (two threads per column in the
+    // reflector apply), up to two threads per column.  Measured with scripts/shape_perf.py, ms per batch:
+    //   LexLSE 60/60/60 x 41 (3 per SM either way): 2 warps 4.44, 4 warps 4.04;   20 x 101 (8 vs 4 per SM): 0.20 vs 0.32;
+    //   LexLSE 30 x 151: 2 warps (5 per SM) 0.58, 4 warps (4) 0.64, 8 warps (2) 1.02;   40/40/40 x 201 (1 per SM): 8 warps 4.2, 4 warps 5.1;
+    //   LexLSI 60/60/60 x 41: 68 vs 62;   LexLSI 30 x 141 (5 per SM either way): 4.37 vs 4.28, 8 warps (2 per SM) 7.2.
     const unsigned sm_smem = (unsigned)prop.sharedMemPerMultiprocessor;
     auto fit = [&](const SmemMap &mm) { return sm_smem / (mm.total + 1024u); };
     const bool w_forced = getenv("LEXLS_B200_WARPS") != nullptr;
-    if (!w_forced && !panel_only && cols <= 64 && m.total <= max_smem && fit(m) <= 4) W = 4;
-    //  * > 128 columns but a small work matrix (>= 3 problems per SM by shared memory): 4 warps keep 3 problems per SM where
-    //    8 warps keep 2 (registers) — LexLSE 30 x 151: 1.02 -> 0.85 ms
-    if (!w_forced && cols > 128 && m.total <= max_smem && fit(m) >= 3) W = 4;
+    if (!w_forced && !panel_only && m.total <= max_smem)
+    {
+        const unsigned by_smem = fit(m);
+        int wmax = 2;
+        while (wmax < 8 && 32 * wmax < 2 * cols) wmax *= 2; // two threads per column are the most the apply can use
+        unsigned best = 0;
+        for (int w = 2; w <= wmax; w *= 2)
+        {
+            const unsigned by_regs = lsi ? (w == 2 ? 10u : (w == 4 ? 5u : 2u)) : (w == 2 ? 8u : (w == 4 ? 4u : 2u));
+            const unsigned r       = by_smem < by_regs ? by_smem : by_regs;
+            if (r >= best)
+            {
+                best = r;
+                W    = w;
+            }
+        }
+    }
     bool auto_lg = false;
     // (a batch that fits one wave of the shared-memory kernel stays there: 2.7 vs 3.0 ms for one test_01.dat problem)
     if (m.total <= max_smem && fit(m) <= 1 && h->batch > (uint64_t)prop.multiProcessorCount && !getenv("LEXLS_B200_NO_AUTO_LODGLOBAL"))
