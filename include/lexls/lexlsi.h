@@ -65,6 +65,7 @@ public:
         if (static_cast<Index>(data.rows()) != dim[ObjIndex]) throw Exception("Incorrect number of equations");
         lexls_b200_check(lexls_b200_set_data(h_, ObjIndex, detail::data_of(data), detail::ld_of(data),
                                              static_cast<uint64_t>(detail::ld_of(data)) * (nVar + 2)));
+        lexls_b200_check(lexls_b200_validate(h_)); // throws here, as lexlsi.h:430 does, when lb > ub
     }
     void setData(Index ObjIndex, Index *VarIndex, const dMatrixConstRef &data) // lexlsi.h:444
     {
@@ -72,6 +73,7 @@ public:
         if (static_cast<Index>(data.rows()) != dim[ObjIndex]) throw Exception("Incorrect number of equations");
         lexls_b200_check(lexls_b200_set_simple_bounds(h_, VarIndex, 0, detail::data_of(data), detail::ld_of(data),
                                                       static_cast<uint64_t>(detail::ld_of(data)) * 2));
+        lexls_b200_check(lexls_b200_validate(h_)); // lexlsi.h:474 (lb > ub), :485 (VarIndex not unique)
     }
     void api_activate(Index ObjIndex, Index CtrIndex, ConstraintActivationType type) // lexlsi.h:120
     {

@@ -18,6 +18,15 @@
  *     LexLSI level, 2 [lb|ub] for a simple-bounds level) — i.e. what Eigen::Map<dMatrixType> over the reference's
  *     setData argument would see (typedefs.h:19,30).
  *   - *_dev variants take DEVICE pointers (same layouts) and enqueue on the handle's stream without synchronising.
+ *   - input validation that needs the data (lb > ub, duplicate VarIndex) runs on the device inside the set_* calls, which do
+ *     NOT wait for its verdict: the host variants return as soon as the caller's buffer has been copied.  The verdict is
+ *     reported by lexls_b200_validate() (synchronises; the batch-of-1 facades call it where the reference throws, lexlsi.h:430),
+ *     or else by the first synchronising call after lexls_b200_solve_batch (the solve itself is refused on the device, every
+ *     status stays LEXLS_B200_STATUS_UNKNOWN).  A whole batch therefore costs one synchronisation, not one per set_* call.
+ *   - a handle created by lexls_b200_create_batch_multi spans several GPUs of one box: contiguous shards, one stream and one
+ *     host thread per device, no inter-device traffic; every entry point below works on it unchanged (host arrays are
+ *     [batch]-major, each device reads / writes its own slice), except the *_dev variants, set_stream and device_results,
+ *     which address one device: fetch the shard's own handle with lexls_b200_get_shard.
  *   - the CUDA path is the only path: there is no CPU fallback; creating a handle without a usable GPU fails.
  */
 #ifndef LEXLS_B200_H
@@ -30,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LEXLS_B200_ABI_VERSION 2
+#define LEXLS_B200_ABI_VERSION 3
 
 /* error codes */
 #define LEXLS_B200_OK 0
@@ -107,6 +116,12 @@ int lexls_b200_device_count(int *count);
  * keeps data and parameters). */
 int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType,
                             uint64_t batch, int device, lexls_b200_batch_t **out);
+/* the same batch sharded over `ndev` devices (ordinals in `devices`, distinct): problems
+ * [first_i, first_i + count_i) live on devices[i]; the first batch % ndev devices hold one problem more. */
+int lexls_b200_create_batch_multi(int kind, uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType,
+                                  uint64_t batch, const int *devices, int ndev, lexls_b200_batch_t **out);
+int lexls_b200_shard_count(lexls_b200_batch_t *h, int *count); /* 1 for a single-device handle */
+int lexls_b200_get_shard(lexls_b200_batch_t *h, int index, lexls_b200_batch_t **shard, uint64_t *first, uint64_t *count, int *device);
 int lexls_b200_destroy(lexls_b200_batch_t *h);
 int lexls_b200_reset(lexls_b200_batch_t *h);
 int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p); /* setParameters lexlsi.h:325, lexlse.h:1467 */
@@ -117,6 +132,7 @@ int lexls_b200_set_stream(lexls_b200_batch_t *h, void *cuda_stream);            
  * detected and activated inside the solve exactly as the reference does at :374-380).  lb > ub -> EBOUNDS.
  * set_simple_bounds: LexLSI::setData(ObjIndex, VarIndex, data) lexlsi.h:444-491; var_index is 0-based, [batch][ObjDim[0]]
  * with index_stride elements between problems (0 = one index vector shared by the batch); duplicates -> EINVAL (:485).
+ * (lb > ub and duplicates are found on the device: see lexls_b200_validate.)
  * set_fixed_variables: LexLSE::setFixedVariablesCount + fixVariable lexlse.h:1449-1462, :1381-1388 (LSE kind only);
  * type may be NULL (CTR_ACTIVE_UB, the reference default). */
 int lexls_b200_set_data(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride);
@@ -130,11 +146,18 @@ int lexls_b200_set_fixed_variables(lexls_b200_batch_t *h, uint32_t count, const 
 
 /* ---- warm start (LSI) -----------------------------------------------------------------------------------------
  * set_active_guess: api_activate lexlsi.h:120-136 for every row whose type is LB or UB, applied level-major / row
- * ascending — the order the reference's own front-end uses (interfaces/matlab-octave/lexlsi.cpp:591-622).
+ * ascending — the order the reference's own front-end uses (interfaces/matlab-octave/lexlsi.cpp:591-622); any other call
+ * order: set_active_guess_ordered.
  * types is [batch][ObjDim[level]]; NULL clears the guess of that level.
  * set_x0 / set_v0: lexlsi.h:306-320 (x0 [batch][nVar]; v0 [batch][ObjDim[level]]); NULL clears. */
 int lexls_b200_set_active_guess(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types);
 int lexls_b200_set_active_guess_dev(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types);
+/* api_activate lexlsi.h:120-136 in the caller's CALL ORDER (the order fixes active[] of workingset.h:67-77, hence the row order
+ * of the LexLSE problem, its rounding and its ties): entry e of problem p is (obj, ctr, type)[p * problem_stride + e], e < count;
+ * type CTR_INACTIVE pads a ragged list, CTR_ACTIVE_EQ is ignored as the reference ignores it.  Replaces any set_active_guess
+ * (and vice versa); count = 0 clears. */
+int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, const uint32_t *obj, const uint32_t *ctr,
+                                        const uint8_t *type, uint64_t problem_stride);
 int lexls_b200_set_x0(lexls_b200_batch_t *h, const double *x0);
 int lexls_b200_set_x0_dev(lexls_b200_batch_t *h, const double *x0);
 int lexls_b200_set_v0(lexls_b200_batch_t *h, uint32_t level, const double *v0);
@@ -146,6 +169,9 @@ int lexls_b200_set_v0(lexls_b200_batch_t *h, uint32_t level, const double *v0);
 int lexls_b200_solve_batch(lexls_b200_batch_t *h);
 int lexls_b200_solve_batch_sync(lexls_b200_batch_t *h);
 int lexls_b200_synchronize(lexls_b200_batch_t *h);
+/* waits for the set_* calls issued so far and reports what their device-side checks found: EBOUNDS for lb > ub
+ * (lexlsi.h:430, :474), EINVAL for duplicate / out-of-range VarIndex (lexlsi.h:485); the offending data must be set again */
+int lexls_b200_validate(lexls_b200_batch_t *h);
 
 /* ---- results (host destinations; each call synchronises the handle's stream) -----------------------------------
  * get_x: get_x lexlse.h:1587 / lexlsi.h:508 -> [batch][nVar]
@@ -179,12 +205,18 @@ int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
  *            re-factorized with its final working set first. */
 #define LEXLS_B200_OUT_LEXQR 1u
 #define LEXLS_B200_OUT_LAMBDA 2u
+#define LEXLS_B200_OUT_XSTAR 4u
 int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask);
 int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh);
 int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda);
+/* get_xStar lexlsi.h:519-526 (LSI, LEXLS_B200_OUT_XSTAR): the LexLSE problem of the FINAL working set is formed, factorized and
+ * solved once more at the end of the solve -> xstar [batch][nVar]; data [batch][(nVar+1) x M] = LexLSI::get_data() lexlsi.h:612
+ * (its constraints [A | rhs] in working-set order, zero rows below); lexqr / hh = what get_lexqr() lexlsi.h:607 returns AFTER
+ * get_xStar (tests/test_numerical_error.cpp:83-86 reads all three).  Any destination may be NULL. */
+int lexls_b200_get_xstar(lexls_b200_batch_t *h, double *xstar, double *data, double *lexqr, double *hh);
 /* getWorkingSetLog lexlsi.h:739 (entries typedefs.h:380-432), written when params.log_working_set_enabled != 0:
  * entries [batch][capacity][6] = {obj_index, ctr_index, ctr_type (0 = removed), alpha_or_lambda, rank, cycling_detected};
- * count [batch] = entries the solve produced (<= max_number_of_factorizations + 1; more than `capacity` are cut). */
+ * count [batch] = valid rows of entries[p]: what the solve produced (<= max_number_of_factorizations + 1), cut at `capacity`. */
 int lexls_b200_get_working_set_log(lexls_b200_batch_t *h, uint32_t capacity, double *entries, uint32_t *count);
 
 /* device views of the result buffers (valid until destroy; contents valid after the solve completes on the stream):

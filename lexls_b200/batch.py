@@ -23,19 +23,45 @@ def _dp(a):
 class _Batch:
     kind = None
 
-    def __init__(self, nVar, ObjDim, ObjType=None, batch=1, device=0):
+    def __init__(self, nVar, ObjDim, ObjType=None, batch=1, device=0, devices=None, strict=True):
+        """devices: a list of CUDA ordinals shards the batch over several GPUs of the box (contiguous ranges, one stream and
+        host thread per device inside the library: lexls_b200_create_batch_multi); the arrays of every call stay [B, ...].
+        strict: setData raises on lb > ub / duplicate VarIndex where the reference throws (one synchronisation per call);
+        strict=False defers those checks to solve() / validate() — one synchronisation per batch."""
         self.nVar = int(nVar)
         self.ObjDim = [int(m) for m in ObjDim]
         self.nObj = len(self.ObjDim)
         self.ObjType = [int(t) for t in ObjType] if ObjType is not None else None
         self.batch = int(batch)
         self.device = int(device)
+        self.devices = [int(d) for d in devices] if devices is not None else None
+        self.strict = bool(strict)
         dims = (C.c_uint32 * self.nObj)(*self.ObjDim)
         types = (C.c_int32 * self.nObj)(*self.ObjType) if self.ObjType is not None else None
         h = C.c_void_p()
-        check(lib().lexls_b200_create_batch(self.kind, C.c_uint32(self.nVar), C.c_uint32(self.nObj), dims, types,
-                                            C.c_uint64(self.batch), C.c_int(self.device), C.byref(h)))
+        if self.devices is not None:
+            devs = (C.c_int * len(self.devices))(*self.devices)
+            check(lib().lexls_b200_create_batch_multi(self.kind, C.c_uint32(self.nVar), C.c_uint32(self.nObj), dims, types,
+                                                      C.c_uint64(self.batch), devs, C.c_int(len(self.devices)), C.byref(h)))
+        else:
+            check(lib().lexls_b200_create_batch(self.kind, C.c_uint32(self.nVar), C.c_uint32(self.nObj), dims, types,
+                                                C.c_uint64(self.batch), C.c_int(self.device), C.byref(h)))
         self._h = h
+
+    def validate(self):
+        """Waits for the set* calls issued so far and raises what their device-side checks found (lexlsi.h:430, :474, :485)."""
+        check(lib().lexls_b200_validate(self._h))
+
+    def shards(self):
+        """[(device, first, count)] of a multi-device batch (one entry for a single-device one)."""
+        n = C.c_int()
+        check(lib().lexls_b200_shard_count(self._h, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            first, count, dev = C.c_uint64(), C.c_uint64(), C.c_int()
+            check(lib().lexls_b200_get_shard(self._h, C.c_int(i), None, C.byref(first), C.byref(count), C.byref(dev)))
+            out.append((dev.value, first.value, count.value))
+        return out
 
     def close(self):
         if getattr(self, "_h", None):
@@ -71,6 +97,8 @@ class _Batch:
         if a.shape != (self.batch, cols, m):
             raise ValueError("level %d: expected shape %s, got %s" % (level, (self.batch, cols, m), a.shape))
         check(lib().lexls_b200_set_data(self._h, C.c_uint32(level), _dp(a), C.c_uint32(max(m, 1)), C.c_uint64(m * cols)))
+        if self.strict:
+            self.validate()
 
     def setData_dev(self, level, ptr, ld=None, problem_stride=None):
         m, cols = self.ObjDim[level], self._cols(level)
@@ -116,9 +144,11 @@ class _Batch:
         check(lib().lexls_b200_get_ranks(self._h, r.ctypes.data_as(C.POINTER(C.c_uint32))))
         return r
 
-    def request_outputs(self, lexqr=False, multipliers=False):
-        """Optional outputs written by the next solves: the factorized work matrix (get_lexqr) / LexLSI multipliers."""
-        check(lib().lexls_b200_request_outputs(self._h, (capi.OUT_LEXQR if lexqr else 0) | (capi.OUT_LAMBDA if multipliers else 0)))
+    def request_outputs(self, lexqr=False, multipliers=False, xstar=False):
+        """Optional outputs written by the next solves: the factorized work matrix (get_lexqr) / LexLSI multipliers /
+        LexLSI get_xStar with get_data and get_lexqr of that last equality-constrained problem."""
+        check(lib().lexls_b200_request_outputs(self._h, (capi.OUT_LEXQR if lexqr else 0) | (capi.OUT_LAMBDA if multipliers else 0)
+                                               | (capi.OUT_XSTAR if xstar else 0)))
 
     def get_lexqr(self):
         """(lexqr [B, nVar+1, M] — i.e. per problem column-major M x (nVar+1) —, hh [B, M])."""
@@ -192,6 +222,8 @@ class LexLSIBatch(_Batch):
             check(lib().lexls_b200_set_simple_bounds(self._h, vi.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                      C.c_uint64(0 if shared else m), _dp(a), C.c_uint32(max(m, 1)),
                                                      C.c_uint64(2 * m)))
+            if self.strict:
+                self.validate()
         else:
             super().setData(level, data)
 
@@ -203,6 +235,31 @@ class LexLSIBatch(_Batch):
         if t.shape != (self.batch, self.ObjDim[level]):
             raise ValueError("guess must be [B, m]")
         check(lib().lexls_b200_set_active_guess(self._h, C.c_uint32(level), t.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def set_active_guess_ordered(self, obj, ctr, types):
+        """api_activate calls in CALL order (lexlsi.h:120-136): obj, ctr, types are [B, count]; type 0 pads ragged lists."""
+        if obj is None:
+            check(lib().lexls_b200_set_active_guess_ordered(self._h, C.c_uint32(0), None, None, None, C.c_uint64(0)))
+            return
+        o = np.ascontiguousarray(obj, dtype=np.uint32).reshape(self.batch, -1)
+        c = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(self.batch, -1)
+        t = np.ascontiguousarray(types, dtype=np.uint8).reshape(self.batch, -1)
+        if not (o.shape == c.shape == t.shape):
+            raise ValueError("obj, ctr, types must have the same [B, count] shape")
+        u32 = C.POINTER(C.c_uint32)
+        check(lib().lexls_b200_set_active_guess_ordered(self._h, C.c_uint32(o.shape[1]), o.ctypes.data_as(u32), c.ctypes.data_as(u32),
+                                                        t.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(o.shape[1])))
+
+    def get_xStar(self):
+        """(xstar [B, nVar], data [B, nVar+1, M], lexqr [B, nVar+1, M], hh [B, M]): get_xStar (lexlsi.h:519) and what get_data /
+        get_lexqr return after it.  Needs request_outputs(xstar=True) before the solve."""
+        M = sum(d for k, d in enumerate(self.ObjDim) if not (self.ObjType and self.ObjType[k] == 1))
+        xs = np.empty((self.batch, self.nVar))
+        data = np.empty((self.batch, self.nVar + 1, M))
+        q = np.empty((self.batch, self.nVar + 1, M))
+        hh = np.empty((self.batch, M))
+        check(lib().lexls_b200_get_xstar(self._h, _dp(xs), _dp(data), _dp(q), _dp(hh)))
+        return xs, data, q, hh
 
     def set_x0(self, x0):
         if x0 is None:

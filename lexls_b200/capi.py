@@ -17,9 +17,10 @@ SYMBOLS = [
     "lexls_b200_get_active_set", "lexls_b200_get_active_order", "lexls_b200_get_status", "lexls_b200_get_counters",
     "lexls_b200_get_ranks", "lexls_b200_get_column_permutations", "lexls_b200_device_results", "lexls_b200_kernel_info",
     "lexls_b200_last_solve_ms", "lexls_b200_measure_fp64_peak", "lexls_b200_request_outputs", "lexls_b200_get_lexqr",
-    "lexls_b200_get_lambda", "lexls_b200_get_working_set_log",
+    "lexls_b200_get_lambda", "lexls_b200_get_working_set_log", "lexls_b200_validate", "lexls_b200_create_batch_multi",
+    "lexls_b200_shard_count", "lexls_b200_get_shard", "lexls_b200_get_xstar", "lexls_b200_set_active_guess_ordered",
 ]
-OUT_LEXQR, OUT_LAMBDA = 1, 2
+OUT_LEXQR, OUT_LAMBDA, OUT_XSTAR = 1, 2, 4
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, EBOUNDS, ECAPACITY = range(6)
 LSE, LSI = 0, 1

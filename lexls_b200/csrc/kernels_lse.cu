@@ -4,7 +4,11 @@ namespace lexls_dev
 {
 kernel_fn pick_lse_pair_kernel()
 {
+#ifdef LEXLS_B200_WITH_PAIR
     return (kernel_fn)lse_pair_kernel<0>;
+#else
+    return nullptr; // experiment not compiled into the product library (build with -DLEXLS_B200_WITH_PAIR)
+#endif
 }
 kernel_fn pick_lse_kernel(int W, bool LG)
 {

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace lexls_dev;
@@ -32,8 +33,20 @@ static int fail(int code, const std::string &msg)
 // ---------------------------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------------------------
+struct lexls_b200_batch;
+struct Shard
+{
+    lexls_b200_batch *h;
+    uint64_t first, count;
+};
+
 struct lexls_b200_batch
 {
+    // a multi-device batch (lexls_b200_create_batch_multi) owns one single-device handle per shard and nothing else: every
+    // entry point fans out over the shards with the caller's arrays offset by the shard's first problem
+    std::vector<Shard> shards;
+    bool multi() const { return !shards.empty(); }
+
     int kind = 0, device = 0;
     uint64_t batch = 0;
     Shape sh{};
@@ -47,7 +60,7 @@ struct lexls_b200_batch
     bool planned = false;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_switch = nullptr;
     bool timed = false;
 
     // device buffers
@@ -62,13 +75,22 @@ struct lexls_b200_batch
     unsigned char *act = nullptr;
     unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
+    double *xstar = nullptr, *lexdata = nullptr, *lexqr_star = nullptr, *hh_star = nullptr; // LEXLS_B200_OUT_XSTAR
+    unsigned *glist = nullptr;                                     // api_activate calls in call order (set_active_guess_ordered)
+    unsigned gcap = 0;
+    bool have_glist = false;
     double *wslog = nullptr;                                      // working-set log (params.log_working_set_enabled)
     unsigned *wslog_count = nullptr;
     unsigned wslog_cap = 0;
     unsigned want = 0;
     int *status = nullptr, *flag = nullptr;
+    int *hflag = nullptr;          // pinned host copy of `flag`, refreshed by every solve_batch (no extra synchronisation)
+    bool flag_pending = false;     // a solve has been enqueued whose flag copy has not been inspected yet
+    cudaEvent_t ev_copy = nullptr; // completion of the last host -> staging copy (the caller's buffer is then free)
+    uint64_t nfix_cap = 0;         // elements allocated in fidx / fval / ftype
     unsigned long long *queue = nullptr;
     uint64_t lod_stride = 0;
+    size_t lod_bytes = 0;
     // staging for host inputs
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -91,7 +113,7 @@ static int ensure_stage(lexls_b200_batch *h, size_t bytes)
 // dst[p*dstride + c*dld + roff + i] = src[p*sstride + c*sld + i], i < m, c < cols.  flag |= 1 when col lbcol > col ubcol.
 __global__ void repack_level_kernel(double *dst, unsigned long long dstride, int dld, int roff, const double *src,
                                     unsigned long long sstride, int sld, int m, int cols, unsigned long long batch, int lbcol,
-                                    int ubcol, int *flag)
+                                    int ubcol, int *flag, int bit = 1)
 {
     const unsigned long long per = (unsigned long long)m * cols;
     const unsigned long long tot = per * batch;
@@ -106,7 +128,7 @@ __global__ void repack_level_kernel(double *dst, unsigned long long dstride, int
         if (lbcol >= 0 && c == ubcol)
         {
             const double lb = src[p * sstride + (unsigned long long)lbcol * sld + i];
-            if (lb > val) atomicOr(flag, 1);
+            if (lb > val) atomicOr(flag, bit);
         }
     }
 }
@@ -269,11 +291,27 @@ static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &nam
     return pick_lsi_wn_kernel(W, DS, LG);
 }
 
+// cudaGetDeviceProperties costs ~1 ms: cached per device (plan() runs again whenever the shape of a handle changes)
+static int device_props(int device, const cudaDeviceProp **out)
+{
+    static cudaDeviceProp props[64];
+    static bool have[64] = {false};
+    if (device < 0 || device >= 64) return fail(LEXLS_B200_EINVAL, "bad device ordinal");
+    if (!have[device])
+    {
+        CK(cudaGetDeviceProperties(&props[device], device));
+        have[device] = true;
+    }
+    *out = &props[device];
+    return 0;
+}
+
 static int plan(lexls_b200_batch *h)
 {
     if (h->planned) return 0;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, h->device));
+    const cudaDeviceProp *propp = nullptr;
+    if (int rc = device_props(h->device, &propp)) return rc;
+    const cudaDeviceProp &prop = *propp;
     const unsigned max_smem = (unsigned)prop.sharedMemPerBlockOptin;
     const bool lsi          = h->kind == LEXLS_B200_LSI;
     const int cols          = h->sh.n + 1;
@@ -363,7 +401,7 @@ static int plan(lexls_b200_batch *h)
     h->smem = m.total;
     // two LexLSE problems per warp (lexls_pair.cuh): no fixed variables, register-window shapes with <= 20 rows per level
     h->pair = false;
-    if (!lsi && !LG && W == 1 && panel_only && h->sh.nfix == 0 && getenv("LEXLS_B200_PAIR"))
+    if (!lsi && !LG && W == 1 && panel_only && h->sh.nfix == 0 && getenv("LEXLS_B200_PAIR") && pick_lse_pair_kernel())
     {
         h->pair = true;
         for (int k = 0; k < h->sh.P; k++)
@@ -387,11 +425,58 @@ static int plan(lexls_b200_batch *h)
     if (LG)
     {
         h->lod_stride = (uint64_t)h->sh.ld * (h->sh.n + 1);
-        if (h->lod_scratch) cudaFree(h->lod_scratch);
-        CK(cudaMalloc(&h->lod_scratch, sizeof(double) * h->lod_stride * h->grid));
+        const size_t need = sizeof(double) * h->lod_stride * h->grid;
+        if (need > h->lod_bytes)
+        {
+            if (h->lod_scratch) cudaFree(h->lod_scratch);
+            h->lod_scratch = nullptr;
+            h->lod_bytes   = 0;
+            CK(cudaMalloc(&h->lod_scratch, need));
+            h->lod_bytes = need;
+        }
     }
     h->planned = true;
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-device batches: contiguous shards, one handle + stream per device, no inter-device traffic.
+// Blocking calls (host copies in, results out) run one host thread per device, so the copies of all devices are in
+// flight together and land in disjoint slices of the caller's (ideally pinned) buffer.
+// ---------------------------------------------------------------------------------------------------------------
+template <class F> static int fan_out(lexls_b200_batch *m, bool threaded, F f)
+{
+    const size_t n = m->shards.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    auto run = [&](size_t i) {
+        rc[i] = f(m->shards[i]);
+        if (rc[i]) msg[i] = g_err; // thread-local message of the worker
+    };
+    if (threaded && n > 1)
+    {
+        std::vector<std::thread> t;
+        for (size_t i = 0; i < n; i++) t.emplace_back(run, i);
+        for (auto &x : t) x.join();
+    }
+    else
+        for (size_t i = 0; i < n; i++) run(i);
+    for (size_t i = 0; i < n; i++)
+        if (rc[i]) return fail(rc[i], "device " + std::to_string(m->shards[i].h->device) + ": " + msg[i]);
+    return 0;
+}
+#define MULTI(h, threaded, expr)                                                                                        \
+    if ((h) && (h)->multi()) return fan_out((h), (threaded), [&](const Shard &s) -> int { return (expr); })
+#define MULTI_REFUSE(h, what)                                                                                           \
+    if ((h) && (h)->multi()) return fail(LEXLS_B200_EINVAL, what " is a single-device call: use lexls_b200_get_shard")
+template <typename T> static const T *off(const T *p, uint64_t n)
+{
+    return p ? p + n : p;
+}
+template <typename T> static T *off(T *p, uint64_t n)
+{
+    return p ? p + n : p;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -454,6 +539,10 @@ static void to_dev_params(const lexls_b200_params_t &u, Params &p)
     p.mod_inactive = u.modify_type_inactive_enabled;
     p.min_viol     = u.set_min_init_ctr_violation;
     p.phase1_v0    = u.use_phase1_v0;
+    // Gauss step on the FP64 tensor cores (mma.sync m8n8k4, bit-identical to the DFMA chain: profiles/r2_dmma_order.json);
+    // LEXLS_B200_DMMA=0 selects the DFMA version for A/B measurements
+    const char *e = getenv("LEXLS_B200_DMMA");
+    p.dmma        = e ? (atoi(e) != 0) : 1; // only the global-work-matrix kernels contain the tensor-core tiles
 }
 
 int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
@@ -540,6 +629,10 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     h->stream = h->own_stream;
     CKB(cudaEventCreate(&h->ev0));
     CKB(cudaEventCreate(&h->ev1));
+    CKB(cudaEventCreateWithFlags(&h->ev_switch, cudaEventDisableTiming));
+    CKB(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    CKB(cudaMallocHost(&h->hflag, sizeof(int)));
+    *h->hflag = 0;
     const uint64_t B = batch;
     if (kind == LEXLS_B200_LSE)
     {
@@ -568,6 +661,7 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     CKB(cudaMalloc(&h->colperm, sizeof(unsigned) * nVar * B));
     CKB(cudaMalloc(&h->queue, sizeof(unsigned long long)));
     CKB(cudaMalloc(&h->flag, sizeof(int)));
+    CKB(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
     CKB(cudaMemsetAsync(h->status, 0xff, sizeof(int) * B, h->stream));
     CKB(cudaMemsetAsync(h->counters, 0, sizeof(unsigned) * 8 * B, h->stream));
     CKB(cudaMemsetAsync(h->x, 0, sizeof(double) * nVar * B, h->stream));
@@ -578,16 +672,25 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
 
 int lexls_b200_destroy(lexls_b200_batch_t *h)
 {
+    if (h && h->multi())
+    {
+        for (auto &s : h->shards) lexls_b200_destroy(s.h);
+        delete h;
+        return 0;
+    }
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_switch) cudaEventDestroy(h->ev_switch);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->hflag) cudaFreeHost(h->hflag);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -595,10 +698,12 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
 
 int lexls_b200_reset(lexls_b200_batch_t *h)
 {
+    MULTI(h, false, lexls_b200_reset(s.h));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
     h->have_x0    = false;
     h->have_guess = false;
+    h->have_glist = false;
     std::fill(h->have_v0.begin(), h->have_v0.end(), 0);
     if (h->guess) CK(cudaMemsetAsync(h->guess, 0, (size_t)h->sh.Mall * h->batch, h->stream));
     CK(cudaMemsetAsync(h->status, 0xff, sizeof(int) * h->batch, h->stream));
@@ -609,6 +714,7 @@ int lexls_b200_reset(lexls_b200_batch_t *h)
 
 int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
 {
+    MULTI(h, false, lexls_b200_set_params(s.h, p));
     if (!h || !p) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (p->regularization_type != 0)
         return fail(LEXLS_B200_EUNSUPPORTED, "regularization is outside the hot-path scope (REGULARIZATION_NONE only)");
@@ -622,15 +728,52 @@ int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
 
 int lexls_b200_set_stream(lexls_b200_batch_t *h, void *cuda_stream)
 {
+    MULTI_REFUSE(h, "set_stream");
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (next != h->stream)
+    {
+        // work already enqueued for this handle (the zero fill of create_batch, earlier set_* calls or solves) must be ordered
+        // before whatever the caller enqueues on the new stream
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventRecord(h->ev_switch, h->stream));
+        CK(cudaStreamWaitEvent(next, h->ev_switch, 0));
+        h->stream = next;
+    }
     return 0;
 }
 
-static int read_flag(lexls_b200_batch *h, int *val)
+// Input validation is done on the device by the repack kernels, which OR bits into h->flag: 1 general lb > ub, 8 simple
+// lb > ub, 2 duplicate VarIndex, 4 VarIndex >= nVar.  The set_* calls do not wait for it.  The flag is inspected
+//   * by lexls_b200_validate (synchronises; what the batch-of-1 facades call to throw where the reference throws), and
+//   * after a solve: solve_batch enqueues a copy of the flag into pinned host memory in front of the kernel (which returns
+//     at once, status UNKNOWN, when the flag is set); the first synchronising call afterwards reports it.
+// So a batch costs ONE synchronisation (the result read), not one per set_* call.
+static int flag_error(lexls_b200_batch *h, int flag)
 {
-    CK(cudaMemcpyAsync(val, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (!flag) return 0;
+    std::fill(h->data_set.begin(), h->data_set.end(), 0); // the offending data must be set again
+    if (flag & 1) return fail(LEXLS_B200_EBOUNDS, "(general) Lower bound is greater than upper bound.");
+    if (flag & 8) return fail(LEXLS_B200_EBOUNDS, "(simple) Lower bound is greater than upper bound.");
+    if (flag & 2) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
+    return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
+}
+// after the stream has been synchronised: report (once) what the flag copy of the last solve says
+static int check_pending_flag(lexls_b200_batch *h)
+{
+    if (!h->flag_pending) return 0;
+    h->flag_pending = false;
+    const int flag  = *h->hflag;
+    if (!flag) return 0;
+    *h->hflag = 0;
+    cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream);
+    return flag_error(h, flag);
+}
+// host inputs: returns once the caller's buffer has been consumed (copied into the staging buffer)
+static int wait_copy(lexls_b200_batch *h)
+{
+    CK(cudaEventRecord(h->ev_copy, h->stream));
+    CK(cudaEventSynchronize(h->ev_copy));
     return 0;
 }
 
@@ -657,9 +800,9 @@ static int set_data_impl(lexls_b200_batch *h, uint32_t level, const double *data
         const size_t bytes = sizeof(double) * (stride * (h->batch - 1) + (uint64_t)ld * (cols - 1) + m);
         if (int rc = ensure_stage(h, bytes)) return rc;
         CK(cudaMemcpyAsync(h->stage, data, bytes, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = wait_copy(h)) return rc;
         src = (const double *)h->stage;
     }
-    CK(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
     const unsigned long long work = (unsigned long long)m * cols * h->batch;
     if (lsi)
         repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->obj, h->obj_stride, s.ldo, s.goff[g], src, stride, (int)ld, m,
@@ -668,19 +811,18 @@ static int set_data_impl(lexls_b200_batch *h, uint32_t level, const double *data
         repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->rec, h->rec_stride, s.ld, s.goff[g], src, stride, (int)ld, m,
                                                                      cols, h->batch, -1, -1, h->flag);
     CK(cudaGetLastError());
-    int flag = 0;
-    if (int rc = read_flag(h, &flag)) return rc; // also makes the staging buffer reusable / the caller buffer releasable
-    if (flag & 1) return fail(LEXLS_B200_EBOUNDS, "(general) Lower bound is greater than upper bound.");
-    h->data_set[level] = 1;
+    h->data_set[level] = 1; // lb > ub is reported by lexls_b200_validate / after the solve (see flag_error)
     return 0;
 }
 
 int lexls_b200_set_data(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride)
 {
+    MULTI(h, true, lexls_b200_set_data(s.h, level, off(data, s.first * problem_stride), ld, problem_stride));
     return set_data_impl(h, level, data, ld, problem_stride, false);
 }
 int lexls_b200_set_data_dev(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride)
 {
+    MULTI_REFUSE(h, "set_data_dev");
     return set_data_impl(h, level, data, ld, problem_stride, true);
 }
 
@@ -710,12 +852,12 @@ static int set_sb_impl(lexls_b200_batch *h, const unsigned *var_index, uint64_t 
         CK(cudaMemcpyAsync(h->stage, lbub, dbytes, cudaMemcpyHostToDevice, h->stream));
         char *ip = (char *)h->stage + ((dbytes + 15) & ~(size_t)15);
         CK(cudaMemcpyAsync(ip, var_index, ibytes, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = wait_copy(h)) return rc;
         src  = (const double *)h->stage;
         isrc = (const unsigned *)ip;
     }
-    CK(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
     repack_level_kernel<<<blocks_for((unsigned long long)m * 2 * h->batch), 256, 0, h->stream>>>(h->sb, 2ull * m, m, 0, src, stride, (int)ld,
-                                                                                                 m, 2, h->batch, 0, 1, h->flag);
+                                                                                                 m, 2, h->batch, 0, 1, h->flag, 8);
     CK(cudaGetLastError());
     if (index_stride)
     {
@@ -731,59 +873,70 @@ static int set_sb_impl(lexls_b200_batch *h, const unsigned *var_index, uint64_t 
     const unsigned long long cnt = index_stride ? h->batch : 1;
     check_unique_kernel<<<blocks_for(cnt), 256, 0, h->stream>>>(h->sbidx, h->sbidx_stride, m, (unsigned)s.n, cnt, h->flag);
     CK(cudaGetLastError());
-    int flag = 0;
-    if (int rc = read_flag(h, &flag)) return rc;
-    if (flag & 1) return fail(LEXLS_B200_EBOUNDS, "(simple) Lower bound is greater than upper bound.");
-    if (flag & 2) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
-    if (flag & 4) return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
-    h->data_set[0] = 1;
+    h->data_set[0] = 1; // lb > ub / duplicate indices are reported by lexls_b200_validate / after the solve (see flag_error)
     return 0;
 }
 int lexls_b200_set_simple_bounds(lexls_b200_batch_t *h, const uint32_t *var_index, uint64_t index_stride, const double *lbub,
                                  uint32_t ld, uint64_t problem_stride)
 {
+    MULTI(h, true, lexls_b200_set_simple_bounds(s.h, off(var_index, s.first * index_stride), index_stride, off(lbub, s.first * problem_stride), ld, problem_stride));
     return set_sb_impl(h, var_index, index_stride, lbub, ld, problem_stride, false);
 }
 int lexls_b200_set_simple_bounds_dev(lexls_b200_batch_t *h, const uint32_t *var_index, uint64_t index_stride, const double *lbub,
                                      uint32_t ld, uint64_t problem_stride)
 {
+    MULTI_REFUSE(h, "set_simple_bounds_dev");
     return set_sb_impl(h, var_index, index_stride, lbub, ld, problem_stride, true);
 }
 
 int lexls_b200_set_fixed_variables(lexls_b200_batch_t *h, uint32_t count, const uint32_t *var_index, const double *value,
                                    const uint8_t *type)
 {
+    MULTI(h, true, lexls_b200_set_fixed_variables(s.h, count, off(var_index, s.first * count), off(value, s.first * count), off(type, s.first * count)));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     if (h->kind != LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "fixed variables belong to LexLSE; LexLSI uses a simple-bounds objective");
     if (count > (uint32_t)h->sh.n) return fail(LEXLS_B200_EINVAL, "Cannot fix more than nVar variables");
     CK(cudaSetDevice(h->device));
-    if (h->fidx) cudaFree(h->fidx);
-    if (h->fval) cudaFree(h->fval);
-    if (h->ftype) cudaFree(h->ftype);
-    h->fidx = nullptr; h->fval = nullptr; h->ftype = nullptr;
+    // the plan (kernel variant, shared-memory map, scratch) depends on the COUNT only: a batch-of-1 facade that re-sends the
+    // same number of fixed variables before every factorize() keeps its plan and its device buffers
+    if (h->sh.nfix != (int)count) h->planned = false;
     h->sh.nfix = (int)count;
-    h->planned = false;
     if (count == 0) return 0;
     if (!var_index || !value) return fail(LEXLS_B200_EINVAL, "NULL argument");
     const uint64_t N = (uint64_t)count * h->batch;
-    for (uint64_t p = 0; p < h->batch; p++)
-        for (uint32_t a = 0; a < count; a++)
+    {
+        std::vector<unsigned char> seen((size_t)h->sh.n);
+        for (uint64_t p = 0; p < h->batch; p++)
         {
-            if (var_index[p * count + a] >= (uint32_t)h->sh.n) return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
-            for (uint32_t b = a + 1; b < count; b++)
-                if (var_index[p * count + a] == var_index[p * count + b]) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
+            std::fill(seen.begin(), seen.end(), 0);
+            for (uint32_t a = 0; a < count; a++)
+            {
+                const uint32_t v = var_index[p * count + a];
+                if (v >= (uint32_t)h->sh.n) return fail(LEXLS_B200_EINVAL, "VarIndex >= nVar");
+                if (seen[v]) return fail(LEXLS_B200_EINVAL, "Elements of VarIndex are not unique.");
+                seen[v] = 1;
+            }
         }
-    CK(cudaMalloc(&h->fidx, sizeof(unsigned) * N));
-    CK(cudaMalloc(&h->fval, sizeof(double) * N));
+    }
+    if (N > h->nfix_cap)
+    {
+        if (h->fidx) cudaFree(h->fidx);
+        if (h->fval) cudaFree(h->fval);
+        if (h->ftype) cudaFree(h->ftype);
+        h->fidx = nullptr; h->fval = nullptr; h->ftype = nullptr;
+        h->nfix_cap = 0;
+        CK(cudaMalloc(&h->fidx, sizeof(unsigned) * N));
+        CK(cudaMalloc(&h->fval, sizeof(double) * N));
+        CK(cudaMalloc(&h->ftype, N));
+        h->nfix_cap = N;
+    }
     CK(cudaMemcpyAsync(h->fidx, var_index, sizeof(unsigned) * N, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->fval, value, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
     if (type)
-    {
-        CK(cudaMalloc(&h->ftype, N));
         CK(cudaMemcpyAsync(h->ftype, type, N, cudaMemcpyHostToDevice, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    else
+        CK(cudaMemsetAsync(h->ftype, LEXLS_B200_CTR_ACTIVE_UB, N, h->stream)); // the reference's default, lexlse.h:1381
+    return wait_copy(h);
 }
 
 } // extern "C"
@@ -831,14 +984,18 @@ static int set_guess_impl(lexls_b200_batch *h, uint32_t level, const uint8_t *ty
         return 0;
     }
     h->have_guess = true;
+    h->have_glist = false; // the two ways of giving a guess are alternatives
     return scatter_level<unsigned char>(h, &h->guess, level, types, on_device);
 }
 int lexls_b200_set_active_guess(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_set_active_guess(s.h, level, off(types, s.first * h->sh.dim[level])));
     return set_guess_impl(h, level, types, false);
 }
 int lexls_b200_set_active_guess_dev(lexls_b200_batch_t *h, uint32_t level, const uint8_t *types)
 {
+    MULTI_REFUSE(h, "set_active_guess_dev");
     return set_guess_impl(h, level, types, true);
 }
 
@@ -861,14 +1018,18 @@ static int set_x0_impl(lexls_b200_batch *h, const double *x0, bool on_device)
 }
 int lexls_b200_set_x0(lexls_b200_batch_t *h, const double *x0)
 {
+    MULTI(h, true, lexls_b200_set_x0(s.h, off(x0, s.first * h->sh.n)));
     return set_x0_impl(h, x0, false);
 }
 int lexls_b200_set_x0_dev(lexls_b200_batch_t *h, const double *x0)
 {
+    MULTI_REFUSE(h, "set_x0_dev");
     return set_x0_impl(h, x0, true);
 }
 int lexls_b200_set_v0(lexls_b200_batch_t *h, uint32_t level, const double *v0)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_set_v0(s.h, level, off(v0, s.first * h->sh.dim[level])));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     if (h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "v0 belongs to LexLSI");
     if ((int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
@@ -884,6 +1045,7 @@ int lexls_b200_set_v0(lexls_b200_batch_t *h, uint32_t level, const double *v0)
 // ---- solve ------------------------------------------------------------------------------------------------------
 int lexls_b200_solve_batch(lexls_b200_batch_t *h)
 {
+    MULTI(h, false, lexls_b200_solve_batch(s.h)); // asynchronous per device: all devices run concurrently
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
     const Shape &s = h->sh;
@@ -907,7 +1069,7 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.fidx         = h->fidx;
     b.fval         = h->fval;
     b.ftype        = h->ftype;
-    b.guess        = h->have_guess ? h->guess : nullptr;
+    b.guess        = (h->have_guess && !h->have_glist) ? h->guess : nullptr;
     b.x0           = h->have_x0 ? h->x0 : nullptr;
     b.v0           = use_v0 ? h->v0 : nullptr;
     b.rec_stride   = h->rec_stride;
@@ -924,6 +1086,15 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.lexqr        = (h->want & LEXLS_B200_OUT_LEXQR) ? h->lexqr : nullptr;
     b.hhout        = h->hhout;
     b.lambda       = (h->want & LEXLS_B200_OUT_LAMBDA) ? h->lambda : nullptr;
+    if (h->want & LEXLS_B200_OUT_XSTAR)
+    {
+        b.xstar      = h->xstar;
+        b.lexdata    = h->lexdata;
+        b.lexqr_star = h->lexqr_star;
+        b.hh_star    = h->hh_star;
+    }
+    b.glist = h->have_glist ? h->glist : nullptr;
+    b.gcap  = h->gcap;
     if (h->kind == LEXLS_B200_LSI && h->user_params.log_working_set_enabled)
     {
         // at most one entry per iteration, and every iteration but the first costs a factorization
@@ -949,7 +1120,10 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
 
     std::string name;
     kernel_fn k = h->pair ? pick_lse_pair_kernel() : pick_kernel(h->kind, h->W, h->DS, h->LG, name);
+    b.flag         = h->flag;
     CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemcpyAsync(h->hflag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream)); // inspected after the next synchronisation
+    h->flag_pending = true;
     CK(cudaEventRecord(h->ev0, h->stream));
     void *args[] = {(void *)&h->sh, (void *)&h->pr, (void *)&h->sm, (void *)&b};
     CK(cudaLaunchKernel((const void *)k, dim3(h->grid), dim3(32 * h->W), args, h->smem, h->stream));
@@ -960,10 +1134,23 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
 
 int lexls_b200_synchronize(lexls_b200_batch_t *h)
 {
+    MULTI(h, false, lexls_b200_synchronize(s.h));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_pending_flag(h);
+}
+int lexls_b200_validate(lexls_b200_batch_t *h)
+{
+    MULTI(h, false, lexls_b200_validate(s.h));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) CK(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
+    h->flag_pending = false;
+    return flag_error(h, flag);
 }
 int lexls_b200_solve_batch_sync(lexls_b200_batch_t *h)
 {
@@ -977,7 +1164,7 @@ static int d2h(lexls_b200_batch *h, void *dst, const void *src, size_t bytes)
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_pending_flag(h);
 }
 } // extern "C"
 template <typename T> static int get_level(lexls_b200_batch *h, uint32_t level, const T *src, T *dst)
@@ -1009,45 +1196,59 @@ template <typename T> static int get_level(lexls_b200_batch *h, uint32_t level, 
 extern "C" {
 int lexls_b200_get_x(lexls_b200_batch_t *h, double *x)
 {
+    MULTI(h, true, lexls_b200_get_x(s.h, off(x, s.first * h->sh.n)));
     if (!h || !x) return fail(LEXLS_B200_EINVAL, "NULL argument");
     return d2h(h, x, h->x, sizeof(double) * h->sh.n * h->batch);
 }
 int lexls_b200_get_v(lexls_b200_batch_t *h, uint32_t level, double *v)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_get_v(s.h, level, off(v, s.first * h->sh.dim[level])));
     return get_level<double>(h, level, h ? h->v : nullptr, v);
 }
 int lexls_b200_get_constraint_violation(lexls_b200_batch_t *h, uint32_t level, double *viol)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_get_constraint_violation(s.h, level, off(viol, s.first * h->sh.dim[level])));
     return get_level<double>(h, level, h ? h->viol : nullptr, viol);
 }
 int lexls_b200_get_active_set(lexls_b200_batch_t *h, uint32_t level, uint8_t *types)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_get_active_set(s.h, level, off(types, s.first * h->sh.dim[level])));
     return get_level<unsigned char>(h, level, h ? h->act : nullptr, types);
 }
 int lexls_b200_get_active_order(lexls_b200_batch_t *h, uint32_t level, uint32_t *order)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_get_active_order(s.h, level, off(order, s.first * h->sh.dim[level])));
     return get_level<unsigned>(h, level, h ? h->order : nullptr, order);
 }
 int lexls_b200_get_status(lexls_b200_batch_t *h, int32_t *status)
 {
+    MULTI(h, true, lexls_b200_get_status(s.h, off(status, s.first)));
     if (!h || !status) return fail(LEXLS_B200_EINVAL, "NULL argument");
     return d2h(h, status, h->status, sizeof(int) * h->batch);
 }
 int lexls_b200_get_counters(lexls_b200_batch_t *h, uint32_t *counters)
 {
+    MULTI(h, true, lexls_b200_get_counters(s.h, off(counters, s.first * 8)));
     if (!h || !counters) return fail(LEXLS_B200_EINVAL, "NULL argument");
     return d2h(h, counters, h->counters, sizeof(unsigned) * 8 * h->batch);
 }
 int lexls_b200_get_ranks(lexls_b200_batch_t *h, uint32_t *ranks)
 {
+    MULTI(h, true, lexls_b200_get_ranks(s.h, off(ranks, s.first * h->sh.G)));
     if (!h || !ranks) return fail(LEXLS_B200_EINVAL, "NULL argument");
     return d2h(h, ranks, h->ranks, sizeof(unsigned) * h->sh.G * h->batch);
 }
 int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
 {
+    MULTI(h, false, lexls_b200_request_outputs(s.h, mask));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
-    if (mask & ~(uint32_t)(LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA)) return fail(LEXLS_B200_EINVAL, "unknown output bit");
+    if (mask & ~(uint32_t)(LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA | LEXLS_B200_OUT_XSTAR)) return fail(LEXLS_B200_EINVAL, "unknown output bit");
     if ((mask & LEXLS_B200_OUT_LAMBDA) && h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "Lagrange multipliers exist for LexLSI only");
+    if ((mask & LEXLS_B200_OUT_XSTAR) && h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "get_xStar exists for LexLSI only");
     CK(cudaSetDevice(h->device));
     const Shape &s = h->sh;
     const int M    = std::max(s.M, 1);
@@ -1058,11 +1259,19 @@ int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
     }
     if ((mask & LEXLS_B200_OUT_LAMBDA) && !h->lambda)
         CK(cudaMalloc(&h->lambda, sizeof(double) * (size_t)s.P * std::max(s.Mall, 1) * h->batch));
+    if ((mask & LEXLS_B200_OUT_XSTAR) && !h->xstar)
+    {
+        CK(cudaMalloc(&h->xstar, sizeof(double) * (size_t)s.n * h->batch));
+        CK(cudaMalloc(&h->lexdata, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(cudaMalloc(&h->lexqr_star, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(cudaMalloc(&h->hh_star, sizeof(double) * (size_t)M * h->batch));
+    }
     h->want = mask;
     return 0;
 }
 int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh)
 {
+    MULTI(h, true, lexls_b200_get_lexqr(s.h, off(lexqr, s.first * (uint64_t)h->sh.M * (h->sh.n + 1)), off(hh, s.first * (uint64_t)h->sh.M)));
     if (!h || !lexqr) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (!(h->want & LEXLS_B200_OUT_LEXQR)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_LEXQR before the solve");
     const Shape &s = h->sh;
@@ -1072,6 +1281,8 @@ int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh)
 }
 int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
 {
+    if (h && h->multi() && (int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    MULTI(h, true, lexls_b200_get_lambda(s.h, level, off(lambda, s.first * (uint64_t)h->sh.P * h->sh.dim[level])));
     if (!h || !lambda) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (!(h->want & LEXLS_B200_OUT_LAMBDA)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_LAMBDA before the solve");
     const Shape &s = h->sh;
@@ -1089,11 +1300,13 @@ int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
 }
 int lexls_b200_get_working_set_log(lexls_b200_batch_t *h, uint32_t capacity, double *entries, uint32_t *count)
 {
+    MULTI(h, true, lexls_b200_get_working_set_log(s.h, capacity, off(entries, s.first * (uint64_t)capacity * 6), off(count, s.first)));
     if (!h || !entries || !count) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (!h->wslog) return fail(LEXLS_B200_EINVAL, "set log_working_set_enabled before the solve");
     CK(cudaSetDevice(h->device));
     if (int rc = d2h(h, count, h->wslog_count, sizeof(unsigned) * h->batch)) return rc;
     const uint32_t take = std::min(capacity, h->wslog_cap);
+    for (uint64_t p = 0; p < h->batch; p++) count[p] = std::min(count[p], take); // = valid rows of entries[p]
     if (take == 0) return 0;
     CK(cudaMemcpy2DAsync(entries, sizeof(double) * 6 * capacity, h->wslog, sizeof(double) * 6 * h->wslog_cap, sizeof(double) * 6 * take,
                          h->batch, cudaMemcpyDeviceToHost, h->stream));
@@ -1102,12 +1315,14 @@ int lexls_b200_get_working_set_log(lexls_b200_batch_t *h, uint32_t capacity, dou
 }
 int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
 {
+    MULTI(h, true, lexls_b200_get_column_permutations(s.h, off(colperm, s.first * h->sh.n)));
     if (!h || !colperm) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (h->kind != LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "column permutations are reported for LexLSE batches");
     return d2h(h, colperm, h->colperm, sizeof(unsigned) * h->sh.n * h->batch);
 }
 int lexls_b200_device_results(lexls_b200_batch_t *h, const double **x, const int32_t **status, const uint32_t **counters)
 {
+    MULTI_REFUSE(h, "device_results");
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     if (x) *x = h->x;
     if (status) *status = h->status;
@@ -1117,6 +1332,7 @@ int lexls_b200_device_results(lexls_b200_batch_t *h, const double **x, const int
 
 int lexls_b200_kernel_info(lexls_b200_batch_t *h, lexls_b200_kernel_info_t *info)
 {
+    if (h && h->multi()) return lexls_b200_kernel_info(h->shards[0].h, info); // same shape, same plan on every device
     if (!h || !info) return fail(LEXLS_B200_EINVAL, "NULL argument");
     CK(cudaSetDevice(h->device));
     if (int rc = plan(h)) return rc;
@@ -1133,6 +1349,19 @@ int lexls_b200_kernel_info(lexls_b200_batch_t *h, lexls_b200_kernel_info_t *info
 
 int lexls_b200_last_solve_ms(lexls_b200_batch_t *h, float *ms)
 {
+    if (h && h->multi())
+    {
+        if (!ms) return fail(LEXLS_B200_EINVAL, "NULL argument");
+        float worst = 0.f;
+        for (auto &s : h->shards)
+        {
+            float t = 0.f;
+            if (int rc = lexls_b200_last_solve_ms(s.h, &t)) return rc;
+            worst = std::max(worst, t);
+        }
+        *ms = worst; // the devices run concurrently: the batch takes as long as the slowest shard
+        return 0;
+    }
     if (!h || !ms) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (!h->timed) return fail(LEXLS_B200_EINVAL, "no solve has been issued");
     CK(cudaSetDevice(h->device));
@@ -1141,4 +1370,132 @@ int lexls_b200_last_solve_ms(lexls_b200_batch_t *h, float *ms)
     return 0;
 }
 
+int lexls_b200_get_xstar(lexls_b200_batch_t *h, double *xstar, double *data, double *lexqr, double *hh)
+{
+    MULTI(h, true, lexls_b200_get_xstar(s.h, off(xstar, s.first * h->sh.n), off(data, s.first * (uint64_t)h->sh.M * (h->sh.n + 1)),
+                                        off(lexqr, s.first * (uint64_t)h->sh.M * (h->sh.n + 1)), off(hh, s.first * (uint64_t)h->sh.M)));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (!(h->want & LEXLS_B200_OUT_XSTAR)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_XSTAR before the solve");
+    const Shape &s   = h->sh;
+    const size_t mat = sizeof(double) * (size_t)s.M * (s.n + 1) * h->batch;
+    if (xstar)
+        if (int rc = d2h(h, xstar, h->xstar, sizeof(double) * (size_t)s.n * h->batch)) return rc;
+    if (data && s.M)
+        if (int rc = d2h(h, data, h->lexdata, mat)) return rc;
+    if (lexqr && s.M)
+        if (int rc = d2h(h, lexqr, h->lexqr_star, mat)) return rc;
+    if (hh && s.M)
+        if (int rc = d2h(h, hh, h->hh_star, sizeof(double) * (size_t)s.M * h->batch)) return rc;
+    return 0;
+}
+
+int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, const uint32_t *obj, const uint32_t *ctr, const uint8_t *type,
+                                        uint64_t problem_stride)
+{
+    MULTI(h, true, lexls_b200_set_active_guess_ordered(s.h, count, off(obj, s.first * problem_stride), off(ctr, s.first * problem_stride),
+                                                       off(type, s.first * problem_stride), problem_stride));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if (h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "active-set guesses belong to LexLSI");
+    if (count == 0)
+    {
+        h->have_glist = false;
+        return 0;
+    }
+    if (!obj || !ctr || !type) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (h->batch > 1 && problem_stride < count) return fail(LEXLS_B200_EINVAL, "problem_stride too small");
+    const Shape &s = h->sh;
+    const unsigned cap = count + 1; // the terminator
+    std::vector<unsigned> packed((size_t)cap * h->batch, 0xFFFFFFFFu);
+    for (uint64_t p = 0; p < h->batch; p++)
+    {
+        unsigned w = 0;
+        for (uint32_t e = 0; e < count; e++)
+        {
+            const uint64_t at = p * problem_stride + e;
+            const unsigned t  = type[at];
+            if (t == LEXLS_B200_CTR_INACTIVE) continue; // padding of a ragged list
+            if (obj[at] >= (uint32_t)s.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+            if (ctr[at] >= (uint32_t)s.dim[obj[at]]) return fail(LEXLS_B200_EINVAL, "CtrIndex >= nCtr");
+            if (t != LEXLS_B200_CTR_ACTIVE_LB && t != LEXLS_B200_CTR_ACTIVE_UB) continue; // the reference only warns (lexlsi.h:130-134)
+            packed[p * cap + w++] = (obj[at] << 24) | (t << 16) | ctr[at];
+        }
+    }
+    CK(cudaSetDevice(h->device));
+    if (h->gcap < cap)
+    {
+        if (h->glist) cudaFree(h->glist);
+        h->glist = nullptr;
+        h->gcap  = 0;
+        CK(cudaMalloc(&h->glist, sizeof(unsigned) * (size_t)cap * h->batch));
+        h->gcap = cap;
+    }
+    if (h->gcap != cap) // a shorter list than the buffer was sized for: keep the buffer's row stride
+    {
+        std::vector<unsigned> wide((size_t)h->gcap * h->batch, 0xFFFFFFFFu);
+        for (uint64_t p = 0; p < h->batch; p++) std::copy(packed.begin() + p * cap, packed.begin() + (p + 1) * cap, wide.begin() + p * h->gcap);
+        packed.swap(wide);
+    }
+    CK(cudaMemcpyAsync(h->glist, packed.data(), sizeof(unsigned) * packed.size(), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = wait_copy(h)) return rc;
+    h->have_glist = true;
+    return 0;
+}
+
+int lexls_b200_create_batch_multi(int kind, uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
+                                  const int *devices, int ndev, lexls_b200_batch_t **out)
+{
+    if (!out) return fail(LEXLS_B200_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1) return fail(LEXLS_B200_EINVAL, "a device list is required");
+    if (batch == 0) return fail(LEXLS_B200_EINVAL, "empty batch");
+    for (int a = 0; a < ndev; a++)
+        for (int b = a + 1; b < ndev; b++)
+            if (devices[a] == devices[b]) return fail(LEXLS_B200_EINVAL, "a device appears twice in the device list");
+    lexls_b200_batch *m = new lexls_b200_batch();
+    // contiguous ranges; the first (batch % ndev) devices take one problem more
+    const uint64_t base = batch / (uint64_t)ndev, extra = batch % (uint64_t)ndev;
+    uint64_t first = 0;
+    for (int i = 0; i < ndev; i++)
+    {
+        const uint64_t count = base + ((uint64_t)i < extra ? 1 : 0);
+        if (count == 0) continue;
+        lexls_b200_batch *c = nullptr;
+        if (int rc = lexls_b200_create_batch(kind, nVar, nObj, ObjDim, ObjType, count, devices[i], &c))
+        {
+            const std::string msg = g_err;
+            for (auto &s : m->shards) lexls_b200_destroy(s.h);
+            delete m;
+            return fail(rc, "device " + std::to_string(devices[i]) + ": " + msg);
+        }
+        m->shards.push_back(Shard{c, first, count});
+        first += count;
+    }
+    m->kind   = kind;
+    m->batch  = batch;
+    m->device = m->shards[0].h->device;
+    m->sh     = m->shards[0].h->sh; // the shape (dimensions, offsets) is shared by every shard
+    lexls_b200_default_params(&m->user_params);
+    *out = m;
+    return 0;
+}
+int lexls_b200_shard_count(lexls_b200_batch_t *h, int *count)
+{
+    if (!h || !count) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    *count = h->multi() ? (int)h->shards.size() : 1;
+    return 0;
+}
+int lexls_b200_get_shard(lexls_b200_batch_t *h, int index, lexls_b200_batch_t **shard, uint64_t *first, uint64_t *count, int *device)
+{
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    const int n = h->multi() ? (int)h->shards.size() : 1;
+    if (index < 0 || index >= n) return fail(LEXLS_B200_EINVAL, "shard index out of range");
+    lexls_b200_batch *c = h->multi() ? h->shards[index].h : h;
+    if (shard) *shard = c;
+    if (first) *first = h->multi() ? h->shards[index].first : 0;
+    if (count) *count = c->batch;
+    if (device) *device = c->device;
+    return 0;
+}
+
 } // extern "C"
+

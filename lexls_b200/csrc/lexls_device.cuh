@@ -75,6 +75,7 @@ struct Params
     unsigned cyc_max;
     double cyc_step;
     int mod_x, mod_active, mod_inactive, min_viol, phase1_v0;
+    int dmma; // Gauss step: Schur update (and the off-diagonal part of Left * inv(R)) on the FP64 tensor cores
 };
 
 // byte offsets into the dynamic shared memory of one group
@@ -114,10 +115,17 @@ struct Buffers
     double *lexqr;             // [B][(n+1) x M] factorized work matrix (column-major, ld = M) or null   (get_lexqr)
     double *hhout;             // [B][M] Householder scalars, with lexqr
     double *lambda;            // LSI: [B][P][Mall] Lagrange multipliers (getLambda, lexlsi.h:552-605) or null
+    double *xstar;             // LSI: [B][n] get_xStar (lexlsi.h:519): x of the LexLSE problem of the FINAL working set, or null
+    double *lexdata;           // LSI, with xstar: [B][(n+1) x M] that problem's constraints as given (LexLSE::get_data, lexlse.h:119, :1631)
+    double *lexqr_star;        // LSI, with xstar: [B][(n+1) x M] its factorization (what get_lexqr returns after get_xStar)
+    double *hh_star;           // LSI, with xstar: [B][M]
+    const unsigned *glist;     // LSI: [B][gcap] api_activate calls in CALL ORDER: obj << 24 | type << 16 | ctr, 0xFFFFFFFF ends the list; or null
+    unsigned gcap;
     double *wslog;             // LSI: [B][wslog_cap][6] working-set log {obj, ctr, type, alpha_or_lambda, rank, cycling} or null
     unsigned *wslog_count;     // LSI: [B] entries written (capped by wslog_cap)
     unsigned wslog_cap;
     unsigned long long *queue; // work counter
+    const int *flag;           // input-validation flag of the set_* calls: non-zero -> the solve is refused (status UNKNOWN)
     unsigned long long batch;
     double *lod_scratch;       // "LOD in global memory" variants: [grid][lod_stride] work matrices (L2 resident)
     unsigned long long lod_stride;
@@ -315,9 +323,92 @@ __device__ __forceinline__ unsigned long long dkey(double v)
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 tensor cores.  tcgen05 has no FP64 kind, so on sm_100a FP64 tensor work is mma.sync (SASS: DMMA).
+// D = A * B + C for one 8 x 8 output tile and 4 pivots.  Measured on B200 (scripts/dmma_order.cu ->
+// profiles/r2_dmma_order.json, 262,144 outputs with heavy cancellation): every output is bit-identical to the chain
+// c = fma(a[k], b[k], c), k = 0, 1, 2, 3 — the (S) order of the arithmetic contract — so a k-loop of these
+// instructions reproduces the DFMA Schur update of the oracle bit for bit while issuing 8x fewer instructions.
+// Fragments (lane = 4 g + t): A(8 x 4) a = A[g][t];  B(4 x 8) b = B[t][g];  C(8 x 8) c0, c1 = C[g][2t], C[g][2t + 1].
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, const double a, const double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C(rows, cols) -= L(rows, 0:kmax) * U(0:kmax, cols) in 8 x 8 tiles, one warp per row tile (lexlse.h:464-469 and the
+// finished-column part of :450-461).  rows [r_lo, r_hi) of `LOD` (leading dimension ld; shared memory, or global memory for
+// the global-work-matrix kernels), L(row, k) = LOD[row + ld * (lc + k)], U(k, col) = RB[k + rl * col] (shared memory),
+// columns [c_lo, c_hi).  Per entry the updates arrive in ascending k.  Padding pivots / rows / columns carry zeros in A.
+template <int W>
+__device__ __noinline__ void schur_dmma(double *const LOD, const int ld, const double *const RB, const int rl, const int r_lo,
+                                        const int r_hi, const int lc, const int kmax, const int c_lo, const int c_hi)
+{
+    // (a real call: the tensor-core variant must not disturb the register allocation of the DFMA code around it)
+    constexpr int KF = 10; // A fragments held in registers per pass: 40 pivots
+    constexpr int CT = 4;  // column tiles in flight per warp: independent accumulators hide the DMMA and load latency
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int nrt = (r_hi - r_lo + 7) >> 3, nct = (c_hi - c_lo + 7) >> 3;
+    for (int rt = warp; rt < nrt; rt += W)
+    {
+        const int r      = r_lo + 8 * rt + g;
+        const bool rok   = r < r_hi;
+        double *const rp = LOD + (rok ? r : r_hi - 1);
+        for (int k0 = 0; k0 < kmax; k0 += 4 * KF)
+        {
+            double af[KF];
+#pragma unroll
+            for (int q = 0; q < KF; q++)
+            {
+                const int k = k0 + 4 * q + t4;
+                af[q]       = (rok && k < kmax) ? -rp[ld * (lc + k)] : 0.0;
+            }
+            for (int ct0 = 0; ct0 < nct; ct0 += CT)
+            {
+                double d0[CT], d1[CT];
+                const double *bp[CT];
+                bool s0[CT], s1[CT], bok[CT];
+#pragma unroll
+                for (int j = 0; j < CT; j++)
+                {
+                    const int cc  = c_lo + 8 * (ct0 + j); // beyond the last tile: every predicate below is false
+                    const int c0i = cc + 2 * t4, c1i = c0i + 1, cb = cc + g;
+                    s0[j]  = rok && c0i < c_hi;
+                    s1[j]  = rok && c1i < c_hi;
+                    bok[j] = cb < c_hi;
+                    d0[j]  = s0[j] ? rp[ld * c0i] : 0.0;
+                    d1[j]  = s1[j] ? rp[ld * c1i] : 0.0;
+                    bp[j]  = RB + rl * (bok[j] ? cb : c_lo) + k0 + t4;
+                }
+#pragma unroll
+                for (int q = 0; q < KF; q++)
+                    if (k0 + 4 * q < kmax) // warp-uniform
+                    {
+                        const bool kok = k0 + 4 * q + t4 < kmax;
+#pragma unroll
+                        for (int j = 0; j < CT; j++)
+                        {
+                            const double b = (bok[j] && kok) ? bp[j][4 * q] : 0.0;
+                            dmma_884(d0[j], d1[j], af[q], b);
+                        }
+                    }
+#pragma unroll
+                for (int j = 0; j < CT; j++)
+                {
+                    const int c0i = c_lo + 8 * (ct0 + j) + 2 * t4;
+                    if (s0[j]) rp[ld * c0i] = d0[j];
+                    if (s1[j]) rp[ld * (c0i + 1)] = d1[j];
+                }
+            }
+        }
+    }
+}
+
 } // namespace lexls_dev
 #include "lexls_panel.cuh"
+#ifdef LEXLS_B200_WITH_PAIR // the two-problems-per-warp experiment (measured slower): not in the product build
 #include "lexls_pair.cuh"
+#endif
 namespace lexls_dev
 {
 
@@ -617,7 +708,8 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool LGV = (W == 16)>
 __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const int ld, const int nCtr, const int fr, const int dim,
-                                                const int fc, const int rank, const int ColIndex, const int ldv = 0)
+                                                const int fc, const int rank, const int ColIndex, const int ldv = 0,
+                                                const int dmma = 0)
 {
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x;
@@ -719,8 +811,16 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
         }
     }
     gsync<W>();
-    // Trailing -= Left * Up over columns ColIndex .. n; work item = (row pair, strip of SW columns); the global-work-matrix
+    // Trailing -= Left * Up over columns ColIndex .. n.  dmma: 8 x 8 tiles on the FP64 tensor cores (same chain per entry);
+    // otherwise work item = (row pair, strip of SW columns); the global-work-matrix
     // kernels use strips of 8: every L entry is an L2 round trip there, and wider strips halve them
+    // Measured (profiles/r2_dmma_ab.json): the tensor-core tiles pay off where the blocks are large — the global-work-matrix
+    // kernels (C4: 40 pivots x up to 200 columns x up to 360 rows per level, 880 -> 853 ms); for the small shared-memory shapes
+    // they are slower (C2 3.40 -> 3.53 ms, C3 unchanged) and the extra routine costs the two-warp kernel its occupancy, so
+    // only the LGV kernels carry it.
+    if (LGV && dmma)
+        schur_dmma<W>(LOD, ld, RB, rl, frn, nCtr, fc, rank, ColIndex, n + 1);
+    else
     {
         constexpr int SW = LGV ? 8 : 4;
         const int ncols = n - ColIndex + 1, nstrips = (ncols + SW - 1) / SW, npairs = t1 - t0;
@@ -784,9 +884,9 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
-                                              const int nCtr, const int nFixed, const double tol, FlopCount &fl)
+                                              const int nCtr, const int nFixed, const double tol, FlopCount &fl, const int dmma = 0)
 {
-    const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol);
+    const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol, dmma);
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
     double *const LOD = c.LOD;
@@ -878,7 +978,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__
             if constexpr (PANEL)
                 gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
-                gauss_step_smem<W, LGV>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv);
+                gauss_step_smem<W, LGV>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv, dmma);
             fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
         }
 
@@ -1070,16 +1170,23 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
 
 // get_lexqr (lexlse.h:1626): the factorized work matrix and the Householder scalars of problem p go to global memory
 template <int NT>
-__device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, const unsigned long long p, const int n, const int ld,
-                                           const int nCtr, const int M)
+__device__ __forceinline__ void dump_lod(const Ctx &c, double *const qbase, double *const hbase, const unsigned long long p, const int n,
+                                         const int ld, const int nCtr, const int M)
 {
-    double *dst = bf.lexqr + p * (unsigned long long)M * (n + 1);
+    double *dst = qbase + p * (unsigned long long)M * (n + 1);
     for (int e = threadIdx.x; e < M * (n + 1); e += NT)
     {
         const int r = e % M, col = e / M;
         dst[e]      = (r < nCtr) ? c.LOD[r + ld * col] : 0.0;
     }
-    for (int k = threadIdx.x; k < M; k += NT) bf.hhout[p * M + k] = (k < nCtr) ? c.hh[k] : 0.0;
+    if (hbase)
+        for (int k = threadIdx.x; k < M; k += NT) hbase[p * M + k] = (k < nCtr) ? c.hh[k] : 0.0;
+}
+template <int NT>
+__device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, const unsigned long long p, const int n, const int ld,
+                                           const int nCtr, const int M)
+{
+    dump_lod<NT>(c, bf.lexqr, bf.hhout, p, n, ld, nCtr, M);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1098,6 +1205,14 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
     if constexpr (LG) c.LOD = bf.lod_scratch + blockIdx.x * bf.lod_stride;
     const int tid = threadIdx.x;
     const int n = sh.n, ld = sh.ld, G = sh.G, nCtr = sh.M;
+    // the set_* calls found invalid input (lb > ub, duplicate VarIndex): the reference throws in setData; here the solve is
+    // refused — every status stays TERMINATION_STATUS_UNKNOWN and the host reports the error at its next synchronisation
+    if (bf.flag && *bf.flag)
+    {
+        for (unsigned long long q = blockIdx.x * (unsigned long long)NT + threadIdx.x; q < bf.batch; q += (unsigned long long)gridDim.x * NT)
+            bf.status[q] = ST_UNKNOWN;
+        return;
+    }
 
     if (tid == 0)
     {
@@ -1156,7 +1271,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl);
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma);
         lse_solve<W, LG>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v) lse_get_v<W>(c, n, ld, G);
@@ -1183,6 +1298,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
     }
 }
 
+#ifdef LEXLS_B200_WITH_PAIR
 // ---------------------------------------------------------------------------------------------------------------
 // LexLSE, two problems per warp (lexls_pair.cuh): each half warp factorizes its own problem in its own shared-memory
 // slice; solve / residuals / outputs then run per problem on the full warp with the ordinary routines.
@@ -1352,6 +1468,8 @@ __global__ void __launch_bounds__(32, 5) lse_pair_kernel(const __grid_constant__
         }
     }
 }
+
+#endif // LEXLS_B200_WITH_PAIR
 
 // ===============================================================================================================
 // LexLSI
@@ -1633,7 +1751,8 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
 // The context is rebuilt from the shared-memory map (kernel parameter, __grid_constant__: its address may be taken).
 template <int W, bool DS, bool LG>
 __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap &sm, const double tol, double *lod, double *objp,
-                                                  double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl)
+                                                  double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl,
+                                                  const int dmma, double *const data_dump = nullptr)
 {
     extern __shared__ __align__(128) unsigned char smem_fs[];
     Ctx c = make_ctx(smem_fs, sm);
@@ -1641,7 +1760,12 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     ObjView<DS> ov{c, sh, objp, sbp};
     const int nCtr = lsi_form_lexlse<W, DS>(c, sh, ov, nFixed, nFixedPrev);
     nFixedPrev     = nFixed;
-    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl);
+    if (data_dump) // PROBLEM_DATA = LOD on entry of factorize(), lexlse.h:119 (data_dump already points at this problem)
+    {
+        dump_lod<32 * W>(c, data_dump, nullptr, 0ull, sh.n, sh.ld, nCtr, sh.M);
+        gsync<W>();
+    }
+    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl, dmma);
     lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
@@ -1655,6 +1779,14 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
     if constexpr (LG) c.LOD = bf.lod_scratch + blockIdx.x * bf.lod_stride;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n = sh.n, ld = sh.ld, G = sh.G, P = sh.P;
+    // the set_* calls found invalid input (lb > ub, duplicate VarIndex): the reference throws in setData; here the solve is
+    // refused — every status stays TERMINATION_STATUS_UNKNOWN and the host reports the error at its next synchronisation
+    if (bf.flag && *bf.flag)
+    {
+        for (unsigned long long q = blockIdx.x * (unsigned long long)NT + threadIdx.x; q < bf.batch; q += (unsigned long long)gridDim.x * NT)
+            bf.status[q] = ST_UNKNOWN;
+        return;
+    }
 
     if (tid == 0)
     {
@@ -1770,7 +1902,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                 }
                 alleq    = __all_sync(0xffffffffu, alleq);
                 anyeq    = __any_sync(0xffffffffu, anyeq);
-                anyguess = __any_sync(0xffffffffu, anyguess) && bf.guess != nullptr;
+                anyguess = (__any_sync(0xffffffffu, anyguess) && bf.guess != nullptr) || bf.glist != nullptr;
                 if (alleq && m > 0)
                 {
                     for (int i = lane; i < m; i += 32)
@@ -1790,12 +1922,27 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                     if (anyeq)
                         for (int i = 0; i < m; i++)
                             if (eqflag[o + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
-                    if (anyguess)
+                    if (bf.glist)
+                    {
+                        // api_activate in the caller's CALL order (lexlsi.h:120-136 -> workingset.h:67-77): the order fixes
+                        // active[] and with it the row order of the LexLSE problem.  Levels do not interact, so this
+                        // level replays its own entries of the list.
+                        const unsigned *gl = bf.glist + p * bf.gcap;
+                        for (unsigned e = 0; e < bf.gcap; e++)
+                        {
+                            const unsigned w = gl[e];
+                            if (w == 0xFFFFFFFFu) break;
+                            const int ko = (int)(w >> 24), t = (int)((w >> 16) & 0xffu), i = (int)(w & 0xffffu);
+                            if (ko == k && i < m && (t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[o + i] == CTR_INACTIVE)
+                                ws_activate(c, sh, k, i, t);
+                        }
+                    }
+                    else if (anyguess)
                         for (int i = 0; i < m; i++)
                         {
                             const int t = gs[o + i];
                             if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[o + i] == CTR_INACTIVE)
-                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136
+                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136 (level-major, row ascending)
                         }
                 }
                 __syncwarp();
@@ -1830,7 +1977,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             }
         };
         auto factor_and_solve = [&]() {
-            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl);
+            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma);
         };
 
         // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------
@@ -2133,11 +2280,24 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             dump_lexqr<NT>(c, bf, p, n, ld, nc, sh.M);
             gsync<W>();
         }
+        if (bf.xstar)
+        {
+            // get_xStar, lexlsi.h:519-526: formLexLSE + factorize + solve with the FINAL working set; get_data() and
+            // get_lexqr() called after it return this problem's constraints and factorization (tests/test_numerical_error.cpp:83-86)
+            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma,
+                                            bf.lexdata + p * (unsigned long long)sh.M * (n + 1));
+            for (int k = tid; k < n; k += NT) bf.xstar[p * n + k] = c.lx[k];
+            int nc = 0;
+            for (int g = 0; g < G; g++) nc += c.ldim[g];
+            dump_lod<NT>(c, bf.lexqr_star, bf.hh_star, p, n, ld, nc, sh.M);
+            gsync<W>();
+        }
         if (bf.lambda)
         {
             double *lam = bf.lambda + p * (unsigned long long)P * sh.Mall;
             for (int e = tid; e < P * sh.Mall; e += NT) lam[e] = 0.0;
-            if (status != ST_SOLVED) factor_and_solve(); // lexlsi.h:566-571 (the working set changed after the last one)
+            // lexlsi.h:566-571: the working set changed after the last factorization (unless get_xStar just redid it)
+            if (status != ST_SOLVED && !bf.xstar) factor_and_solve();
             gsync<W>();
             for (int j = 0; j < G; j++)
             {
@@ -2196,7 +2356,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
         }
         if (tid == 0)
         {
-            if (bf.wslog_count) bf.wslog_count[p] = nLog;
+            if (bf.wslog_count) bf.wslog_count[p] = nLog < bf.wslog_cap ? nLog : bf.wslog_cap;
             bf.status[p]  = status;
             unsigned *cnt = bf.counters + p * 8;
             cnt[0]        = nFact;

@@ -27,6 +27,11 @@ namespace lexls_dev
 {
 
 #define LX_PANEL_MAXRH 20
+// Schur update of the warp-per-problem Gauss step on the FP64 tensor cores: measured SLOWER than the row-per-lane DFMA code
+// on C2 (3.40 -> 3.53 ms: 15 small tiles per level do not amortise the fragment loads), so it is compiled in on request only
+#ifndef LX_PANEL_DMMA
+#define LX_PANEL_DMMA 0
+#endif
 // staging buffer (doubles): 2 phases x [2 parities x RH rows of the pivot column]
 #define LX_PANEL_TMP_PHASE (2 * LX_PANEL_MAXRH)
 #define LX_PANEL_TMP_DOUBLES (2 * LX_PANEL_TMP_PHASE)
@@ -38,8 +43,9 @@ struct PanelArgs
     unsigned lod, ptmp, invd, hh, colperm, varofcol; // byte offsets into the group's shared memory
     int n, ld, nCtr;
     double tol;
+    int dmma;
 };
-__device__ __forceinline__ PanelArgs make_panel_args(const SmemMap &m, int n, int ld, int nCtr, double tol)
+__device__ __forceinline__ PanelArgs make_panel_args(const SmemMap &m, int n, int ld, int nCtr, double tol, int dmma = 0)
 {
     PanelArgs a;
     a.lod      = m.lod;
@@ -52,6 +58,7 @@ __device__ __forceinline__ PanelArgs make_panel_args(const SmemMap &m, int n, in
     a.ld       = ld;
     a.nCtr     = nCtr;
     a.tol      = tol;
+    a.dmma     = dmma;
     return a;
 }
 #define LX_PANEL_PTRS                                                                                                   \
@@ -431,8 +438,8 @@ static __device__ __noinline__ void gauss_rows_dyn(const PanelArgs pa, const int
             __syncwarp(); // lanes re-read their own stores only, but keep the passes in step
         }
 
-        // Trailing -= Left * Up over columns ColIndex .. n
-        for (int c = ColIndex; c <= n; c += 4)
+        // Trailing -= Left * Up over columns ColIndex .. n   (pa.dmma: done by schur_dmma in the dispatch routine)
+        for (int c = (LX_PANEL_DMMA && pa.dmma) ? n + 1 : ColIndex; c <= n; c += 4)
         {
             const double *Uc[4];
             double t[4];
@@ -569,8 +576,8 @@ __device__ __noinline__ void gauss_rows_win(const PanelArgs pa, const int r0, co
         }
     }
 
-    // Trailing -= Left * Up over columns ColIndex .. n
-    for (int c = ColIndex; c <= n; c += 4)
+    // Trailing -= Left * Up over columns ColIndex .. n   (pa.dmma: done by schur_dmma in the dispatch routine)
+    for (int c = (LX_PANEL_DMMA && pa.dmma) ? n + 1 : ColIndex; c <= n; c += 4)
     {
         int cc[4];
         double t[4];
@@ -658,9 +665,18 @@ template <bool COMPACT>
 __device__ __forceinline__ bool gauss_step_panel_dispatch(const PanelArgs &pa, const int fr, const int dim, const int fc,
                                                           const int rank, const int ColIndex)
 {
+    auto trailing_dmma = [&]() {
+        // Schur update on the FP64 tensor cores: 8 x 8 tiles, same ascending-k chain per entry (lexls_device.cuh: schur_dmma)
+        LX_PANEL_PTRS
+        (void)hh; (void)colperm; (void)varofcol; (void)ptmp; (void)invd;
+        __syncwarp();
+        schur_dmma<1>(LOD, ld, LOD + fr, ld, fr + dim, pa.nCtr, fc, rank, ColIndex, n + 1);
+        __syncwarp();
+    };
     if (COMPACT || rank > 40)
     {
         gauss_rows_dyn(pa, fr + dim, fr, fc, rank, ColIndex);
+        if (LX_PANEL_DMMA && pa.dmma) trailing_dmma();
         return true;
     }
     const int frn  = fr + dim;
@@ -680,6 +696,7 @@ __device__ __forceinline__ bool gauss_step_panel_dispatch(const PanelArgs &pa, c
         else LX_GS(10)
 #undef LX_GS
     }
+    if (LX_PANEL_DMMA && pa.dmma) trailing_dmma();
     return true;
 }
 

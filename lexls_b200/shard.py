@@ -58,7 +58,7 @@ class ShardedBatch:
         self.parts = []
         for dev, (lo, hi) in zip(self.devices, self.ranges):
             if hi > lo:
-                kw = dict(batch=hi - lo, device=dev)
+                kw = dict(batch=hi - lo, device=dev, strict=False)
                 self.parts.append((lo, hi, cls(nVar, ObjDim, ObjType, **kw) if ObjType is not None else cls(nVar, ObjDim, **kw)))
 
     def close(self):
@@ -109,7 +109,7 @@ class PipelinedBatch:
         self.ranges = shard_ranges(batch, chunks)
         self.parts = []
         for lo, hi in self.ranges:
-            kw = dict(batch=hi - lo, device=device)
+            kw = dict(batch=hi - lo, device=device, strict=False)
             self.parts.append((lo, hi, cls(nVar, ObjDim, ObjType, **kw) if ObjType is not None else cls(nVar, ObjDim, **kw)))
         self._lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=len(self.parts))

@@ -185,11 +185,47 @@ int oracle_lse_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
 //   totalRank, nActiveTotal, 0}; margins [batch][4] = {min_pivot_gap, min_rank_margin, min_alpha_gap, min_lambda_gap};
 //   active_order [batch][sum m_k] = concatenated active[] lists per level (padded with 0xFFFFFFFF)
 // ---------------------------------------------------------------------------------------------
+// Extras of the _ex entry: api_activate calls in CALL ORDER (lexlsi.h:120-136) as per-problem lists
+//   (g_obj, g_ctr, g_type)[p * g_count + e], type 0 = padding — used instead of guess[] when g_count > 0;
+//   xstar [batch][nVar] = get_xStar() (lexlsi.h:519), called after solve(); then lexdata / lexqr_star
+//   [batch][(nVar+1) x M] (column-major, leading dimension M = rows of all general levels, rows >= nCtr zero) =
+//   get_data() / get_lexqr() as tests/test_numerical_error.cpp:83-86 reads them.
+static int lsi_batch_impl(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
+                          const double *const *data, const uint32_t *var_index, const uint8_t *const *guess, const double *x0,
+                          const double *const *v0, const oracle_params *params, double *x, double *const *v,
+                          double *const *viol, uint8_t *const *active, int32_t *status, uint32_t *counters, double *margins,
+                          uint32_t *active_order, int threads, uint32_t g_count, const uint32_t *g_obj, const uint32_t *g_ctr,
+                          const uint8_t *g_type, double *xstar, double *lexdata, double *lexqr_star);
+
 int oracle_lsi_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
                            const double *const *data, const uint32_t *var_index, const uint8_t *const *guess, const double *x0,
                            const double *const *v0, const oracle_params *params, double *x, double *const *v,
                            double *const *viol, uint8_t *const *active, int32_t *status, uint32_t *counters, double *margins,
                            uint32_t *active_order, int threads)
+{
+    return lsi_batch_impl(nVar, nObj, ObjDim, ObjType, batch, data, var_index, guess, x0, v0, params, x, v, viol, active, status,
+                          counters, margins, active_order, threads, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int oracle_lsi_solve_batch_ex(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
+                              const double *const *data, const uint32_t *var_index, const uint8_t *const *guess, const double *x0,
+                              const double *const *v0, const oracle_params *params, double *x, double *const *v,
+                              double *const *viol, uint8_t *const *active, int32_t *status, uint32_t *counters, double *margins,
+                              uint32_t *active_order, int threads, uint32_t g_count, const uint32_t *g_obj, const uint32_t *g_ctr,
+                              const uint8_t *g_type, double *xstar, double *lexdata, double *lexqr_star)
+{
+    return lsi_batch_impl(nVar, nObj, ObjDim, ObjType, batch, data, var_index, guess, x0, v0, params, x, v, viol, active, status,
+                          counters, margins, active_order, threads, g_count, g_obj, g_ctr, g_type, xstar, lexdata, lexqr_star);
+}
+
+} // extern "C"
+
+static int lsi_batch_impl(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, const int32_t *ObjType, uint64_t batch,
+                          const double *const *data, const uint32_t *var_index, const uint8_t *const *guess, const double *x0,
+                          const double *const *v0, const oracle_params *params, double *x, double *const *v,
+                          double *const *viol, uint8_t *const *active, int32_t *status, uint32_t *counters, double *margins,
+                          uint32_t *active_order, int threads, uint32_t g_count, const uint32_t *g_obj, const uint32_t *g_ctr,
+                          const uint8_t *g_type, double *xstar, double *lexdata, double *lexqr_star)
 {
     Parameters par = to_params(params);
     std::vector<int> types(nObj);
@@ -222,7 +258,15 @@ int oracle_lsi_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
             if (v0)
                 for (uint32_t k = 0; k < nObj; k++)
                     if (v0[k]) lsi.set_v0(k, v0[k] + p * ObjDim[k]);
-            if (guess)
+            if (g_count > 0)
+            {
+                for (uint32_t e = 0; e < g_count; e++)
+                {
+                    const uint64_t at = p * (uint64_t)g_count + e;
+                    if (g_type[at] != CTR_INACTIVE) lsi.api_activate(g_obj[at], g_ctr[at], g_type[at]);
+                }
+            }
+            else if (guess)
                 for (uint32_t k = 0; k < nObj; k++)
                     if (guess[k])
                         for (uint32_t i = 0; i < ObjDim[k]; i++)
@@ -275,9 +319,31 @@ int oracle_lsi_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
                 margins[p * 4 + 2] = lsi.min_alpha_gap;
                 margins[p * 4 + 3] = lsi.getLexLSE().min_lambda_gap;
             }
+            if (xstar || lexdata || lexqr_star)
+            {
+                // the call sequence of tests/test_numerical_error.cpp:83-86: get_xStar(), then get_data() and get_lexqr()
+                const std::vector<double> &xs = lsi.get_xStar();
+                if (xstar) std::memcpy(xstar + p * nVar, xs.data(), sizeof(double) * nVar);
+                uint32_t M = 0;
+                for (uint32_t k = 0; k < nObj; k++)
+                    if (types[k] != SIMPLE_BOUNDS_OBJECTIVE) M += ObjDim[k];
+                const LexLSE &e     = lsi.getLexLSE();
+                const uint32_t nCtr = e.get_nCtr(), ld = e.get_ld();
+                for (int which = 0; which < 2; which++)
+                {
+                    double *dst = which ? lexqr_star : lexdata;
+                    if (!dst) continue;
+                    const std::vector<double> &src = which ? e.get_lexqr() : e.get_data();
+                    dst += p * (uint64_t)M * (nVar + 1);
+                    for (uint32_t c = 0; c <= nVar; c++)
+                        for (uint32_t r = 0; r < M; r++) dst[(uint64_t)c * M + r] = r < nCtr ? src[(uint64_t)c * ld + r] : 0.0;
+                }
+            }
         }
     });
 }
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------------
 // Single LexLSI problem with debugging outputs: multipliers (getLambda, lexlsi.h:552-605) and the

@@ -130,9 +130,16 @@ def _prep_lsi(nVar, ObjDim, ObjType, data, var_index, guess, v0):
     return nObj, dims, types, data, vi, g, vv
 
 
-def lsi_solve_batch(nVar, ObjDim, ObjType, data, var_index=None, guess=None, x0=None, v0=None, params=None, threads=1):
-    """data[k]: [B, nVar+2, m_k] (general) or [B, 2, m_0] (simple bounds); var_index [B, m_0] 0-based."""
+def lsi_solve_batch(nVar, ObjDim, ObjType, data, var_index=None, guess=None, x0=None, v0=None, params=None, threads=1,
+                    guess_ordered=None, want_xstar=False):
+    """data[k]: [B, nVar+2, m_k] (general) or [B, 2, m_0] (simple bounds); var_index [B, m_0] 0-based.
+    guess_ordered = (obj, ctr, type) arrays [B, count]: api_activate calls in CALL order (type 0 = padding), used instead of
+    guess.  want_xstar: also return xstar [B, nVar], lexdata and lexqr_star [B, nVar+1, M] (get_xStar / get_data / get_lexqr
+    called after solve(), as tests/test_numerical_error.cpp does)."""
     L = lib()
+    if guess_ordered is not None or want_xstar:
+        return _lsi_solve_batch_ex(L, nVar, ObjDim, ObjType, data, var_index, guess, x0, v0, params, threads, guess_ordered,
+                                   want_xstar)
     nObj, dims, types, data, vi, g, vv = _prep_lsi(nVar, ObjDim, ObjType, data, var_index, guess, v0)
     B = data[0].shape[0]
     mtot = int(dims.sum())
@@ -157,6 +164,49 @@ def lsi_solve_batch(nVar, ObjDim, ObjType, data, var_index=None, guess=None, x0=
     if rc != 0:
         raise RuntimeError(L.oracle_last_error().decode())
     return dict(x=x, v=v, viol=viol, active=act, status=status, counters=counters, margins=margins, active_order=order)
+
+
+def _lsi_solve_batch_ex(L, nVar, ObjDim, ObjType, data, var_index, guess, x0, v0, params, threads, guess_ordered, want_xstar):
+    nObj, dims, types, data, vi, g, vv = _prep_lsi(nVar, ObjDim, ObjType, data, var_index, guess, v0)
+    B = data[0].shape[0]
+    mtot = int(dims.sum())
+    M = int(sum(int(m) for m, t in zip(dims, types) if t != 1))
+    x0a = _f64(x0) if x0 is not None else None
+    x = np.zeros((B, nVar))
+    v = [np.zeros((B, int(m))) for m in dims]
+    viol = [np.zeros((B, int(m))) for m in dims]
+    act = [np.zeros((B, int(m)), dtype=np.uint8) for m in dims]
+    status = np.zeros(B, dtype=np.int32)
+    counters = np.zeros((B, 8), dtype=np.uint32)
+    margins = np.zeros((B, 4))
+    order = np.zeros((B, mtot), dtype=np.uint32)
+    u32, u8 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    go = gc = gt = None
+    gcount = 0
+    if guess_ordered is not None:
+        go = np.ascontiguousarray(guess_ordered[0], dtype=np.uint32).reshape(B, -1)
+        gc = np.ascontiguousarray(guess_ordered[1], dtype=np.uint32).reshape(B, -1)
+        gt = np.ascontiguousarray(guess_ordered[2], dtype=np.uint8).reshape(B, -1)
+        gcount = go.shape[1]
+    xstar = np.zeros((B, nVar)) if want_xstar else None
+    lexdata = np.zeros((B, nVar + 1, M)) if want_xstar else None
+    lexqr_star = np.zeros((B, nVar + 1, M)) if want_xstar else None
+    p = params if params is not None else OracleParams()
+    rc = L.oracle_lsi_solve_batch_ex(
+        C.c_uint32(nVar), C.c_uint32(nObj), dims.ctypes.data_as(u32), types.ctypes.data_as(C.POINTER(C.c_int32)),
+        C.c_uint64(B), _ptr_array(data, C.c_double), vi.ctypes.data_as(u32) if vi is not None else None,
+        _ptr_array(g, C.c_uint8) if g is not None else None, _dp(x0a),
+        _ptr_array(vv, C.c_double) if vv is not None else None, C.byref(p), _dp(x), _ptr_array(v, C.c_double),
+        _ptr_array(viol, C.c_double), _ptr_array(act, C.c_uint8), status.ctypes.data_as(C.POINTER(C.c_int32)),
+        counters.ctypes.data_as(u32), _dp(margins), order.ctypes.data_as(u32), C.c_int(threads), C.c_uint32(gcount),
+        go.ctypes.data_as(u32) if go is not None else None, gc.ctypes.data_as(u32) if gc is not None else None,
+        gt.ctypes.data_as(u8) if gt is not None else None, _dp(xstar), _dp(lexdata), _dp(lexqr_star))
+    if rc != 0:
+        raise RuntimeError(L.oracle_last_error().decode())
+    out = dict(x=x, v=v, viol=viol, active=act, status=status, counters=counters, margins=margins, active_order=order)
+    if want_xstar:
+        out.update(xstar=xstar, lexdata=lexdata, lexqr_star=lexqr_star)
+    return out
 
 
 def lsi_solve_detail(nVar, ObjDim, ObjType, data, var_index=None, guess=None, x0=None, params=None, log_capacity=1024):

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "missing export: " + name
     assert sorted(capi.SYMBOLS) == declared, "capi.SYMBOLS and the header disagree"
-    assert lib.lexls_b200_abi_version() == 2
+    assert lib.lexls_b200_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -184,6 +184,8 @@ def test_two_problems_per_warp_kernel(oracle, monkeypatch):
     w = problems.workload("c2", 257)
     data, _ = problems.generate(w)
     wx, exact, got = _check(oracle, w.nVar, w.ObjDim, data)
+    if got["info"]["name"] != "lse_pair":
+        pytest.skip("the experiment is not compiled into the product library (build with -DLEXLS_B200_WITH_PAIR)")
     assert got["info"]["name"] == "lse_pair" and exact
     rng = np.random.default_rng(21)
     for dims, n in (([17, 3, 20], 15), ([20, 20], 47), ([9, 12, 5], 30)):

@@ -1,0 +1,286 @@
+"""GPU parity, round 2: the BASELINE batches at FULL size, get_xStar / get_data, api_activate in call order, multi-device
+handles, deferred input validation.  Everything goes through the C-ABI (lexls_b200.batch -> liblexls_b200.so)."""
+import numpy as np
+import pytest
+
+from helpers import compare_lsi, solve_lse_gpu, solve_lsi_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _lsi_both(oracle, w, data, vi, guess=None, x0=None, **par):
+    import lexls_b200 as lx
+    B = data[0].shape[0]
+    vib = np.tile(vi, (B, 1)) if (vi is not None and vi.ndim == 1) else vi
+    ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, guess=guess, x0=x0,
+                                 params=oracle.OracleParams(**par) if par else None, threads=0)
+    got = solve_lsi_gpu(w.nVar, w.ObjDim, w.ObjType, data, var_index=vi, guess=guess, x0=x0, params=lx.Params(**par) if par else None)
+    return got, ref
+
+
+# ---- full BASELINE sizes ------------------------------------------------------------------------
+def test_c2_full_size_65536_bit_identical(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("c2")
+    assert w.batch == 65536
+    data, _ = problems.generate(w)
+    ref = oracle.lse_solve_batch(w.nVar, w.ObjDim, data, threads=0)
+    got = solve_lse_gpu(w.nVar, w.ObjDim, data)
+    assert np.array_equal(got["ranks"], ref["ranks"])
+    assert np.array_equal(got["x"], ref["x"]) and np.array_equal(got["v"], ref["v"])
+    assert (got["ranks"][:, :2] < 20).any(axis=1).sum() > 1000  # the rank-deficient tenth of the batch is really there
+
+
+def test_c3_full_size_16384_cold_and_warm(oracle):
+    from lexls_b200 import problems
+    w = problems.workload("c3")
+    assert w.batch == 16384
+    data, vi = problems.generate(w)
+    got, ref = _lsi_both(oracle, w, data, vi)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"]) and (got["status"] == 0).all()
+    d2 = problems.perturb(w, data)
+    got2, ref2 = _lsi_both(oracle, w, d2, vi, guess=got["active"], x0=got["x"])
+    compare_lsi(got2, ref2, len(w.ObjDim))
+    assert np.array_equal(got2["x"], ref2["x"]) and (got2["status"] == 0).all()
+    assert got2["counters"][:, 0].mean() < 1.5 < got["counters"][:, 0].mean()
+
+
+def test_c4_64_problems_solved_at_full_factorization_count(oracle):
+    """n = 200, 10 levels x 40 rows, cold start: 310-380 factorizations per problem until PROBLEM_SOLVED (the default cap of 200
+    would stop every one of them), work matrix in the global scratch, Schur update on the FP64 tensor cores."""
+    from lexls_b200 import problems
+    w = problems.workload("c4", 64)
+    data, vi = problems.generate(w)
+    got, ref = _lsi_both(oracle, w, data, vi, max_number_of_factorizations=1000)
+    assert got["info"]["name"].endswith("_lodglobal")
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"])
+    assert (got["status"] == 0).all() and got["counters"][:, 0].min() > 200
+
+
+@pytest.mark.parametrize("dmma", ["0", "1"])
+def test_global_work_matrix_dmma_and_dfma_agree_with_the_oracle(oracle, monkeypatch, dmma):
+    """The Schur update of the global-work-matrix kernels: mma.sync m8n8k4 f64 tiles (default) and the DFMA strips give the same
+    bits as the oracle's ascending-k chain."""
+    monkeypatch.setenv("LEXLS_B200_DMMA", dmma)
+    monkeypatch.setenv("LEXLS_B200_FORCE_LODGLOBAL", "1")
+    from lexls_b200 import problems
+    rng = np.random.default_rng(5)
+    for n, dims in ((37, [9, 14, 6, 11]), (70, [33, 5, 41]), (21, [3, 30])):
+        B = 19
+        data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+        ref = oracle.lse_solve_batch(n, dims, data, threads=0)
+        got = solve_lse_gpu(n, dims, data)
+        assert got["info"]["name"].endswith("_lodglobal")
+        assert np.array_equal(got["x"], ref["x"]) and np.array_equal(got["v"], ref["v"])
+    w = problems.workload("c4", 4)
+    data, vi = problems.generate(w)
+    got, ref = _lsi_both(oracle, w, data, vi, max_number_of_factorizations=12)
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"])
+
+
+# ---- get_xStar / get_data / get_lexqr after it (lexlsi.h:519, :607, :612) --------------------------------------------
+@pytest.mark.parametrize("name,count,cap", [("tiny_lsi", 24, None), ("c3", 16, None), ("c3", 12, 3)])
+def test_get_xstar_and_get_data_match_the_oracle(oracle, name, count, cap):
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload(name, count)
+    data, vi = problems.generate(w)
+    par = dict(max_number_of_factorizations=cap) if cap else {}
+    vib = np.tile(vi, (w.batch, 1))
+    ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, params=oracle.OracleParams(**par) if par else None,
+                                 threads=0, want_xstar=True)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        if par:
+            s.setParameters(lx.Params(**par))
+        s.request_outputs(xstar=True, lexqr=True, multipliers=True)
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        xs, dat, q, hh = s.get_xStar()
+        x, status = s.get_x(), s.get_status()
+    assert np.array_equal(status, ref["status"]) and np.array_equal(x, ref["x"])
+    if cap:
+        assert (status == 2).any()  # some problems stopped by the cap: xStar belongs to a working set that was never factorized
+    assert np.array_equal(xs, ref["xstar"]), "get_xStar differs from the oracle"
+    assert np.array_equal(dat, ref["lexdata"]), "get_data differs from the oracle"
+    assert np.array_equal(q, ref["lexqr_star"]), "get_lexqr after get_xStar differs from the oracle"
+    solved = status == 0
+    assert np.allclose(xs[solved], x[solved], rtol=0, atol=1e-9)  # a solved problem ends on the solution of its last LexLSE
+
+
+# ---- api_activate in CALL order (lexlsi.h:120-136 -> workingset.h:67-77) ----------------------------------------------
+def test_active_guess_in_call_order_matches_the_oracle(oracle):
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c3", 48)
+    data, vi = problems.generate(w)
+    vib = np.tile(vi, (w.batch, 1))
+    cold = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, threads=0)
+    # the final active inequalities of the cold solve, shuffled per problem = an arbitrary call order of api_activate
+    rng = np.random.default_rng(3)
+    lists = []
+    for p in range(w.batch):
+        e = [(k, i, int(cold["active"][k][p, i])) for k in range(len(w.ObjDim)) for i in range(w.ObjDim[k])
+             if cold["active"][k][p, i] in (1, 2)]
+        rng.shuffle(e)
+        lists.append(e)
+    cnt = max(len(e) for e in lists) + 2
+    obj = np.zeros((w.batch, cnt), dtype=np.uint32)
+    ctr = np.zeros((w.batch, cnt), dtype=np.uint32)
+    typ = np.zeros((w.batch, cnt), dtype=np.uint8)
+    for p, e in enumerate(lists):
+        for j, (k, i, t) in enumerate(e):
+            obj[p, j], ctr[p, j], typ[p, j] = k, i, t
+    d2 = problems.perturb(w, data)
+    ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, d2, var_index=vib, x0=cold["x"], threads=0, guess_ordered=(obj, ctr, typ))
+    sorted_ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, d2, var_index=vib, x0=cold["x"], threads=0, guess=cold["active"])
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        for k, d in enumerate(d2):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.set_x0(cold["x"])
+        s.set_active_guess_ordered(obj, ctr, typ)
+        s.solve()
+        P = len(w.ObjDim)
+        got = dict(x=s.get_x(), v=[s.get_v(k) for k in range(P)], viol=[s.getConstraintViolation(k) for k in range(P)],
+                   active=[s.getActiveCtr(k) for k in range(P)], order=[s.getActiveCtr_order(k) for k in range(P)],
+                   status=s.get_status(), counters=s.get_counters())
+        # switching back to the per-row form replaces the list
+        for k in range(P):
+            s.set_active_guess(k, cold["active"][k])
+        s.solve()
+        x_sorted = s.get_x()
+    compare_lsi(got, ref, len(w.ObjDim))
+    assert np.array_equal(got["x"], ref["x"])
+    assert np.array_equal(x_sorted, sorted_ref["x"])
+    # the call order is visible in the working-set order (and may be in the last bits of x)
+    assert not np.array_equal(ref["active_order"], sorted_ref["active_order"])
+
+
+# ---- multi-device handles (lexls_b200_create_batch_multi) -------------------------------------------------------------
+def _device_count():
+    import ctypes as C
+    from lexls_b200 import capi
+    n = C.c_int()
+    capi.check(capi.lib().lexls_b200_device_count(C.byref(n)))
+    return n.value
+
+
+@pytest.mark.parametrize("ndev", [1, 2, 4, 8])
+def test_multi_device_batch_equals_single_device(oracle, ndev):
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    if _device_count() < ndev:
+        pytest.skip("needs %d CUDA devices" % ndev)
+    devices = list(range(ndev))
+    # LexLSE: ragged split (batch not a multiple of the device count), fixed variables, factorization output
+    w = problems.workload("c2", 1003)
+    data, _ = problems.generate(w)
+    ref = oracle.lse_solve_batch(w.nVar, w.ObjDim, data, threads=0, want_factors=True)
+    with lx.LexLSEBatch(w.nVar, w.ObjDim, batch=w.batch, devices=devices) as s:
+        sh = s.shards()
+        assert len(sh) == ndev and sum(c for _, _, c in sh) == w.batch and [d for d, _, _ in sh] == devices
+        s.request_outputs(lexqr=True)
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        x, ranks = s.get_x(), s.get_ranks()
+        v = np.concatenate([s.get_v(k) for k in range(len(w.ObjDim))], axis=1)
+        q, hh = s.get_lexqr()
+        assert s.last_solve_ms() > 0
+    assert np.array_equal(x, ref["x"]) and np.array_equal(v, ref["v"]) and np.array_equal(ranks, ref["ranks"])
+    assert np.array_equal(q, ref["lexqr"]) and np.array_equal(hh, ref["hh"])
+    # LexLSI: cold, then warm start through the same multi-device handle
+    w = problems.workload("c3", 517)
+    data, vi = problems.generate(w)
+    vib = np.tile(vi, (w.batch, 1))
+    ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, threads=0)
+    P = len(w.ObjDim)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch, devices=devices, strict=False) as s:
+        def run():
+            s.solve()
+            return dict(x=s.get_x(), v=[s.get_v(k) for k in range(P)], viol=[s.getConstraintViolation(k) for k in range(P)],
+                        active=[s.getActiveCtr(k) for k in range(P)], order=[s.getActiveCtr_order(k) for k in range(P)],
+                        status=s.get_status(), counters=s.get_counters())
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        got = run()
+        compare_lsi(got, ref, P)
+        assert np.array_equal(got["x"], ref["x"])
+        d2 = problems.perturb(w, data)
+        ref2 = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, d2, var_index=vib, guess=got["active"], x0=got["x"], threads=0)
+        for k, d in enumerate(d2):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        for k in range(P):
+            s.set_active_guess(k, got["active"][k])
+        s.set_x0(got["x"])
+        got2 = run()
+        compare_lsi(got2, ref2, P)
+        assert np.array_equal(got2["x"], ref2["x"])
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_sharded_batch_python(oracle, ndev):
+    """lexls_b200.ShardedBatch (one single-device handle per GPU inside one Python process) against the oracle."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    if _device_count() < ndev:
+        pytest.skip("needs %d CUDA devices" % ndev)
+    w = problems.workload("c2", 301)
+    data, _ = problems.generate(w)
+    ref = oracle.lse_solve_batch(w.nVar, w.ObjDim, data, threads=0)
+    with lx.ShardedBatch(lx.LexLSEBatch, w.nVar, w.ObjDim, batch=w.batch, devices=list(range(ndev))) as s:
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        x = s.gather("get_x")
+        ranks = s.gather("get_ranks")
+    assert np.array_equal(x, ref["x"]) and np.array_equal(ranks, ref["ranks"])
+
+
+# ---- deferred validation: one synchronisation per batch ---------------------------------------------------------------
+def test_deferred_validation_reports_at_solve():
+    import lexls_b200 as lx
+    with lx.LexLSIBatch(4, [3, 2], [1, 0], batch=5, strict=False) as s:
+        bad = np.zeros((5, 2, 3))
+        bad[3, 0, 1] = 1.0  # lb > ub in one problem of the batch
+        s.setData(0, bad, var_index=np.array([0, 1, 2], dtype=np.uint32))  # not reported here ...
+        s.setData(1, np.zeros((5, 6, 2)))
+        with pytest.raises(lx.LexLSError) as e:
+            s.solve()  # ... but here: the device refuses the solve, the first synchronisation reports it
+        assert e.value.code == 4 and "(simple)" in str(e.value)
+        with pytest.raises(lx.LexLSError):
+            s.solve()  # the offending data must be set again
+        ok = np.zeros((5, 2, 3))
+        ok[:, 1, :] = 1.0
+        s.setData(0, ok, var_index=np.array([0, 1, 2], dtype=np.uint32))
+        gen = np.zeros((5, 6, 2))
+        gen[:, 4, :] = 2.0   # lb
+        gen[:, 5, :] = 1.0   # ub < lb
+        s.setData(1, gen)
+        with pytest.raises(lx.LexLSError) as e:
+            s.validate()
+        assert e.value.code == 4 and "(general)" in str(e.value)
+        gen[:, 5, :] = 3.0
+        s.setData(1, gen)
+        s.setData(0, ok, var_index=np.array([0, 1, 2], dtype=np.uint32))
+        s.solve()
+        assert (s.get_status() == 0).all()
+
+
+def test_working_set_log_count_never_exceeds_capacity(oracle):
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c3", 8)
+    data, vi = problems.generate(w)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        s.setParameters(lx.Params(log_working_set_enabled=1))
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        full, n_full = s.getWorkingSetLog(capacity=256)
+        cut, n_cut = s.getWorkingSetLog(capacity=3)
+    assert n_full.max() > 3 and (n_cut == np.minimum(n_full, 3)).all()
+    assert np.array_equal(cut[:, :3, :], full[:, :3, :])
