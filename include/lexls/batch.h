@@ -38,6 +38,15 @@ public:
         for (Index k = 0; k < nObj; k++) type[k] = static_cast<int32_t>(ObjType_[k]);
         internal::lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSI, nVar, nObj, dim.data(), type.data(), batch, device, &h_));
     }
+    // the batch sharded over several GPUs of the box (contiguous ranges, one stream + host thread per device inside the library)
+    LexLSIBatch(Index nVar_, Index nObj_, Index *ObjDim_, ObjectiveType *ObjType_, uint64_t batch_, const std::vector<int> &devices)
+    : h_(0), nVar(nVar_), nObj(nObj_), batch(batch_), dim(ObjDim_, ObjDim_ + nObj_), solved(false)
+    {
+        type.resize(nObj);
+        for (Index k = 0; k < nObj; k++) type[k] = static_cast<int32_t>(ObjType_[k]);
+        internal::lexls_b200_check(lexls_b200_create_batch_multi(LEXLS_B200_LSI, nVar, nObj, dim.data(), type.data(), batch, devices.data(),
+                                                                 static_cast<int>(devices.size()), &h_));
+    }
     ~LexLSIBatch()
     {
         if (h_) lexls_b200_destroy(h_);
@@ -106,6 +115,29 @@ public:
             for (Index i = 0; i < dim[ObjIndex]; i++) t[q * dim[ObjIndex] + i] = static_cast<uint8_t>(per_problem[q][i]);
         }
         internal::lexls_b200_check(lexls_b200_set_active_guess(h_, ObjIndex, t.data()));
+        solved = false;
+    }
+    // warm start in CALL ORDER: calls[q] = the api_activate(obj, ctr, type) sequence of problem q (lexlsi.h:120-136)
+    void setActiveGuessOrdered(const std::vector<std::vector<ConstraintIdentifier> > &calls)
+    {
+        if (calls.size() != batch) throw Exception("setActiveGuessOrdered: one call list per problem");
+        size_t cnt = 0;
+        for (uint64_t q = 0; q < batch; q++) cnt = std::max(cnt, calls[q].size());
+        if (cnt == 0)
+        {
+            internal::lexls_b200_check(lexls_b200_set_active_guess_ordered(h_, 0, 0, 0, 0, 0));
+            return;
+        }
+        std::vector<uint32_t> o(batch * cnt, 0), c(batch * cnt, 0);
+        std::vector<uint8_t> t(batch * cnt, 0); // CTR_INACTIVE pads the shorter lists
+        for (uint64_t q = 0; q < batch; q++)
+            for (size_t e = 0; e < calls[q].size(); e++)
+            {
+                o[q * cnt + e] = calls[q][e].obj_index;
+                c[q * cnt + e] = calls[q][e].ctr_index;
+                t[q * cnt + e] = static_cast<uint8_t>(calls[q][e].ctr_type);
+            }
+        internal::lexls_b200_check(lexls_b200_set_active_guess_ordered(h_, static_cast<uint32_t>(cnt), o.data(), c.data(), t.data(), cnt));
         solved = false;
     }
     void set_x0(const std::vector<dVectorType> &x0) // lexlsi.h:306
@@ -205,6 +237,12 @@ public:
     {
         internal::lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSE, nVar, nObj, dim.data(), 0, batch, device, &h_));
     }
+    LexLSEBatch(Index nVar_, Index nObj_, Index *ObjDim_, uint64_t batch_, const std::vector<int> &devices)
+    : h_(0), nVar(nVar_), nObj(nObj_), batch(batch_), dim(ObjDim_, ObjDim_ + nObj_), solved(false)
+    {
+        internal::lexls_b200_check(lexls_b200_create_batch_multi(LEXLS_B200_LSE, nVar, nObj, dim.data(), 0, batch, devices.data(),
+                                                                 static_cast<int>(devices.size()), &h_));
+    }
     ~LexLSEBatch()
     {
         if (h_) lexls_b200_destroy(h_);
@@ -281,10 +319,39 @@ struct BatchResult
 };
 
 // LexLSI: data[q][k] = [A | lb | ub] of level k of problem q (level 0 of a SIMPLE_BOUNDS hierarchy: [lb | ub], with VarIndex)
+namespace internal
+{
+template <class Batch> inline BatchResult solve_lsi_batch(Batch &b, Index nObj, ObjectiveType *ObjType, const ParametersLexLSI &par,
+                                                          const std::vector<std::vector<dMatrixType> > &data, Index *VarIndex);
+template <class Batch> inline BatchResult solve_lse_batch(Batch &b, Index nObj, const ParametersLexLSE &par,
+                                                          const std::vector<std::vector<dMatrixType> > &data);
+} // namespace internal
+
+// the same entry points over several GPUs of one box: `devices` = CUDA ordinals, the batch is split into contiguous shards
+inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, ObjectiveType *ObjType, const ParametersLexLSI &par,
+                              const std::vector<std::vector<dMatrixType> > &data, Index *VarIndex, const std::vector<int> &devices)
+{
+    LexLSIBatch b(nVar, nObj, ObjDim, ObjType, data.size(), devices);
+    return internal::solve_lsi_batch(b, nObj, ObjType, par, data, VarIndex);
+}
+inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, const ParametersLexLSE &par,
+                              const std::vector<std::vector<dMatrixType> > &data, const std::vector<int> &devices)
+{
+    LexLSEBatch b(nVar, nObj, ObjDim, data.size(), devices);
+    return internal::solve_lse_batch(b, nObj, par, data);
+}
+
 inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, ObjectiveType *ObjType, const ParametersLexLSI &par,
                               const std::vector<std::vector<dMatrixType>> &data, Index *VarIndex = 0, int device = 0)
 {
     LexLSIBatch b(nVar, nObj, ObjDim, ObjType, data.size(), device);
+    return internal::solve_lsi_batch(b, nObj, ObjType, par, data, VarIndex);
+}
+namespace internal
+{
+template <class Batch> inline BatchResult solve_lsi_batch(Batch &b, Index nObj, ObjectiveType *ObjType, const ParametersLexLSI &par,
+                                                          const std::vector<std::vector<dMatrixType> > &data, Index *VarIndex)
+{
     b.setParameters(par);
     std::vector<dMatrixType> level(data.size());
     for (Index k = 0; k < nObj; k++)
@@ -308,12 +375,20 @@ inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, ObjectiveTy
     }
     return r;
 }
+} // namespace internal
 
 // LexLSE: data[q][k] = [A | b] of level k of problem q
 inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, const ParametersLexLSE &par,
                               const std::vector<std::vector<dMatrixType>> &data, int device = 0)
 {
     LexLSEBatch b(nVar, nObj, ObjDim, data.size(), device);
+    return internal::solve_lse_batch(b, nObj, par, data);
+}
+namespace internal
+{
+template <class Batch> inline BatchResult solve_lse_batch(Batch &b, Index nObj, const ParametersLexLSE &par,
+                                                          const std::vector<std::vector<dMatrixType> > &data)
+{
     b.setParameters(par);
     std::vector<dMatrixType> level(data.size());
     for (Index k = 0; k < nObj; k++)
@@ -334,4 +409,5 @@ inline BatchResult solveBatch(Index nVar, Index nObj, Index *ObjDim, const Param
     }
     return r;
 }
+} // namespace internal
 } // namespace LexLS

@@ -1,7 +1,8 @@
 // lexls/lexlsi.h — drop-in LexLS::internal::LexLSI (reference include/lexls/lexlsi.h; member signatures :51-104, :120, :205,
 // :306-545, :635-750) as a batch-of-1 facade over the C-ABI in include/lexls_b200.h.  solve() runs the whole active-set loop
-// on the GPU.  api_activate calls are applied level-major / row-ascending (the order of the reference's own front-end,
-// interfaces/matlab-octave/lexlsi.cpp:591-622).
+// on the GPU.  api_activate calls are replayed by the kernel in CALL ORDER (lexls_b200_set_active_guess_ordered), as the
+// reference applies them (lexlsi.h:120-136 -> workingset.h:67-77).  get_xStar / get_data / get_lexqr follow the reference's
+// state semantics: after get_xStar(), get_data() and get_lexqr() describe the LexLSE problem of the final working set.
 #pragma once
 
 #include <lexls/lexlse.h>
@@ -32,15 +33,20 @@ public:
         for (Index k = 0; k < nObj; k++) types[k] = static_cast<int32_t>(ObjType_[k]);
         release();
         lexls_b200_check(lexls_b200_create_batch(LEXLS_B200_LSI, nVar, nObj, dim.data(), types.data(), 1, 0, &h_));
-        // getLambda() / get_lexqr() are part of the surface: a batch of one always asks the kernel for them
-        lexls_b200_check(lexls_b200_request_outputs(h_, LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA));
+        // getLambda() / get_lexqr() / get_xStar() are part of the surface: a batch of one always asks the kernel for them
+        lexls_b200_check(lexls_b200_request_outputs(h_, LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA | LEXLS_B200_OUT_XSTAR));
         applyParameters();
         nGeneral = 0;
         for (Index k = 0; k < nObj; k++)
             if (ObjType_[k] != SIMPLE_BOUNDS_OBJECTIVE) nGeneral += dim[k];
         lexqr_.resize(nGeneral > 0 ? nGeneral : 1, nVar + 1);
-        guess.assign(nObj, std::vector<uint8_t>());
-        for (Index k = 0; k < nObj; k++) guess[k].assign(dim[k], 0);
+        lexqr_star_.resize(nGeneral > 0 ? nGeneral : 1, nVar + 1);
+        data_star_.resize(nGeneral > 0 ? nGeneral : 1, nVar + 1);
+        xstar_.resize(nVar);
+        star_called = false;
+        g_obj.clear();
+        g_ctr.clear();
+        g_type.clear();
         guess_dirty = false;
         x.resize(nVar);
         v.assign(nObj, dVectorType());
@@ -50,8 +56,11 @@ public:
     void reset() // lexlsi.h:88
     {
         lexls_b200_check(lexls_b200_reset(h_));
-        for (Index k = 0; k < nObj; k++) std::fill(guess[k].begin(), guess[k].end(), 0);
+        g_obj.clear();
+        g_ctr.clear();
+        g_type.clear();
         guess_dirty = false;
+        star_called = false;
         status      = TERMINATION_STATUS_UNKNOWN;
     }
     void setParameters(const ParametersLexLSI &p) // lexlsi.h:325
@@ -81,7 +90,10 @@ public:
         if (CtrIndex >= dim[ObjIndex]) throw Exception("CtrIndex >= nCtr");
         if (type == CTR_ACTIVE_LB || type == CTR_ACTIVE_UB)
         {
-            if (guess[ObjIndex][CtrIndex] == 0) guess[ObjIndex][CtrIndex] = static_cast<uint8_t>(type);
+            // recorded in call order; the kernel skips a constraint that is already active (lexlsi.h:124)
+            g_obj.push_back(ObjIndex);
+            g_ctr.push_back(CtrIndex);
+            g_type.push_back(static_cast<uint8_t>(type));
             guess_dirty = true;
         }
         else
@@ -93,9 +105,13 @@ public:
     TerminationStatus solve() // lexlsi.h:205
     {
         if (guess_dirty)
-            for (Index k = 0; k < nObj; k++)
-                if (dim[k]) lexls_b200_check(lexls_b200_set_active_guess(h_, k, guess[k].data()));
+        {
+            lexls_b200_check(lexls_b200_set_active_guess_ordered(h_, static_cast<uint32_t>(g_obj.size()), g_obj.data(), g_ctr.data(),
+                                                                 g_type.data(), g_obj.size()));
+            guess_dirty = false;
+        }
         lexls_b200_check(lexls_b200_solve_batch_sync(h_));
+        star_called = false;
         int32_t st = 0;
         lexls_b200_check(lexls_b200_get_status(h_, &st));
         status = static_cast<TerminationStatus>(st);
@@ -104,6 +120,7 @@ public:
         for (Index k = 0; k < nObj; k++)
             if (dim[k]) lexls_b200_check(lexls_b200_get_v(h_, k, v[k].data()));
         if (nGeneral) lexls_b200_check(lexls_b200_get_lexqr(h_, lexqr_.data(), 0));
+        lexls_b200_check(lexls_b200_get_xstar(h_, xstar_.data(), nGeneral ? data_star_.data() : 0, nGeneral ? lexqr_star_.data() : 0, 0));
         working_set_log.clear();
         if (parameters.log_working_set_enabled)
         {
@@ -133,7 +150,24 @@ public:
             if (dim[k]) lexls_b200_check(lexls_b200_get_lambda(h_, k, vec_lambda[k].data()));
         }
     }
-    const dMatrixType &get_lexqr() const { return lexqr_; } // lexlsi.h:607: the last factorization (active rows)
+    // lexlsi.h:519-526: the solution of the LexLSE problem of the last active set (formed, factorized and solved once more —
+    // by the solve kernel, at its end).  As in the reference, get_data() and get_lexqr() afterwards describe THAT problem.
+    const dVectorType &get_xStar()
+    {
+        star_called = true;
+        return xstar_;
+    }
+    // lexlsi.h:607: the last factorization (active rows in working-set order)
+    const dMatrixType &get_lexqr() const { return star_called ? lexqr_star_ : lexqr_; }
+    // lexlsi.h:612 -> lexlse.h:119, :1631: the constraints [A | rhs] of the inner LexLSE problem as they were given to its
+    // last factorize().  Without a get_xStar() call that is the problem of the last in-loop factorization, which differs from
+    // the one of the final working set only when the solve did not end PROBLEM_SOLVED.
+    const dMatrixType &get_data()
+    {
+        if (!star_called && status != PROBLEM_SOLVED && status != TERMINATION_STATUS_UNKNOWN)
+            throw Exception("get_data(): call get_xStar() first (the final working set was never factorized by solve())");
+        return data_star_;
+    }
     const dVectorType &get_x() const { return x; }                  // lexlsi.h:508
     const dVectorType &get_v(Index ObjIndex) const { return v[ObjIndex]; } // :528
     void getConstraintViolation(Index ObjIndex, dVectorType &out) const // :542
@@ -209,8 +243,11 @@ private:
     lexls_b200_batch_t *h_;
     Index nVar, nObj;
     std::vector<Index> dim;
-    std::vector<std::vector<uint8_t>> guess;
-    bool guess_dirty = false;
+    std::vector<uint32_t> g_obj, g_ctr; // api_activate calls in call order
+    std::vector<uint8_t> g_type;
+    bool guess_dirty = false, star_called = false;
+    dVectorType xstar_;
+    dMatrixType lexqr_star_, data_star_;
     ParametersLexLSI parameters;
     TerminationStatus status;
     uint32_t cnt[LEXLS_B200_NCOUNTERS];

@@ -40,12 +40,36 @@ class OracleParams(C.Structure):
             setattr(self, k, v)
 
 
+def _cpu_id():
+    """Model + flags of the host CPU: the library is built with -march=native, so a copy built on another machine
+    (the build container vs the GPU box) must be rebuilt, not loaded."""
+    try:
+        model = flags = ""
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name") and not model:
+                    model = ln.split(":", 1)[1].strip()
+                elif ln.startswith("flags") and not flags:
+                    flags = ln.split(":", 1)[1].strip()
+                if model and flags:
+                    break
+        import hashlib
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()
+    except Exception:
+        return "unknown"
+
+
 def build(force=False):
-    """Compile oracle/_build/liblexls_oracle.so (g++; no dependencies)."""
+    """Compile oracle/_build/liblexls_oracle.so (g++ -O3 -march=native; no dependencies)."""
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "lexls_oracle.hpp", "Makefile")]
-    if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+    stamp = os.path.join(_HERE, "_build", "cpu.txt")
+    cpu = _cpu_id()
+    same_cpu = os.path.exists(stamp) and open(stamp).read() == cpu
+    if (not force) and same_cpu and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
-    subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    with open(stamp, "w") as f:
+        f.write(cpu)
     return _SO
 
 

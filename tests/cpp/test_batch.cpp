@@ -111,6 +111,29 @@ int main()
             for (Index j = 0; j < ne; j++)
                 if (one.get_x()(j) != re.x[q](j)) { std::printf("FAIL LexLSE x of problem %u\n", unsigned(q)); return 1; }
         }
+        // the same entry point over a device list (lexls_b200_create_batch_multi): one device, then every device of the box
+        {
+            int ndev = 0;
+            lexls_b200_device_count(&ndev);
+            for (int use = 1; use <= ndev; use = (use < ndev && 2 * use > ndev) ? ndev : 2 * use)
+            {
+                std::vector<int> devices;
+                for (int d = 0; d < use; d++) devices.push_back(d);
+                BatchResult rm = solveBatch(ne, Pe, de, pe, eq, devices);
+                for (uint64_t q = 0; q < B; q++)
+                    for (Index j = 0; j < ne; j++)
+                        if (rm.x[q](j) != re.x[q](j)) { std::printf("FAIL multi-device LexLSE x (%d devices) of problem %u\n", use, unsigned(q)); return 1; }
+                BatchResult ri = solveBatch(n, P, dims, types, par, data, var_index, devices);
+                for (uint64_t q = 0; q < B; q++)
+                {
+                    if (ri.status[q] != r.status[q]) { std::printf("FAIL multi-device LexLSI status\n"); return 1; }
+                    for (Index j = 0; j < n; j++)
+                        if (ri.x[q](j) != r.x[q](j)) { std::printf("FAIL multi-device LexLSI x (%d devices) of problem %u\n", use, unsigned(q)); return 1; }
+                }
+                std::printf("multi-device solveBatch: %d device(s) ok\n", use);
+                if (use == ndev) break;
+            }
+        }
         // the handle classes: ranks, packed data, fixed variables, residuals
         {
             LexLSEBatch b(ne, Pe, de, B);

@@ -47,3 +47,23 @@ def test_cpp_solve_batch_equals_single_problem_solves(tmp_path):
     exe = _build(tmp_path, "test_batch")
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_tools_header_and_numerical_error_replay_compile(tmp_path, golden_dir):
+    """include/lexls/tools.h (HierarchyFileProcessor::import) and the get_xStar / get_data / get_lexqr surface build; without a
+    GPU the run fails loudly after the import succeeded."""
+    exe = _build(tmp_path, "test_numerical_error_replay")
+    import torch
+    if not torch.cuda.is_available():
+        res = subprocess.run([exe, os.path.join(golden_dir, "test_01.dat")], capture_output=True, text=True)
+        assert res.returncode == 2 and "no CPU fallback" in res.stdout
+
+
+@pytest.mark.gpu
+def test_numerical_error_replay_on_test_01_dat(tmp_path, golden_dir):
+    """The reference's tests/test_numerical_error.cpp call sequence on its fixture tests/test_01.dat: LexLSI solve, get_xStar,
+    get_data, get_lexqr, getActiveCtr_order, then LexLSE on the final working set — reproduced bit for bit (errors exactly 0)."""
+    exe = _build(tmp_path, "test_numerical_error_replay")
+    res = subprocess.run([exe, os.path.join(golden_dir, "test_01.dat")], capture_output=True, text=True)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+    assert "error(x)     = 0.000000000000000000e+00" in res.stdout
