@@ -321,6 +321,7 @@ def measure(name, args, torch, dist, rank, world, local, steps, e2e_steps, batch
     w = problems.workload(name, hi - lo)
     data, vi = problems.generate(w, start=lo, count=hi - lo)
     r = Runner(w, data, vi, local, torch, params=params)
+    r.x_all = torch.empty((global_batch, w.nVar), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
     info = r.s.kernel_info()
     for _ in range(max(args.warmup, 3)):
         r.step()
@@ -338,7 +339,7 @@ def measure(name, args, torch, dist, rank, world, local, steps, e2e_steps, batch
         def step():
             fn()
             if world > 1:
-                gather_to_rank0(r.x_pinned.numpy(), global_batch)
+                gather_to_rank0(r.x_pinned, global_batch, out=r.x_all)
         return step
     legs = {}
     for _ in range(2):
@@ -389,7 +390,7 @@ def measure(name, args, torch, dist, rank, world, local, steps, e2e_steps, batch
                     "pipelined_value": rate(legs["pipelined"]) if "pipelined" in legs else None,
                     "device_inputs_value": rate(legs["device_inputs"]),
                     "device_inputs_api": "set_data_dev (device pointers), solve, get_x into pinned host memory",
-                    "final_gather": "gather_to_rank0(x) over NCCL inside the timed region" if world > 1 else "single rank: x lands in the caller's pinned buffer",
+                    "final_gather": "lexls_b200.shard.gather_to_rank0(x): shards GPU to GPU over NCCL into one device buffer on rank 0, one D2H into a pinned [global_batch, nVar] buffer; inside the timed region" if world > 1 else "single rank: x lands in the caller's pinned buffer",
                     "host_link": {"h2d_gbs_per_gpu_all_ranks_copying": link_gbs,
                                   "ceiling_problems_per_s": global_batch / (r.h2d_bytes / (link_gbs * 1e9)),
                                   "note": "a plain pinned cudaMemcpyAsync of the step's input bytes on every rank at once: the "

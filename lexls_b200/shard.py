@@ -22,30 +22,53 @@ def shard_ranges(batch, world):
     return [shard_range(batch, world, r) for r in range(world)]
 
 
-def gather_to_rank0(local, batch, group=None):
-    """Final gather over torch.distributed (any backend): rank 0 returns the [batch, ...] array, other ranks None."""
+_GATHER_CACHE = {}
+
+
+def gather_to_rank0(local, batch, group=None, out=None):
+    """Final gather over torch.distributed (any backend): rank 0 returns the [batch, ...] array, other ranks None.
+
+    `local` is this rank's [rows, ...] result (numpy array, or a torch tensor — pinned host memory makes the staging copy
+    asynchronous).  With NCCL the shards travel GPU to GPU (NVLink) into one device buffer on rank 0 and come down in ONE
+    device-to-host copy; staging and receive buffers are cached per shape, `out` (a pinned [batch, ...] torch tensor or numpy
+    array over pinned memory) receives the result without a further copy."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    local = np.ascontiguousarray(local)
-    orig = local.dtype
-    if orig == np.uint32:      # collectives lack unsigned 32-bit: ship the bits as int32
-        local = local.view(np.int32)
-    t = torch.from_numpy(local)
-    if dist.get_backend(group) == "nccl":
-        t = t.cuda()
+    t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
+    orig = t.dtype
+    if orig == torch.uint32:   # collectives lack unsigned 32-bit: ship the bits as int32
+        t = t.view(torch.int32)
     tail = tuple(t.shape[1:])
     sizes = [hi - lo for lo, hi in shard_ranges(batch, world)]
     smax = max(sizes)
-    if t.shape[0] < smax:  # gather needs equal shapes: pad ragged shards, trim after
-        pad = torch.zeros((smax - t.shape[0],) + tail, dtype=t.dtype, device=t.device)
-        t = torch.cat([t, pad], dim=0)
-    bufs = [torch.empty((smax,) + tail, dtype=t.dtype, device=t.device) for _ in sizes] if rank == 0 else None
-    dist.gather(t, bufs, dst=0, group=group)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    key = (str(dev), t.dtype, smax, tail, world, rank == 0)
+    bufs = _GATHER_CACHE.get(key)
+    if bufs is None:
+        send = torch.zeros((smax,) + tail, dtype=t.dtype, device=dev)  # padded: gather needs equal shapes
+        recv = torch.empty((world, smax) + tail, dtype=t.dtype, device=dev) if rank == 0 else None
+        bufs = _GATHER_CACHE[key] = (send, recv)
+    send, recv = bufs
+    send[:t.shape[0]].copy_(t, non_blocking=True)
+    dist.gather(send, list(recv.unbind(0)) if rank == 0 else None, dst=0, group=group)
     if rank != 0:
         return None
-    out = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0).cpu().numpy()
-    return out.view(np.uint32) if orig == np.uint32 else out
+    if out is None:
+        res = torch.empty((int(batch),) + tail, dtype=t.dtype, pin_memory=nccl)
+    else:
+        res = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+        if orig == torch.uint32:
+            res = res.view(torch.int32)
+    lo = 0
+    for r, n in enumerate(sizes):
+        res[lo:lo + n].copy_(recv[r, :n], non_blocking=True)
+        lo += n
+    if nccl:
+        torch.cuda.current_stream().synchronize()
+    a = res.numpy()
+    return a.view(np.uint32) if orig == torch.uint32 else a
 
 
 class ShardedBatch:
