@@ -88,7 +88,7 @@ typedef struct lexls_b200_params
     int32_t set_min_init_ctr_violation;    /* 1     */
     int32_t use_phase1_v0;                 /* 0     */
     int32_t log_working_set_enabled;       /* 0     */
-    int32_t deactivate_first_wrong_sign;   /* 0 (1 is EUNSUPPORTED this round) */
+    int32_t deactivate_first_wrong_sign;   /* 0; 1 = lexlsi.h:1063-1105 (EUNSUPPORTED with a simple-bounds objective: undefined in the reference) */
 } lexls_b200_params_t;
 
 typedef struct lexls_b200_batch lexls_b200_batch_t; /* opaque */
@@ -237,6 +237,9 @@ typedef struct lexls_b200_kernel_info
 int lexls_b200_kernel_info(lexls_b200_batch_t *h, lexls_b200_kernel_info_t *info);
 int lexls_b200_last_solve_ms(lexls_b200_batch_t *h, float *ms);
 int lexls_b200_measure_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops, double *sm_clock_mhz);
+/* debug aid: with LEXLS_B200_CANARY=1 in the environment every device buffer of a handle is followed by a 256-byte guard band;
+ * this counts the bands that were written into (0 = no kernel wrote past the end of a buffer). */
+int lexls_b200_check_guard_bands(lexls_b200_batch_t *h, uint32_t *violations);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,12 @@ class _Batch:
         """Waits for the set* calls issued so far and raises what their device-side checks found (lexlsi.h:430, :474, :485)."""
         check(lib().lexls_b200_validate(self._h))
 
+    def check_guard_bands(self):
+        """LEXLS_B200_CANARY=1: number of device buffers whose trailing guard band was written into (0 = clean)."""
+        v = C.c_uint32()
+        check(lib().lexls_b200_check_guard_bands(self._h, C.byref(v)))
+        return v.value
+
     def shards(self):
         """[(device, first, count)] of a multi-device batch (one entry for a single-device one)."""
         n = C.c_int()

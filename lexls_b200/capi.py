@@ -19,6 +19,7 @@ SYMBOLS = [
     "lexls_b200_last_solve_ms", "lexls_b200_measure_fp64_peak", "lexls_b200_request_outputs", "lexls_b200_get_lexqr",
     "lexls_b200_get_lambda", "lexls_b200_get_working_set_log", "lexls_b200_validate", "lexls_b200_create_batch_multi",
     "lexls_b200_shard_count", "lexls_b200_get_shard", "lexls_b200_get_xstar", "lexls_b200_set_active_guess_ordered",
+    "lexls_b200_check_guard_bands",
 ]
 OUT_LEXQR, OUT_LAMBDA, OUT_XSTAR = 1, 2, 4
 

@@ -76,6 +76,7 @@ struct lexls_b200_batch
     unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
     double *xstar = nullptr, *lexdata = nullptr, *lexqr_star = nullptr, *hh_star = nullptr; // LEXLS_B200_OUT_XSTAR
+    unsigned *wsl = nullptr;                                       // chronological activation list (deactivate_first_wrong_sign)
     unsigned *glist = nullptr;                                     // api_activate calls in call order (set_active_guess_ordered)
     unsigned gcap = 0;
     bool have_glist = false;
@@ -88,6 +89,7 @@ struct lexls_b200_batch
     bool flag_pending = false;     // a solve has been enqueued whose flag copy has not been inspected yet
     cudaEvent_t ev_copy = nullptr; // completion of the last host -> staging copy (the caller's buffer is then free)
     uint64_t nfix_cap = 0;         // elements allocated in fidx / fval / ftype
+    std::vector<std::pair<void *, size_t>> guards; // LEXLS_B200_CANARY=1: (buffer, bytes) of every allocation, each followed by a guard band
     unsigned long long *queue = nullptr;
     uint64_t lod_stride = 0;
     size_t lod_bytes = 0;
@@ -96,13 +98,44 @@ struct lexls_b200_batch
     size_t stage_bytes = 0;
 };
 
+
+// LEXLS_B200_CANARY=1 (debug aid; compute-sanitizer is closed on the GPU pool): every device buffer of a handle is followed by a
+// 256-byte guard band filled with 0xA5; lexls_b200_check_guard_bands counts the bands a kernel wrote into.
+#define LX_GUARD_BYTES 256
+static bool canary_enabled()
+{
+    const char *e = getenv("LEXLS_B200_CANARY");
+    return e && atoi(e) != 0;
+}
+static cudaError_t guarded_malloc(lexls_b200_batch *h, void **p, size_t bytes)
+{
+    if (!canary_enabled()) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMalloc(p, bytes + LX_GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset((char *)*p + bytes, 0xA5, LX_GUARD_BYTES);
+    if (e == cudaSuccess)
+    {
+        for (auto &g : h->guards)
+            if (g.first == *p) g.second = (size_t)-1; // address reused after a free: the old record is stale
+        h->guards.push_back(std::make_pair(*p, bytes));
+    }
+    return e;
+}
+
+static void guarded_free(lexls_b200_batch *h, void *p)
+{
+    for (auto &g : h->guards)
+        if (g.first == p) g.second = (size_t)-1;
+    cudaFree(p);
+}
+
 static int ensure_stage(lexls_b200_batch *h, size_t bytes)
 {
     if (h->stage_bytes >= bytes) return 0;
-    if (h->stage) cudaFree(h->stage);
+    if (h->stage) guarded_free(h, h->stage);
     h->stage       = nullptr;
     h->stage_bytes = 0;
-    CK(cudaMalloc(&h->stage, bytes));
+    CK(guarded_malloc(h, (void **)&h->stage, bytes));
     h->stage_bytes = bytes;
     return 0;
 }
@@ -428,10 +461,10 @@ static int plan(lexls_b200_batch *h)
         const size_t need = sizeof(double) * h->lod_stride * h->grid;
         if (need > h->lod_bytes)
         {
-            if (h->lod_scratch) cudaFree(h->lod_scratch);
+            if (h->lod_scratch) guarded_free(h, h->lod_scratch);
             h->lod_scratch = nullptr;
             h->lod_bytes   = 0;
-            CK(cudaMalloc(&h->lod_scratch, need));
+            CK(guarded_malloc(h, (void **)&h->lod_scratch, need));
             h->lod_bytes = need;
         }
     }
@@ -539,6 +572,7 @@ static void to_dev_params(const lexls_b200_params_t &u, Params &p)
     p.mod_inactive = u.modify_type_inactive_enabled;
     p.min_viol     = u.set_min_init_ctr_violation;
     p.phase1_v0    = u.use_phase1_v0;
+    p.dfirst       = u.deactivate_first_wrong_sign;
     // Gauss step on the FP64 tensor cores (mma.sync m8n8k4, bit-identical to the DFMA chain: profiles/r2_dmma_order.json);
     // LEXLS_B200_DMMA=0 selects the DFMA version for A/B measurements
     const char *e = getenv("LEXLS_B200_DMMA");
@@ -636,31 +670,31 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     const uint64_t B = batch;
     if (kind == LEXLS_B200_LSE)
     {
-        CKB(cudaMalloc(&h->rec, sizeof(double) * h->rec_stride * B));
+        CKB(guarded_malloc(h, (void **)&h->rec, sizeof(double) * h->rec_stride * B));
         CKB(cudaMemsetAsync(h->rec, 0, sizeof(double) * h->rec_stride * B, h->stream));
-        CKB(cudaMalloc(&h->v, sizeof(double) * std::max(s.M, 1) * B));
+        CKB(guarded_malloc(h, (void **)&h->v, sizeof(double) * std::max(s.M, 1) * B));
     }
     else
     {
-        CKB(cudaMalloc(&h->obj, sizeof(double) * h->obj_stride * B));
+        CKB(guarded_malloc(h, (void **)&h->obj, sizeof(double) * h->obj_stride * B));
         CKB(cudaMemsetAsync(h->obj, 0, sizeof(double) * h->obj_stride * B, h->stream));
         if (s.m0)
         {
-            CKB(cudaMalloc(&h->sb, sizeof(double) * 2 * s.m0 * B));
-            CKB(cudaMalloc(&h->sbidx, sizeof(unsigned) * s.m0 * B));
+            CKB(guarded_malloc(h, (void **)&h->sb, sizeof(double) * 2 * s.m0 * B));
+            CKB(guarded_malloc(h, (void **)&h->sbidx, sizeof(unsigned) * s.m0 * B));
         }
-        CKB(cudaMalloc(&h->v, sizeof(double) * s.Mall * B));
-        CKB(cudaMalloc(&h->viol, sizeof(double) * s.Mall * B));
-        CKB(cudaMalloc(&h->act, s.Mall * B));
-        CKB(cudaMalloc(&h->order, sizeof(unsigned) * s.Mall * B));
+        CKB(guarded_malloc(h, (void **)&h->v, sizeof(double) * s.Mall * B));
+        CKB(guarded_malloc(h, (void **)&h->viol, sizeof(double) * s.Mall * B));
+        CKB(guarded_malloc(h, (void **)&h->act, s.Mall * B));
+        CKB(guarded_malloc(h, (void **)&h->order, sizeof(unsigned) * s.Mall * B));
     }
-    CKB(cudaMalloc(&h->x, sizeof(double) * nVar * B));
-    CKB(cudaMalloc(&h->status, sizeof(int) * B));
-    CKB(cudaMalloc(&h->counters, sizeof(unsigned) * 8 * B));
-    CKB(cudaMalloc(&h->ranks, sizeof(unsigned) * std::max(s.G, 1) * B));
-    CKB(cudaMalloc(&h->colperm, sizeof(unsigned) * nVar * B));
-    CKB(cudaMalloc(&h->queue, sizeof(unsigned long long)));
-    CKB(cudaMalloc(&h->flag, sizeof(int)));
+    CKB(guarded_malloc(h, (void **)&h->x, sizeof(double) * nVar * B));
+    CKB(guarded_malloc(h, (void **)&h->status, sizeof(int) * B));
+    CKB(guarded_malloc(h, (void **)&h->counters, sizeof(unsigned) * 8 * B));
+    CKB(guarded_malloc(h, (void **)&h->ranks, sizeof(unsigned) * std::max(s.G, 1) * B));
+    CKB(guarded_malloc(h, (void **)&h->colperm, sizeof(unsigned) * nVar * B));
+    CKB(guarded_malloc(h, (void **)&h->queue, sizeof(unsigned long long)));
+    CKB(guarded_malloc(h, (void **)&h->flag, sizeof(int)));
     CKB(cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream));
     CKB(cudaMemsetAsync(h->status, 0xff, sizeof(int) * B, h->stream));
     CKB(cudaMemsetAsync(h->counters, 0, sizeof(unsigned) * 8 * B, h->stream));
@@ -683,7 +717,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -718,8 +752,10 @@ int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
     if (!h || !p) return fail(LEXLS_B200_EINVAL, "NULL argument");
     if (p->regularization_type != 0)
         return fail(LEXLS_B200_EUNSUPPORTED, "regularization is outside the hot-path scope (REGULARIZATION_NONE only)");
-    if (p->deactivate_first_wrong_sign)
-        return fail(LEXLS_B200_EUNSUPPORTED, "deactivate_first_wrong_sign is not implemented (largest-multiplier rule only)");
+    if (p->deactivate_first_wrong_sign && h->kind == LEXLS_B200_LSI && h->sh.off)
+        return fail(LEXLS_B200_EUNSUPPORTED,
+                    "deactivate_first_wrong_sign with a simple-bounds objective: the reference tests the wrong multipliers and indexes out "
+                    "of bounds there (lexlse.h:596-599, lexlsi.h:1092), so there is no behaviour to reproduce");
     if (p->max_number_of_factorizations == 0) return fail(LEXLS_B200_EINVAL, "max_number_of_factorizations must be positive");
     h->user_params = *p;
     to_dev_params(*p, h->pr);
@@ -920,14 +956,14 @@ int lexls_b200_set_fixed_variables(lexls_b200_batch_t *h, uint32_t count, const 
     }
     if (N > h->nfix_cap)
     {
-        if (h->fidx) cudaFree(h->fidx);
-        if (h->fval) cudaFree(h->fval);
-        if (h->ftype) cudaFree(h->ftype);
+        if (h->fidx) guarded_free(h, h->fidx);
+        if (h->fval) guarded_free(h, h->fval);
+        if (h->ftype) guarded_free(h, h->ftype);
         h->fidx = nullptr; h->fval = nullptr; h->ftype = nullptr;
         h->nfix_cap = 0;
-        CK(cudaMalloc(&h->fidx, sizeof(unsigned) * N));
-        CK(cudaMalloc(&h->fval, sizeof(double) * N));
-        CK(cudaMalloc(&h->ftype, N));
+        CK(guarded_malloc(h, (void **)&h->fidx, sizeof(unsigned) * N));
+        CK(guarded_malloc(h, (void **)&h->fval, sizeof(double) * N));
+        CK(guarded_malloc(h, (void **)&h->ftype, N));
         h->nfix_cap = N;
     }
     CK(cudaMemcpyAsync(h->fidx, var_index, sizeof(unsigned) * N, cudaMemcpyHostToDevice, h->stream));
@@ -1010,7 +1046,7 @@ static int set_x0_impl(lexls_b200_batch *h, const double *x0, bool on_device)
     }
     CK(cudaSetDevice(h->device));
     const size_t bytes = sizeof(double) * h->sh.n * h->batch;
-    if (!h->x0) CK(cudaMalloc(&h->x0, bytes));
+    if (!h->x0) CK(guarded_malloc(h, (void **)&h->x0, bytes));
     CK(cudaMemcpyAsync(h->x0, x0, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     if (!on_device) CK(cudaStreamSynchronize(h->stream));
     h->have_x0 = true;
@@ -1094,6 +1130,11 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
         b.hh_star    = h->hh_star;
     }
     b.glist = h->have_glist ? h->glist : nullptr;
+    if (h->kind == LEXLS_B200_LSI && h->pr.dfirst)
+    {
+        if (!h->wsl) CK(guarded_malloc(h, (void **)&h->wsl, sizeof(unsigned) * (size_t)std::max(s.Mall, 1) * h->batch));
+        b.wsl = h->wsl;
+    }
     b.gcap  = h->gcap;
     if (h->kind == LEXLS_B200_LSI && h->user_params.log_working_set_enabled)
     {
@@ -1101,12 +1142,12 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
         const unsigned cap = h->user_params.max_number_of_factorizations + 1;
         if (!h->wslog || h->wslog_cap < cap)
         {
-            if (h->wslog) cudaFree(h->wslog);
-            if (h->wslog_count) cudaFree(h->wslog_count);
+            if (h->wslog) guarded_free(h, h->wslog);
+            if (h->wslog_count) guarded_free(h, h->wslog_count);
             h->wslog = nullptr;
             h->wslog_count = nullptr;
-            CK(cudaMalloc(&h->wslog, sizeof(double) * 6 * (size_t)cap * h->batch));
-            CK(cudaMalloc(&h->wslog_count, sizeof(unsigned) * h->batch));
+            CK(guarded_malloc(h, (void **)&h->wslog, sizeof(double) * 6 * (size_t)cap * h->batch));
+            CK(guarded_malloc(h, (void **)&h->wslog_count, sizeof(unsigned) * h->batch));
             h->wslog_cap = cap;
         }
         b.wslog       = h->wslog;
@@ -1254,17 +1295,17 @@ int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
     const int M    = std::max(s.M, 1);
     if ((mask & LEXLS_B200_OUT_LEXQR) && !h->lexqr)
     {
-        CK(cudaMalloc(&h->lexqr, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
-        CK(cudaMalloc(&h->hhout, sizeof(double) * (size_t)M * h->batch));
+        CK(guarded_malloc(h, (void **)&h->lexqr, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(guarded_malloc(h, (void **)&h->hhout, sizeof(double) * (size_t)M * h->batch));
     }
     if ((mask & LEXLS_B200_OUT_LAMBDA) && !h->lambda)
-        CK(cudaMalloc(&h->lambda, sizeof(double) * (size_t)s.P * std::max(s.Mall, 1) * h->batch));
+        CK(guarded_malloc(h, (void **)&h->lambda, sizeof(double) * (size_t)s.P * std::max(s.Mall, 1) * h->batch));
     if ((mask & LEXLS_B200_OUT_XSTAR) && !h->xstar)
     {
-        CK(cudaMalloc(&h->xstar, sizeof(double) * (size_t)s.n * h->batch));
-        CK(cudaMalloc(&h->lexdata, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
-        CK(cudaMalloc(&h->lexqr_star, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
-        CK(cudaMalloc(&h->hh_star, sizeof(double) * (size_t)M * h->batch));
+        CK(guarded_malloc(h, (void **)&h->xstar, sizeof(double) * (size_t)s.n * h->batch));
+        CK(guarded_malloc(h, (void **)&h->lexdata, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(guarded_malloc(h, (void **)&h->lexqr_star, sizeof(double) * (size_t)M * (s.n + 1) * h->batch));
+        CK(guarded_malloc(h, (void **)&h->hh_star, sizeof(double) * (size_t)M * h->batch));
     }
     h->want = mask;
     return 0;
@@ -1423,10 +1464,10 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
     CK(cudaSetDevice(h->device));
     if (h->gcap < cap)
     {
-        if (h->glist) cudaFree(h->glist);
+        if (h->glist) guarded_free(h, h->glist);
         h->glist = nullptr;
         h->gcap  = 0;
-        CK(cudaMalloc(&h->glist, sizeof(unsigned) * (size_t)cap * h->batch));
+        CK(guarded_malloc(h, (void **)&h->glist, sizeof(unsigned) * (size_t)cap * h->batch));
         h->gcap = cap;
     }
     if (h->gcap != cap) // a shorter list than the buffer was sized for: keep the buffer's row stride
@@ -1438,6 +1479,38 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
     CK(cudaMemcpyAsync(h->glist, packed.data(), sizeof(unsigned) * packed.size(), cudaMemcpyHostToDevice, h->stream));
     if (int rc = wait_copy(h)) return rc;
     h->have_glist = true;
+    return 0;
+}
+
+int lexls_b200_check_guard_bands(lexls_b200_batch_t *h, uint32_t *violations)
+{
+    if (!h || !violations) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    *violations = 0;
+    if (h->multi())
+    {
+        for (auto &s : h->shards)
+        {
+            uint32_t v = 0;
+            if (int rc = lexls_b200_check_guard_bands(s.h, &v)) return rc;
+            *violations += v;
+        }
+        return 0;
+    }
+    if (!canary_enabled()) return fail(LEXLS_B200_EINVAL, "guard bands exist only for handles created with LEXLS_B200_CANARY=1");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned char band[LX_GUARD_BYTES];
+    for (auto &g : h->guards)
+    {
+        if (g.second == (size_t)-1) continue;
+        CK(cudaMemcpy(band, (char *)g.first + g.second, LX_GUARD_BYTES, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < LX_GUARD_BYTES; i++)
+            if (band[i] != 0xA5)
+            {
+                (*violations)++;
+                break;
+            }
+    }
     return 0;
 }
 

@@ -75,6 +75,7 @@ struct Params
     unsigned cyc_max;
     double cyc_step;
     int mod_x, mod_active, mod_inactive, min_viol, phase1_v0;
+    int dfirst; // deactivate_first_wrong_sign (lexlsi.h:1048-1105): drop the wrong-sign constraint that was activated first
     int dmma; // Gauss step: Schur update (and the off-diagonal part of Left * inv(R)) on the FP64 tensor cores
 };
 
@@ -119,6 +120,7 @@ struct Buffers
     double *lexdata;           // LSI, with xstar: [B][(n+1) x M] that problem's constraints as given (LexLSE::get_data, lexlse.h:119, :1631)
     double *lexqr_star;        // LSI, with xstar: [B][(n+1) x M] its factorization (what get_lexqr returns after get_xStar)
     double *hh_star;           // LSI, with xstar: [B][M]
+    unsigned *wsl;             // LSI, deactivate_first_wrong_sign: [B][Mall] chronological list of activations (obj << 16 | ctr), lexlsi.h:158
     const unsigned *glist;     // LSI: [B][gcap] api_activate calls in CALL ORDER: obj << 24 | type << 16 | ctr, 0xFFFFFFFF ends the list; or null
     unsigned gcap;
     double *wslog;             // LSI: [B][wslog_cap][6] working-set log {obj, ctr, type, alpha_or_lambda, rank, cycling} or null
@@ -1952,6 +1954,49 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             gsync<W>();
         }
 
+        // WS of the reference (lexlsi.h:158, :190-192): every activation in chronological order, across objectives.  Only
+        // deactivate_first_wrong_sign reads it.  The initial working set was built level by level above; its order in time is:
+        // all equalities (setData order: level-major, rows ascending — the EQ prefix of each active[] list), then the guess
+        // (call order of the list, or level-major / row ascending).  Thread 0 owns the list from here on.
+        unsigned *const wsl = bf.wsl ? bf.wsl + p * (unsigned long long)sh.Mall : nullptr;
+        int wsn             = 0;
+        if (wsl && tid == 0)
+        {
+            for (int k = 0; k < P; k++)
+                for (int a = 0; a < c.nact[k] && c.atype[sh.uoff[k] + a] == CTR_ACTIVE_EQ; a++)
+                    wsl[wsn++] = ((unsigned)k << 16) | c.active[sh.uoff[k] + a];
+            const int neq = wsn;
+            if (bf.glist)
+            {
+                const unsigned *gl = bf.glist + p * bf.gcap;
+                for (unsigned e = 0; e < bf.gcap && gl[e] != 0xFFFFFFFFu; e++)
+                {
+                    const unsigned w  = gl[e];
+                    const int ko = (int)(w >> 24), t = (int)((w >> 16) & 0xffu), i = (int)(w & 0xffffu);
+                    if (i >= sh.dim[ko] || c.alltype[sh.uoff[ko] + i] != t) continue; // not activated by this call
+                    const unsigned key = ((unsigned)ko << 16) | (unsigned)i;
+                    bool seen          = false;
+                    for (int q = neq; q < wsn; q++) seen = seen || wsl[q] == key;
+                    if (!seen) wsl[wsn++] = key;
+                }
+            }
+            else
+                for (int k = 0; k < P; k++)
+                    for (int a = 0; a < c.nact[k]; a++)
+                        if (c.atype[sh.uoff[k] + a] != CTR_ACTIVE_EQ) wsl[wsn++] = ((unsigned)k << 16) | c.active[sh.uoff[k] + a];
+        }
+        auto track_add = [&](int k, int i) {
+            if (wsl) wsl[wsn++] = ((unsigned)k << 16) | (unsigned)i;
+        };
+        auto track_del = [&](int k, int i) { // order-preserving erase, as std::vector::erase
+            if (!wsl) return;
+            const unsigned key = ((unsigned)k << 16) | (unsigned)i;
+            int q              = 0;
+            while (q < wsn && wsl[q] != key) q++;
+            for (; q + 1 < wsn; q++) wsl[q] = wsl[q + 1];
+            wsn--;
+        };
+
         unsigned nIter = 0, nFact = 0, nAct = 0, nDeact = 0, cycCounter = 0;
         int status = ST_UNKNOWN, totalRank = 0, nFixed = 0, nFixedPrev = 0;
         int cycPrevOp = OP_UNDEFINED, cycPrevObj = 0, cycPrevCtr = 0, cycPrevType = CTR_INACTIVE;
@@ -2007,9 +2052,15 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                             if (t == CTR_INACTIVE && pr.mod_inactive)
                             {
                                 if (ax <= ov.lb(k, i))
+                                {
                                     ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                    track_add(k, i);
+                                }
                                 else if (ax >= ov.ub(k, i))
+                                {
                                     ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                    track_add(k, i);
+                                }
                             }
                             else if (t == CTR_ACTIVE_LB && pr.mod_active)
                             {
@@ -2018,7 +2069,12 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                                     int a = 0;
                                     while (c.active[o + a] != i) a++;
                                     ws_deactivate(c, sh, k, a);
-                                    if (ax >= ov.ub(k, i)) ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                    track_del(k, i);
+                                    if (ax >= ov.ub(k, i))
+                                    {
+                                        ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                        track_add(k, i);
+                                    }
                                 }
                             }
                             else if (t == CTR_ACTIVE_UB && pr.mod_active)
@@ -2028,7 +2084,12 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                                     int a = 0;
                                     while (c.active[o + a] != i) a++;
                                     ws_deactivate(c, sh, k, a);
-                                    if (ax <= ov.lb(k, i)) ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                    track_del(k, i);
+                                    if (ax <= ov.lb(k, i))
+                                    {
+                                        ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                        track_add(k, i);
+                                    }
                                 }
                             }
                         }
@@ -2171,7 +2232,11 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                 idCtr  = c.inactive[gq];
                 idType = (bl.pos & 1) ? CTR_ACTIVE_UB : CTR_ACTIVE_LB;
                 gsync<W>();
-                if (tid == 0) ws_activate(c, sh, idObj, idCtr, idType);
+                if (tid == 0)
+                {
+                    ws_activate(c, sh, idObj, idCtr, idType);
+                    track_add(idObj, idCtr);
+                }
                 log_entry(idObj, idCtr, idType, alpha);
                 nAct++;
                 operation = OP_ADD;
@@ -2184,12 +2249,38 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                 {
                     int found = 0, ctr2rem = 0, obj2rem = 0;
                     double lam2rem = 0.0;
+                    int jfound = 0;
                     for (int j = 0; j < G; j++)
                         if (lse_sensitivity(c, n, ld, j, nFixed, pr.tol_wrong, pr.tol_correct, ctr2rem, obj2rem, lane, &lam2rem))
                         {
-                            found = 1;
+                            found  = 1;
+                            jfound = j;
                             break;
                         }
+                    if (found && pr.dfirst && lane == 0)
+                    {
+                        // findActiveCtr2Remove_first, lexlsi.h:1063-1105: among the constraints of groups jfound, .., 0 whose
+                        // multiplier has the wrong sign (the workspace still holds them), the earliest entry of WS.  Hierarchies
+                        // with a simple-bounds objective are refused by set_params (the reference reads out of bounds there).
+                        lam2rem = 0.0; // lexlsi.h:1069
+                        for (int e = 0; e < wsn; e++)
+                        {
+                            const int k = (int)(wsl[e] >> 16), i = (int)(wsl[e] & 0xffffu), g = k - sh.off;
+                            if (g < 0 || g > jfound) continue;
+                            int a = 0;
+                            while (c.active[sh.uoff[k] + a] != i) a++;
+                            const int row = c.frow[g] + a, t = c.ctype[row];
+                            if (t == CTR_ACTIVE_EQ || t == CORRECT_SIGN_OF_LAMBDA) continue;
+                            double lam = c.wsp[nFixed + row];
+                            if (t == CTR_ACTIVE_LB) lam = -lam;
+                            if (lam < -pr.tol_wrong)
+                            {
+                                ctr2rem = a;
+                                obj2rem = g;
+                                break;
+                            }
+                        }
+                    }
                     if (lane == 0)
                     {
                         c.scal[2] = found;
@@ -2206,7 +2297,11 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
                     idType = c.atype[sh.uoff[idObj] + c.scal[3]];
                     log_entry(idObj, idCtr, CTR_INACTIVE, *(const double *)(c.scal + 6));
                     gsync<W>();
-                    if (tid == 0) ws_deactivate(c, sh, idObj, c.scal[3]);
+                    if (tid == 0)
+                    {
+                        ws_deactivate(c, sh, idObj, c.scal[3]);
+                        track_del(idObj, idCtr);
+                    }
                     nDeact++;
                     operation = OP_REMOVE;
                 }

@@ -639,6 +639,70 @@ public:
         return found;
     }
 
+    // lexlse.h:866-910: every constraint of the group whose multiplier has the wrong sign (same re-typing side effect)
+    void findDescentDirectionList(Index ObjIndex, int FirstRowIndex, Index ObjDim, const double *lambda, double tol_wrong_sign_lambda,
+                                  double tol_correct_sign_lambda, std::vector<std::pair<int, int>> &ctr_wrong_sign)
+    {
+        for (Index k = 0; k < ObjDim; k++)
+        {
+            const Index ind = (Index)FirstRowIndex + k;
+            int *aCtrType   = &ctr_type[ind];
+            if (*aCtrType != CTR_ACTIVE_EQ && *aCtrType != CORRECT_SIGN_OF_LAMBDA)
+            {
+                double aLambda = lambda[ind];
+                if (*aCtrType == CTR_ACTIVE_LB) aLambda = -aLambda;
+                if (aLambda > tol_correct_sign_lambda)
+                    *aCtrType = CORRECT_SIGN_OF_LAMBDA;
+                else if (aLambda < -tol_wrong_sign_lambda)
+                    ctr_wrong_sign.push_back(std::make_pair((int)ObjIndex, (int)k));
+            }
+        }
+    }
+
+    // lexlse.h:511-602 (the variant behind deactivate_first_wrong_sign): all constraints with a wrong-sign multiplier of
+    // objective ObjIndex.  Same arithmetic as ObjectiveSensitivity above.  Restated for nVarFixed == 0 ONLY: with fixed
+    // variables the reference (lexlse.h:596-599) tests Lambda — the multipliers of the general constraints — instead of
+    // LambdaFixed, over obj_info[0].dim entries with the fixed variables' types, and LexLSI then indexes the active list
+    // of the simple-bounds objective with those positions (lexlsi.h:1092), out of bounds whenever the position exceeds the
+    // number of active bounds: undefined behaviour that cannot be a parity target.
+    void ObjectiveSensitivityList(Index ObjIndex, double tol_wrong_sign_lambda, double tol_correct_sign_lambda,
+                                  std::vector<std::pair<int, int>> &ctr_wrong_sign)
+    {
+        if (nVarFixed > 0)
+            throw Exception("deactivate_first_wrong_sign with fixed variables / a simple-bounds objective is undefined in the reference (lexlse.h:596-599)");
+        Index nLambda = 0, nRank = 0;
+        for (Index k = 0; k < ObjIndex; k++)
+        {
+            nLambda += obj_info[k].dim;
+            nRank += obj_info[k].rank;
+        }
+        nLambda += obj_info[ObjIndex].dim;
+        const Index total = nLambda + nRank;
+        for (Index i = 0; i < total; i++) dWorkspace[i] = 0.0;
+        double *Lambda = &dWorkspace[0];
+        double *rhs    = &dWorkspace[nLambda];
+        Index fr = obj_info[ObjIndex].first_row_index, fc = obj_info[ObjIndex].first_col_index;
+        Index dim = obj_info[ObjIndex].dim, rank = obj_info[ObjIndex].rank;
+        for (Index i = rank; i < dim; i++) Lambda[fr + i] = -L(fr + i, nVar);
+        applyQ(ObjIndex, Lambda + fr);
+        findDescentDirectionList(ObjIndex, (int)fr, dim, Lambda, tol_wrong_sign_lambda, tol_correct_sign_lambda, ctr_wrong_sign);
+        if (ObjIndex > 0)
+        {
+            subtractTransposeProduct(rhs, fc, fr, dim, Lambda);
+            for (Index k = ObjIndex; k--;)
+            {
+                fr   = obj_info[k].first_row_index;
+                fc   = obj_info[k].first_col_index;
+                dim  = obj_info[k].dim;
+                rank = obj_info[k].rank;
+                for (Index i = 0; i < rank; i++) Lambda[fr + i] = rhs[fc + i];
+                applyQ(k, Lambda + fr);
+                subtractTransposeProduct(rhs, fc, fr, dim, Lambda);
+                findDescentDirectionList(k, (int)fr, dim, Lambda, tol_wrong_sign_lambda, tol_correct_sign_lambda, ctr_wrong_sign);
+            }
+        }
+    }
+
     // getters ------------------------------------------------------------------------------
     const std::vector<double> &get_x() const { return x; }
     Index getDim(Index k) const { return obj_info[k].dim; }
@@ -1345,6 +1409,39 @@ private:
         return found;
     }
 
+    // lexlsi.h:1063-1105 (+ findFirstCtrWrongSign :1034-1046): of the constraints whose multiplier has the wrong sign for the
+    // first objective that has any, remove the one that entered the working set FIRST (WS = chronological list of activations)
+    bool findActiveCtr2Remove_first(Index &ObjIndex2Remove, Index &CtrIndex2Remove, double &lambda_wrong_sign)
+    {
+        if (nObjOffset > 0)
+            throw Exception("deactivate_first_wrong_sign with a simple-bounds objective is undefined in the reference (lexlse.h:596-599)");
+        std::vector<std::pair<int, int>> wrong;
+        lambda_wrong_sign = 0; // lexlsi.h:1069
+        bool found        = false;
+        for (Index k = 0; k < nObj - nObjOffset; k++)
+        {
+            lexlse.ObjectiveSensitivityList(k, parameters.tol_wrong_sign_lambda, parameters.tol_correct_sign_lambda, wrong);
+            if (!wrong.empty())
+            {
+                found = true;
+                break;
+            }
+        }
+        if (!found) return false;
+        for (auto &w : wrong) // positions in the active lists -> constraint indices, lexlsi.h:1088-1095
+        {
+            w.first += (int)nObjOffset;
+            w.second = (int)objectives[w.first].ws.active[w.second];
+        }
+        Index k = 0;
+        for (;; k++)
+            if (std::find(wrong.begin(), wrong.end(), std::make_pair((int)WS[k].first, (int)WS[k].second)) != wrong.end()) break;
+        ObjIndex2Remove = WS[k].first;
+        const std::vector<Index> &act = objectives[ObjIndex2Remove].ws.active;
+        CtrIndex2Remove = (Index)(std::find(act.begin(), act.end(), WS[k].second) - act.begin()); // getCtrIndex, :1101
+        return true;
+    }
+
     // lexlsi.h:1144-1265
     OperationType verifyWorkingSet()
     {
@@ -1391,9 +1488,10 @@ private:
         else if (normalIteration)
         {
             double lambda_wrong_sign;
-            if (parameters.deactivate_first_wrong_sign)
-                throw Exception("deactivate_first_wrong_sign is not restated in the oracle");
-            if (findActiveCtr2Remove_largest(ObjIndex2Manipulate, CtrIndex2Manipulate, lambda_wrong_sign))
+            const bool found = parameters.deactivate_first_wrong_sign // lexlsi.h:1048-1060
+                                   ? findActiveCtr2Remove_first(ObjIndex2Manipulate, CtrIndex2Manipulate, lambda_wrong_sign)
+                                   : findActiveCtr2Remove_largest(ObjIndex2Manipulate, CtrIndex2Manipulate, lambda_wrong_sign);
+            if (found)
             {
                 const WorkingSet &w = objectives[ObjIndex2Manipulate].ws;
                 id_obj              = ObjIndex2Manipulate;

@@ -284,3 +284,101 @@ def test_working_set_log_count_never_exceeds_capacity(oracle):
         cut, n_cut = s.getWorkingSetLog(capacity=3)
     assert n_full.max() > 3 and (n_cut == np.minimum(n_full, 3)).all()
     assert np.array_equal(cut[:, :3, :], full[:, :3, :])
+
+
+# ---- deactivate_first_wrong_sign (lexlsi.h:1048-1105) -----------------------------------------------------------------
+def test_deactivate_first_wrong_sign_matches_the_oracle(oracle):
+    """Removal rule 'first': of the constraints with a wrong-sign multiplier, the one activated first (the reference's
+    chronological WS list) — different trajectories from the default 'largest' rule, identical to the oracle's."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    rng = np.random.default_rng(17)
+    # general hierarchies only: 4 levels of inequalities / equalities, n = 14
+    n, dims, B = 14, [6, 5, 7, 14], 96
+    data = []
+    for k, m in enumerate(dims):
+        A = rng.standard_normal((B, m, n))
+        ub = rng.random((B, m))
+        lb = ub - rng.random((B, m)) if k != 1 else ub
+        data.append(np.ascontiguousarray(np.concatenate([A, lb[:, :, None], ub[:, :, None]], axis=2).transpose(0, 2, 1)))
+
+    class W:
+        nVar, ObjDim, ObjType = n, dims, [0, 0, 0, 0]
+    par = dict(deactivate_first_wrong_sign=1, max_number_of_factorizations=300, log_working_set_enabled=1)
+    got, ref = _lsi_both(oracle, W, data, None, **par)
+    compare_lsi(got, ref, len(dims))
+    assert np.array_equal(got["x"], ref["x"])
+    assert got["counters"][:, 2].sum() > 0  # constraints really were removed
+    largest = oracle.lsi_solve_batch(n, dims, [0] * 4, data, params=oracle.OracleParams(max_number_of_factorizations=300), threads=0)
+    assert not np.array_equal(largest["counters"][:, :4], ref["counters"][:, :4])  # the rule matters
+    # warm start with a call list: the guess enters WS in call order
+    w = problems.workload("c4", 6)
+    d4, _ = problems.generate(w)
+    got4, ref4 = _lsi_both(oracle, w, d4, None, deactivate_first_wrong_sign=1, max_number_of_factorizations=40)
+    compare_lsi(got4, ref4, len(w.ObjDim))
+    assert np.array_equal(got4["x"], ref4["x"])
+
+
+def test_deactivate_first_wrong_sign_is_refused_with_simple_bounds():
+    import lexls_b200 as lx
+    with lx.LexLSIBatch(4, [3, 2], [1, 0], batch=2) as s:
+        with pytest.raises(lx.LexLSError) as e:
+            s.setParameters(lx.Params(deactivate_first_wrong_sign=1))
+        assert e.value.code == 3 and "lexlse.h:596" in str(e.value)
+    with lx.LexLSIBatch(4, [3, 2], [0, 0], batch=2) as s:
+        s.setParameters(lx.Params(deactivate_first_wrong_sign=1))
+
+
+def test_result_buffers_keep_their_guard_bands(monkeypatch):
+    """LEXLS_B200_CANARY=1 (stand-in for compute-sanitizer memcheck, which is closed on the GPU pool): every device buffer of a
+    handle is followed by a guard band; after solves of every kernel family no band may have been written into."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    monkeypatch.setenv("LEXLS_B200_CANARY", "1")
+    rng = np.random.default_rng(2)
+
+    def lse(n, dims, B, **envs):
+        for k, v in envs.items():
+            monkeypatch.setenv("LEXLS_B200_" + k, str(v))
+        data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+        with lx.LexLSEBatch(n, dims, batch=B) as s:
+            s.request_outputs(lexqr=True)
+            s.fixVariables(np.tile(np.array([1, 0], dtype=np.uint32), (B, 1)), rng.standard_normal((B, 2)))
+            for k, d in enumerate(data):
+                s.setData(k, d)
+            s.solve()
+            s.get_x(), s.get_lexqr()
+            bad = s.check_guard_bands()
+            name = s.kernel_info()["name"]
+        for k in envs:
+            monkeypatch.delenv("LEXLS_B200_" + k)
+        return name, bad
+
+    def lsi(name, B, **envs):
+        for k, v in envs.items():
+            monkeypatch.setenv("LEXLS_B200_" + k, str(v))
+        w = problems.workload(name, B)
+        data, vi = problems.generate(w)
+        with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=B) as s:
+            s.setParameters(lx.Params(log_working_set_enabled=1, max_number_of_factorizations=8))
+            s.request_outputs(lexqr=True, multipliers=True, xstar=True)
+            for k, d in enumerate(data):
+                s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+            s.solve()
+            s.get_x(), s.get_xStar(), s.getWorkingSetLog(16)
+            bad = s.check_guard_bands()
+            kname = s.kernel_info()["name"]
+        for k in envs:
+            monkeypatch.delenv("LEXLS_B200_" + k)
+        return kname, bad
+
+    seen = {}
+    for res in (lse(40, [20, 20, 20], 33), lse(12, [5, 4, 6], 7), lse(30, [9, 14, 6], 9, WARPS=2), lse(30, [9, 14, 6], 9, WARPS=4),
+                lse(30, [9, 14, 6], 5, WARPS=8), lse(37, [9, 14, 6, 11], 5, FORCE_LODGLOBAL=1, LG_WARPS=8),
+                lse(37, [9, 14, 6, 11], 5, FORCE_LODGLOBAL=1, LG_WARPS=16, DMMA=0),
+                lsi("tiny_lsi", 9), lsi("c3", 11), lsi("c3", 5, WARPS=1), lsi("c3", 5, WARPS=4), lsi("c3", 5, WARPS=8),
+                lsi("c3", 5, DATA="smem", WARPS=4), lsi("c3", 4, FORCE_LODGLOBAL=1, LG_WARPS=8), lsi("c3", 4, FORCE_LODGLOBAL=1, LG_WARPS=16),
+                lsi("c4", 2)):
+        seen[res[0]] = seen.get(res[0], 0) + res[1]
+    assert len(seen) >= 12, seen
+    assert all(v == 0 for v in seen.values()), seen
