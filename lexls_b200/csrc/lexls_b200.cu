@@ -453,6 +453,14 @@ static int plan(lexls_b200_batch *h)
     h->per_sm = per_sm;
     unsigned long long g = (unsigned long long)prop.multiProcessorCount * per_sm;
     if (g > h->batch) g = h->batch;
+    if (LG)
+        if (const char *e = getenv("LEXLS_B200_LG_GRID"))
+        {
+            // experiment knob (profiles/r2_c4_traffic.json): fewer problems in flight so that their work matrices and objective
+            // records stay L2-resident (1.3 MB per C4 problem, 126 MB of L2) — less DRAM traffic, less latency hiding
+            const unsigned long long cap = strtoull(e, nullptr, 10);
+            if (cap >= 1 && cap < g) g = cap;
+        }
     if (g < 1) g = 1;
     h->grid = (unsigned)g;
     if (LG)
@@ -1167,6 +1175,22 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     h->flag_pending = true;
     CK(cudaEventRecord(h->ev0, h->stream));
     void *args[] = {(void *)&h->sh, (void *)&h->pr, (void *)&h->sm, (void *)&b};
+    if (h->LG && getenv("LEXLS_B200_LG_PERSIST"))
+    {
+        // experiment knob: ask L2 to keep the work-matrix scratch (read and written many times per factorization) and let the
+        // objective records (read twice per iteration) stream
+        const cudaDeviceProp *pp = nullptr;
+        if (int rc = device_props(h->device, &pp)) return rc;
+        const size_t want = std::min(h->lod_bytes, (size_t)pp->persistingL2CacheMaxSize);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr  = h->lod_scratch;
+        av.accessPolicyWindow.num_bytes = std::min(h->lod_bytes, (size_t)pp->accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio  = (float)std::min(1.0, (double)want / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+        av.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CK(cudaLaunchKernel((const void *)k, dim3(h->grid), dim3(32 * h->W), args, h->smem, h->stream));
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
