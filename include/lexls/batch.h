@@ -56,12 +56,17 @@ public:
 
     uint64_t size() const { return batch; }
     lexls_b200_batch_t *handle() { return h_; } // for the *_dev entry points and lexls_b200_set_stream
+    void setRegularizationFactor(Index ObjIndex, RealScalar factor) // lexlsi.h:497 (one factor per objective for the whole batch)
+    {
+        internal::lexls_b200_check(lexls_b200_set_regularization_factor(h_, ObjIndex, factor));
+    }
 
     void setParameters(const ParametersLexLSI &par) // lexlsi.h:325
     {
-        if (par.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
         lexls_b200_params_t p;
         lexls_b200_default_params(&p);
+        p.regularization_type            = static_cast<int32_t>(par.regularization_type);
+        p.variable_regularization_factor = par.variable_regularization_factor;
         p.max_number_of_factorizations = par.max_number_of_factorizations;
         p.tol_linear_dependence        = par.tol_linear_dependence;
         p.tol_wrong_sign_lambda        = par.tol_wrong_sign_lambda;
@@ -252,11 +257,16 @@ public:
 
     uint64_t size() const { return batch; }
     lexls_b200_batch_t *handle() { return h_; }
+    void setRegularizationFactor(Index ObjIndex, RealScalar factor) // lexlse.h:1478
+    {
+        internal::lexls_b200_check(lexls_b200_set_regularization_factor(h_, ObjIndex, factor));
+    }
     void setParameters(const ParametersLexLSE &par) // lexlse.h:1467
     {
-        if (par.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
         lexls_b200_params_t p;
         lexls_b200_default_params(&p);
+        p.regularization_type            = static_cast<int32_t>(par.regularization_type);
+        p.variable_regularization_factor = par.variable_regularization_factor;
         p.tol_linear_dependence = par.tol_linear_dependence;
         internal::lexls_b200_check(lexls_b200_set_params(h_, &p));
     }

@@ -86,6 +86,13 @@ public:
         if (ObjIndex >= nObj || CtrIndex >= dim[ObjIndex]) throw Exception("CtrIndex >= nCtr");
         ctr_type_[first_row[ObjIndex] + CtrIndex] = static_cast<uint8_t>(type);
     }
+    void setRegularizationFactor(Index ObjIndex, RealScalar factor) // lexlse.h:1478
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        if (reg_factor.size() < nObj) reg_factor.resize(nObj, 0.0);
+        reg_factor[ObjIndex] = factor;
+        if (h_) lexls_b200_check(lexls_b200_set_regularization_factor(h_, ObjIndex, factor));
+    }
     void setFixedVariablesCount(Index nVarFixed_) // lexlse.h:1449
     {
         if (nVarFixed_ > nVar) throw Exception("Cannot fix more than nVar variables");
@@ -151,16 +158,18 @@ private:
     }
     void applyParameters()
     {
-        if (parameters.regularization_type != REGULARIZATION_NONE) throw Exception("regularization is not part of the B200 hot path");
         lexls_b200_params_t p;
         lexls_b200_default_params(&p);
-        p.tol_linear_dependence = parameters.tol_linear_dependence;
-        lexls_b200_check(lexls_b200_set_params(h_, &p));
+        p.tol_linear_dependence          = parameters.tol_linear_dependence;
+        p.regularization_type            = static_cast<int32_t>(parameters.regularization_type);
+        p.variable_regularization_factor = parameters.variable_regularization_factor;
+        lexls_b200_check(lexls_b200_set_params(h_, &p)); // the conjugate-gradient variants and TIKHONOV_1 are refused here
+        for (Index k = 0; k < nObj && k < reg_factor.size(); k++) lexls_b200_check(lexls_b200_set_regularization_factor(h_, k, reg_factor[k]));
     }
     lexls_b200_batch_t *h_;
     Index nVar, nObj, nCtr, nVarFixed, nVarFixedInit, TotalRank;
     std::vector<Index> maxDim, dim, first_row, ranks, fixed_index;
-    std::vector<RealScalar> fixed_value;
+    std::vector<RealScalar> fixed_value, reg_factor;
     std::vector<uint8_t> fixed_type;
     ParametersLexLSE parameters;
     dVectorType x, v, hh_;

@@ -99,6 +99,11 @@ public:
         else
             std::printf("WARNING: the user cannot define explicitly which constraints are of type CTR_ACTIVE_EQ \n\n");
     }
+    void setRegularizationFactor(Index ObjIndex, RealScalar factor) // lexlsi.h:497
+    {
+        if (ObjIndex >= nObj) throw Exception("ObjIndex >= nObj");
+        lexls_b200_check(lexls_b200_set_regularization_factor(h_, ObjIndex, factor));
+    }
     void set_x0(const dVectorType &x0) { lexls_b200_check(lexls_b200_set_x0(h_, x0.data())); }                  // lexlsi.h:306
     void set_v0(Index ObjIndex, dVectorType &v0_) { lexls_b200_check(lexls_b200_set_v0(h_, ObjIndex, v0_.data())); } // :317
 
@@ -238,6 +243,7 @@ private:
         p.use_phase1_v0                = parameters.use_phase1_v0;
         p.log_working_set_enabled      = parameters.log_working_set_enabled;
         p.deactivate_first_wrong_sign  = parameters.deactivate_first_wrong_sign;
+        p.variable_regularization_factor = parameters.variable_regularization_factor;
         lexls_b200_check(lexls_b200_set_params(h_, &p));
     }
     lexls_b200_batch_t *h_;

@@ -70,7 +70,9 @@ extern "C" {
 #define LEXLS_B200_MAX_NUMBER_OF_FACTORIZATIONS_EXCEEDED 2
 
 /* POD mirror of ParametersLexLSI (typedefs.h:127-295; defaults :268-294) and ParametersLexLSE (:78-125).
- * regularization_type must be 0 (REGULARIZATION_NONE): the damping family is outside the hot path. */
+ * regularization_type (typedefs.h:32-44): 0 NONE, 1 TIKHONOV, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 8 TIKHONOV_2, 9 TEST are implemented
+ * (lexlse.h:274-411, :1700-1760, :2078-2251, :2592-2625); 2 / 6 (conjugate-gradient variants) and 7 (the reference's own
+ * test variant) are EUNSUPPORTED.  Regularized batches run on the shared-memory kernels (two or more warps per problem). */
 typedef struct lexls_b200_params
 {
     uint32_t max_number_of_factorizations; /* 200   */
@@ -89,6 +91,7 @@ typedef struct lexls_b200_params
     int32_t use_phase1_v0;                 /* 0     */
     int32_t log_working_set_enabled;       /* 0     */
     int32_t deactivate_first_wrong_sign;   /* 0; 1 = lexlsi.h:1063-1105 (EUNSUPPORTED with a simple-bounds objective: undefined in the reference) */
+    double variable_regularization_factor; /* 0.0: use the objectives' factors as they are; else typedefs.h:170-176 (lexlse.h:281-310) */
 } lexls_b200_params_t;
 
 typedef struct lexls_b200_batch lexls_b200_batch_t; /* opaque */
@@ -126,6 +129,9 @@ int lexls_b200_destroy(lexls_b200_batch_t *h);
 int lexls_b200_reset(lexls_b200_batch_t *h);
 int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p); /* setParameters lexlsi.h:325, lexlse.h:1467 */
 int lexls_b200_set_stream(lexls_b200_batch_t *h, void *cuda_stream);             /* NULL = the handle's own stream */
+/* LexLSI::setRegularizationFactor lexlsi.h:497 / LexLSE::setRegularizationFactor lexlse.h:1478: damping factor of objective
+ * `level` (one value for the whole batch; ignored for a simple-bounds objective, objective.h:489) */
+int lexls_b200_set_regularization_factor(lexls_b200_batch_t *h, uint32_t level, double factor);
 
 /* ---- problem data ---------------------------------------------------------------------------------------------
  * set_data: LexLSE::setData lexlse.h:1522-1530 ([A|b]) / LexLSI::setData lexlsi.h:350-435 ([A|lb|ub], equalities are

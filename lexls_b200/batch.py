@@ -90,6 +90,10 @@ class _Batch:
     def setParameters(self, params):
         check(lib().lexls_b200_set_params(self._h, C.byref(params)))
 
+    def setRegularizationFactor(self, level, factor):
+        """lexlsi.h:497 / lexlse.h:1478 — damping factor of one objective (with Params(regularization_type=...))."""
+        check(lib().lexls_b200_set_regularization_factor(self._h, C.c_uint32(level), C.c_double(float(factor))))
+
     def set_stream(self, stream_ptr):
         check(lib().lexls_b200_set_stream(self._h, C.c_void_p(stream_ptr)))
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "lexls_b200_last_solve_ms", "lexls_b200_measure_fp64_peak", "lexls_b200_request_outputs", "lexls_b200_get_lexqr",
     "lexls_b200_get_lambda", "lexls_b200_get_working_set_log", "lexls_b200_validate", "lexls_b200_create_batch_multi",
     "lexls_b200_shard_count", "lexls_b200_get_shard", "lexls_b200_get_xstar", "lexls_b200_set_active_guess_ordered",
-    "lexls_b200_check_guard_bands",
+    "lexls_b200_check_guard_bands", "lexls_b200_set_regularization_factor",
 ]
 OUT_LEXQR, OUT_LAMBDA, OUT_XSTAR = 1, 2, 4
 
@@ -48,6 +48,7 @@ class Params(C.Structure):
         ("use_phase1_v0", C.c_int32),
         ("log_working_set_enabled", C.c_int32),
         ("deactivate_first_wrong_sign", C.c_int32),
+        ("variable_regularization_factor", C.c_double),
     ]
 
     def __init__(self, **kw):

@@ -76,6 +76,10 @@ struct lexls_b200_batch
     unsigned *order = nullptr, *counters = nullptr, *ranks = nullptr, *colperm = nullptr;
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
     double *xstar = nullptr, *lexdata = nullptr, *lexqr_star = nullptr, *hh_star = nullptr; // LEXLS_B200_OUT_XSTAR
+    double reg_factor_user[LX_MAX_LEVELS] = {0};                   // setRegularizationFactor per user objective
+    double *reg_scratch = nullptr;                                 // regularization work arrays, one slice per resident CTA
+    size_t reg_bytes = 0;
+    uint64_t reg_stride = 0;
     unsigned *wsl = nullptr;                                       // chronological activation list (deactivate_first_wrong_sign)
     unsigned *glist = nullptr;                                     // api_activate calls in call order (set_active_guess_ordered)
     unsigned gcap = 0;
@@ -359,6 +363,7 @@ static int plan(lexls_b200_batch *h)
     {
         int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8) W = w;
+        if (h->user_params.regularization_type != 0 && W == 1) W = 2;
     }
     bool DS = false, LG = false;
     if (const char *e = getenv("LEXLS_B200_DATA"))
@@ -366,6 +371,7 @@ static int plan(lexls_b200_batch *h)
         if (!strcmp(e, "smem")) DS = lsi;
     }
     // every level handled by the register-window panel (lexls_panel.cuh): <= 48 columns, <= 40 rows per level
+    if (h->user_params.regularization_type != 0 && W == 1) W = 2; // the regularization routine lives in the shared-memory kernels
     bool panel_only = (W == 1) && cols <= 48;
     for (int k = 0; k < h->sh.P; k++)
         if (h->sh.dim[k] > 40 && !(lsi && h->sh.off && k == 0)) panel_only = false;
@@ -476,6 +482,20 @@ static int plan(lexls_b200_batch *h)
             h->lod_bytes = need;
         }
     }
+    if (h->user_params.regularization_type != 0)
+    {
+        const uint64_t n = (uint64_t)h->sh.n;
+        h->reg_stride    = 2 * n * (n + 1) + 3 * n + 8;
+        const size_t need = sizeof(double) * h->reg_stride * h->grid;
+        if (need > h->reg_bytes)
+        {
+            if (h->reg_scratch) guarded_free(h, h->reg_scratch);
+            h->reg_scratch = nullptr;
+            h->reg_bytes   = 0;
+            CK(guarded_malloc(h, (void **)&h->reg_scratch, need));
+            h->reg_bytes = need;
+        }
+    }
     h->planned = true;
     return 0;
 }
@@ -551,6 +571,7 @@ void lexls_b200_default_params(lexls_b200_params_t *p)
     p->use_phase1_v0                = 0;
     p->log_working_set_enabled      = 0;
     p->deactivate_first_wrong_sign  = 0;
+    p->variable_regularization_factor = 0.0;
 }
 int lexls_b200_device_count(int *count)
 {
@@ -581,6 +602,8 @@ static void to_dev_params(const lexls_b200_params_t &u, Params &p)
     p.min_viol     = u.set_min_init_ctr_violation;
     p.phase1_v0    = u.use_phase1_v0;
     p.dfirst       = u.deactivate_first_wrong_sign;
+    p.reg_type     = u.regularization_type;
+    p.reg_var      = u.variable_regularization_factor;
     // Gauss step on the FP64 tensor cores (mma.sync m8n8k4, bit-identical to the DFMA chain: profiles/r2_dmma_order.json);
     // LEXLS_B200_DMMA=0 selects the DFMA version for A/B measurements
     const char *e = getenv("LEXLS_B200_DMMA");
@@ -725,7 +748,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -758,8 +781,14 @@ int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
 {
     MULTI(h, false, lexls_b200_set_params(s.h, p));
     if (!h || !p) return fail(LEXLS_B200_EINVAL, "NULL argument");
-    if (p->regularization_type != 0)
-        return fail(LEXLS_B200_EUNSUPPORTED, "regularization is outside the hot-path scope (REGULARIZATION_NONE only)");
+    {
+        const int t = p->regularization_type; // typedefs.h:32-44
+        if (t < 0 || t > 9) return fail(LEXLS_B200_EINVAL, "unknown regularization type");
+        if (t == 2 || t == 6 || t == 7)
+            return fail(LEXLS_B200_EUNSUPPORTED, "REGULARIZATION_TIKHONOV_CG, RT_NO_Z_CG (iterative) and TIKHONOV_1 (the reference's test variant) are "
+                                                 "not implemented; TIKHONOV, TIKHONOV_2, R, R_NO_Z, RT_NO_Z and TEST are");
+        if ((h->user_params.regularization_type != 0) != (t != 0)) h->planned = false; // regularized solves run on the shared-memory routines
+    }
     if (p->deactivate_first_wrong_sign && h->kind == LEXLS_B200_LSI && h->sh.off)
         return fail(LEXLS_B200_EUNSUPPORTED,
                     "deactivate_first_wrong_sign with a simple-bounds objective: the reference tests the wrong multipliers and indexes out "
@@ -1138,6 +1167,12 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
         b.hh_star    = h->hh_star;
     }
     b.glist = h->have_glist ? h->glist : nullptr;
+    for (int g = 0; g < LX_MAX_LEVELS; g++) h->pr.reg_factor[g] = (g + s.off < s.P) ? h->reg_factor_user[g + s.off] : 0.0;
+    if (h->pr.reg_type != 0)
+    {
+        b.reg_scratch = h->reg_scratch;
+        b.reg_stride  = h->reg_stride;
+    }
     if (h->kind == LEXLS_B200_LSI && h->pr.dfirst)
     {
         if (!h->wsl) CK(guarded_malloc(h, (void **)&h->wsl, sizeof(unsigned) * (size_t)std::max(s.Mall, 1) * h->batch));
@@ -1503,6 +1538,15 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
     CK(cudaMemcpyAsync(h->glist, packed.data(), sizeof(unsigned) * packed.size(), cudaMemcpyHostToDevice, h->stream));
     if (int rc = wait_copy(h)) return rc;
     h->have_glist = true;
+    return 0;
+}
+
+int lexls_b200_set_regularization_factor(lexls_b200_batch_t *h, uint32_t level, double factor)
+{
+    MULTI(h, false, lexls_b200_set_regularization_factor(s.h, level, factor));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    if ((int)level >= h->sh.P) return fail(LEXLS_B200_EINVAL, "ObjIndex >= nObj");
+    h->reg_factor_user[level] = factor; // a simple-bounds objective is never regularized (objective.h:489-493): its factor is ignored
     return 0;
 }
 

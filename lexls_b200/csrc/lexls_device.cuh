@@ -75,6 +75,9 @@ struct Params
     unsigned cyc_max;
     double cyc_step;
     int mod_x, mod_active, mod_inactive, min_viol, phase1_v0;
+    int reg_type;       // RegularizationType, typedefs.h:32-44 (0 = none; 1 TIKHONOV, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 8 TIKHONOV_2, 9 TEST)
+    double reg_var;     // variable_regularization_factor, typedefs.h:170-176
+    double reg_factor[LX_MAX_LEVELS]; // setRegularizationFactor per LexLSE level (lexlse.h:1478, objective.h:492)
     int dfirst; // deactivate_first_wrong_sign (lexlsi.h:1048-1105): drop the wrong-sign constraint that was activated first
     int dmma; // Gauss step: Schur update (and the off-diagonal part of Left * inv(R)) on the FP64 tensor cores
 };
@@ -120,6 +123,8 @@ struct Buffers
     double *lexdata;           // LSI, with xstar: [B][(n+1) x M] that problem's constraints as given (LexLSE::get_data, lexlse.h:119, :1631)
     double *lexqr_star;        // LSI, with xstar: [B][(n+1) x M] its factorization (what get_lexqr returns after get_xStar)
     double *hh_star;           // LSI, with xstar: [B][M]
+    double *reg_scratch;       // regularization: [grid][reg_stride] = null-space basis Z (n x (n+1)) | D (n x (n+1)) | 3n work doubles
+    unsigned long long reg_stride;
     unsigned *wsl;             // LSI, deactivate_first_wrong_sign: [B][Mall] chronological list of activations (obj << 16 | ctr), lexlsi.h:158
     const unsigned *glist;     // LSI: [B][gcap] api_activate calls in CALL ORDER: obj << 24 | type << 16 | ctr, 0xFFFFFFFF ends the list; or null
     unsigned gcap;
@@ -422,7 +427,7 @@ namespace lexls_dev
 // for the duration of the level, so that only the column swaps of the other rows go to global memory (L2).
 template <int W, bool LGV>
 __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const int ld, const int fr, const int dim, int &ColIndex,
-                                              const double tol, double *const lv = nullptr, const int ldv = 0)
+                                              const double tol, double *const lv = nullptr, const int ldv = 0, double *const Zs = nullptr)
 {
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -544,6 +549,13 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                 const unsigned short s = c.varofcol[ColIndex];
                 c.varofcol[ColIndex] = c.varofcol[p];
                 c.varofcol[p]        = s;
+                if (Zs) // regularization: the accumulated null-space basis follows the column swap, lexlse.h:228-231
+                    for (int q = 0; q < fc0; q++)
+                    {
+                        const double z      = Zs[q + n * ColIndex];
+                        Zs[q + n * ColIndex] = Zs[q + n * p];
+                        Zs[q + n * p]        = z;
+                    }
             }
             if (rem > 1) c.hh[row] = tau;
         }
@@ -878,6 +890,333 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Regularization of one level, lexlse.h:274-411 (dispatch), :1700-1760 (tikhonov_1), :2078-2138 (tikhonov_2), :2143-2170 (R),
+// :2175-2202 (R_NO_Z), :2207-2242 (RT_NO_Z), :2247-2251 (TEST), :2592-2625 (accumulate_nullspace_basis).  A rarely used,
+// "not mature" (typedefs.h:178) family: one warp, the work arrays Z (accumulated null-space basis, n x (n+1)) and D (n x (n+1))
+// in a global scratch buffer.  Same arithmetic as the oracle: every entry of a product is one sequential fma chain in ascending
+// summation index, so entries may be computed by different lanes; the Cholesky factorization is column oriented.
+//   R(i,j) = LOD(fr+i, fc+j) for i <= j;  T(i,c) = LOD(fr+i, fc+r+c);  b(i) = LOD(fr+i, n);  q = fc - nFixed rows of Z are live
+// ---------------------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void regularize_level(double *const LOD, const int ld, const int n, const int fr, const int fc, const int r,
+                                              const int RC, const int nFixed, const int type, const double factor, const double var_eps,
+                                              const double *const invd, double *const scratch)
+{
+    const int lane = threadIdx.x & 31;
+    double *const Z = scratch, *const D = scratch + (size_t)n * (n + 1), *const d = D + (size_t)n * n, *const w0 = D + (size_t)n * (n + 1),
+                 *const w1 = w0 + n;
+    auto L  = [&](int row, int col) -> double & { return LOD[row + (size_t)ld * col]; };
+    auto Rm = [&](int i, int j) -> double { return LOD[fr + i + (size_t)ld * (fc + j)]; };
+    auto Tm = [&](int i, int c) -> double { return LOD[fr + i + (size_t)ld * (fc + r + c)]; };
+    auto Zn = [&](int p, int c) -> double & { return Z[p + (size_t)n * c]; };
+    auto Dm = [&](int i, int j) -> double & { return D[i + (size_t)n * j]; };
+    const int q = fc - nFixed;
+
+    // the factor, lexlse.h:277-311
+    double a = factor;
+    if (var_eps != 0.0)
+    {
+        a = 0.0;
+        if (r > 0)
+        {
+            double n0 = 0.0, n1 = 0.0;
+            if (lane == 0)
+            {
+                for (int i = 0; i < r; i++)
+                {
+                    w0[i] = L(fr + i, n);
+                    n0    = fma(w0[i], w0[i], n0);
+                }
+                for (int i = r; i--;)
+                {
+                    double acc = w0[i];
+                    for (int k = i + 1; k < r; k++) acc = fma(-Rm(i, k), w0[k], acc);
+                    w0[i] = acc / Rm(i, i);
+                }
+                for (int i = 0; i < r; i++) n1 = fma(w0[i], w0[i], n1);
+            }
+            n0 = __shfl_sync(0xffffffffu, n0, 0);
+            n1 = __shfl_sync(0xffffffffu, n1, 0);
+            const double ce = n0 / n1;
+            if (ce < var_eps) a = sqrt(1 - (ce * ce) / (var_eps * var_eps)) * factor;
+        }
+    }
+    const bool on   = !(fabs(a - 0.0) < 1e-15);
+    const double mu = a * a;
+
+    // Eigen::LLT on the leading N x N block of D (lower triangle), then solveInPlace(d)
+    auto llt_solve = [&](int N) {
+        for (int j = 0; j < N; j++)
+        {
+            double acc = Dm(j, j);
+            for (int k = 0; k < j; k++) acc = fma(-Dm(j, k), Dm(j, k), acc);
+            const double ljj = sqrt(acc);
+            __syncwarp();
+            if (lane == 0) Dm(j, j) = ljj;
+            for (int i = j + 1 + lane; i < N; i += 32)
+            {
+                double v = Dm(i, j);
+                for (int k = 0; k < j; k++) v = fma(-Dm(i, k), Dm(j, k), v);
+                Dm(i, j) = v / ljj;
+            }
+            __syncwarp();
+        }
+        if (lane == 0)
+        {
+            for (int i = 0; i < N; i++)
+            {
+                double v = d[i];
+                for (int k = 0; k < i; k++) v = fma(-Dm(i, k), d[k], v);
+                d[i] = v / Dm(i, i);
+            }
+            for (int i = N; i--;)
+            {
+                double v = d[i];
+                for (int k = i + 1; k < N; k++) v = fma(-Dm(k, i), d[k], v);
+                d[i] = v / Dm(i, i);
+            }
+        }
+        __syncwarp();
+    };
+    // b(0:r) = triu(R) d(0:r)
+    auto apply_R = [&]() {
+        for (int i = lane; i < r; i += 32)
+        {
+            double acc = 0.0;
+            for (int k = i; k < r; k++) acc = fma(Rm(i, k), d[k], acc);
+            w0[i] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < r; i += 32) L(fr + i, n) = w0[i];
+        __syncwarp();
+    };
+    // column j of the stacked [triu(R) T], row k
+    auto colRT = [&](int k, int j) -> double { return j < r ? (k <= j ? Rm(k, j) : 0.0) : Tm(k, j - r); };
+
+    auto tikhonov_1 = [&]() {
+        const int N = RC + r;
+        for (int e = lane; e < N * N; e += 32)
+        {
+            const int i = e / N, j = e - i * N;
+            if (j > i) continue;
+            double acc    = 0.0;
+            const int top = (j < r) ? j + 1 : r;
+            for (int k = 0; k < top; k++) acc = fma(colRT(k, i), colRT(k, j), acc);
+            double up = 0.0;
+            for (int p = 0; p < q; p++) up = fma(Zn(p, fc + i), Zn(p, fc + j), up);
+            acc      = fma(mu, up, acc);
+            Dm(i, j) = (i == j) ? acc + mu : acc;
+        }
+        for (int i = lane; i < N; i += 32)
+        {
+            double acc    = 0.0;
+            const int top = (i < r) ? i + 1 : r;
+            for (int k = 0; k < top; k++) acc = fma(colRT(k, i), L(fr + k, n), acc);
+            double up = 0.0;
+            for (int p = 0; p < q; p++) up = fma(Zn(p, fc + i), Zn(p, n), up);
+            d[i] = fma(mu, up, acc);
+        }
+        __syncwarp();
+        llt_solve(N);
+        for (int i = lane; i < r; i += 32)
+        {
+            double acc = 0.0;
+            for (int k = i; k < r; k++) acc = fma(Rm(i, k), d[k], acc);
+            for (int c = 0; c < RC; c++) acc = fma(Tm(i, c), d[r + c], acc);
+            w0[i] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < r; i += 32) L(fr + i, n) = w0[i];
+        __syncwarp();
+    };
+    auto tikhonov_2 = [&]() {
+        const int N = q + r, Wd = RC + r;
+        for (int e = lane; e < N * N; e += 32)
+        {
+            const int i = e / N, j = e - i * N;
+            if (j > i) continue;
+            double acc = 0.0;
+            if (i < r) // then j < r as well
+            {
+                for (int k = i; k < r; k++) acc = fma(Rm(i, k), Rm(j, k), acc);
+                for (int c = 0; c < RC; c++) acc = fma(Tm(i, c), Tm(j, c), acc);
+            }
+            else if (j >= r)
+            {
+                for (int c = 0; c < Wd; c++) acc = fma(Zn(i - r, fc + c), Zn(j - r, fc + c), acc);
+                acc = mu * acc;
+            }
+            else
+            {
+                for (int k = j; k < r; k++) acc = fma(Zn(i - r, fc + k), Rm(j, k), acc);
+                for (int c = 0; c < RC; c++) acc = fma(Zn(i - r, fc + r + c), Tm(j, c), acc);
+                acc = a * acc;
+            }
+            if (i == j)
+            {
+                w1[i]    = acc;
+                Dm(i, i) = acc + mu;
+            }
+            else
+            {
+                Dm(i, j) = acc;
+                Dm(j, i) = acc;
+            }
+        }
+        for (int i = lane; i < r; i += 32) d[i] = L(fr + i, n);
+        for (int p = lane; p < q; p += 32) d[r + p] = a * Zn(p, n);
+        __syncwarp();
+        llt_solve(N);
+        for (int i = lane; i < r; i += 32)
+        {
+            double acc = 0.0;
+            for (int j = 0; j < N; j++)
+            {
+                const double e = (i == j) ? ((w1[i] + mu) - mu) : (i > j ? Dm(j, i) : Dm(i, j));
+                acc            = fma(e, d[j], acc);
+            }
+            w0[i] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < r; i += 32) L(fr + i, n) = w0[i];
+        __syncwarp();
+    };
+    auto accumulate = [&]() {
+        const int rows = q + r;
+        for (int e = lane; e < r * r; e += 32) Zn(q + e / r, fc + e % r) = (e / r == e % r) ? 1.0 : 0.0;
+        __syncwarp();
+        for (int p = lane; p < rows; p += 32) // each lane owns rows of Z: Left := Left * inv(triu(R)), then Trailing -= Left * Up
+        {
+            for (int c = 0; c < r; c++)
+            {
+                double acc = Zn(p, fc + c);
+                for (int k = 0; k < c; k++) acc = fma(-Zn(p, fc + k), Rm(k, c), acc);
+                Zn(p, fc + c) = acc * invd[fc + c];
+            }
+            for (int j = fc + r; j <= n; j++)
+            {
+                double acc = Zn(p, j);
+                for (int k = 0; k < r; k++) acc = fma(-Zn(p, fc + k), L(fr + k, j), acc);
+                Zn(p, j) = acc;
+            }
+        }
+        __syncwarp();
+    };
+
+    switch (type)
+    {
+    case 1: // REGULARIZATION_TIKHONOV
+        if (on)
+        {
+            if (fc + r <= RC)
+                tikhonov_2();
+            else
+                tikhonov_1();
+        }
+        accumulate();
+        break;
+    case 8: // REGULARIZATION_TIKHONOV_2
+        if (on) tikhonov_2();
+        accumulate();
+        break;
+    case 3: // REGULARIZATION_R
+        if (on)
+        {
+            for (int e = lane; e < r * r; e += 32)
+            {
+                const int i = e / r, j = e - i * r;
+                if (j > i) continue;
+                double acc = 0.0;
+                for (int k = 0; k <= j; k++) acc = fma(Rm(k, i), Rm(k, j), acc);
+                double up = 0.0;
+                for (int p = 0; p < q; p++) up = fma(Zn(p, fc + i), Zn(p, fc + j), up);
+                acc      = fma(mu, up, acc);
+                Dm(i, j) = (i == j) ? acc + mu : acc;
+            }
+            for (int i = lane; i < r; i += 32)
+            {
+                double up = 0.0;
+                for (int p = 0; p < q; p++) up = fma(Zn(p, fc + i), Zn(p, n), up);
+                double acc = up * mu;
+                for (int k = 0; k <= i; k++) acc = fma(Rm(k, i), L(fr + k, n), acc);
+                d[i] = acc;
+            }
+            __syncwarp();
+            llt_solve(r);
+            apply_R();
+        }
+        accumulate();
+        break;
+    case 4: // REGULARIZATION_R_NO_Z
+        if (on)
+        {
+            for (int e = lane; e < r * r; e += 32)
+            {
+                const int i = e / r, j = e - i * r;
+                if (j > i) continue;
+                double acc = 0.0;
+                for (int k = 0; k <= j; k++) acc = fma(Rm(k, i), Rm(k, j), acc);
+                Dm(i, j) = (i == j) ? acc + mu : acc;
+            }
+            for (int i = lane; i < r; i += 32)
+            {
+                double acc = 0.0;
+                for (int k = 0; k <= i; k++) acc = fma(Rm(k, i), L(fr + k, n), acc);
+                d[i] = acc;
+            }
+            __syncwarp();
+            llt_solve(r);
+            apply_R();
+        }
+        break;
+    case 5: // REGULARIZATION_RT_NO_Z
+        if (on)
+        {
+            for (int e = lane; e < r * r; e += 32)
+            {
+                const int i = e / r, j = e - i * r;
+                if (j > i) continue;
+                double acc = 0.0;
+                for (int k = i; k < r; k++) acc = fma(Rm(i, k), Rm(j, k), acc);
+                for (int c = 0; c < RC; c++) acc = fma(Tm(i, c), Tm(j, c), acc);
+                if (i == j)
+                {
+                    w1[i]    = acc;
+                    Dm(i, i) = acc + mu;
+                }
+                else
+                {
+                    Dm(i, j) = acc;
+                    Dm(j, i) = acc;
+                }
+            }
+            for (int i = lane; i < r; i += 32) d[i] = L(fr + i, n);
+            __syncwarp();
+            llt_solve(r);
+            for (int i = lane; i < r; i += 32)
+            {
+                double acc = 0.0;
+                for (int j = 0; j < r; j++)
+                {
+                    const double e = (i == j) ? ((w1[i] + mu) - mu) : (i > j ? Dm(j, i) : Dm(i, j));
+                    acc            = fma(e, d[j], acc);
+                }
+                w0[i] = acc;
+            }
+            __syncwarp();
+            for (int i = lane; i < r; i += 32) L(fr + i, n) = w0[i];
+            __syncwarp();
+        }
+        break;
+    case 9: // REGULARIZATION_TEST
+        if (on)
+            for (int i = lane; i < r; i += 32) L(fr + i, n) = L(fr + i, n) * a;
+        __syncwarp();
+        break;
+    default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // l-QR factorization, lexlse.h:117-506 (REGULARIZATION_NONE)
 //   G levels with c.ldim[g] rows starting at c.frow[g]; nCtr = total rows; nFixed fixed variables whose values are in
 //   c.lx[0..nFixed) and indices in c.fidx.  Writes c.rank/c.fcol/c.hh/c.invd/c.colperm/c.varofcol; returns TotalRank.
@@ -886,9 +1225,17 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
 template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
-                                              const int nCtr, const int nFixed, const double tol, FlopCount &fl, const int dmma = 0)
+                                              const int nCtr, const int nFixed, const double tol, FlopCount &fl, const int dmma = 0,
+                                              const Params *const reg = nullptr, double *const reg_scratch = nullptr)
 {
     const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol, dmma);
+    // regularization (planned onto the shared-memory routines only, W >= 2): the null-space basis starts from zero, lexlse.h:1685
+    const bool regon = (W > 1) && reg && reg->reg_type != 0 && reg_scratch;
+    if (regon)
+    {
+        for (int e = threadIdx.x; e < n * (n + 1); e += 32 * W) reg_scratch[e] = 0.0;
+        gsync<W>();
+    }
     constexpr int NT = 32 * W;
     const int tid = threadIdx.x, lane = tid & 31;
     double *const LOD = c.LOD;
@@ -959,7 +1306,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__
         if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
-            qr_level_smem<W, LGV>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv);
+            qr_level_smem<W, LGV>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv, regon ? reg_scratch : nullptr);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
@@ -972,6 +1319,22 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__
             if (rp > 0) f += 3 * (rp * m - T1) + 4 * rp + 4 * (rp * m * cc - (m + cc) * T1 + T2);
             fl.f += (unsigned long long)f;
         }
+
+        if constexpr (W > 1)
+            if (regon)
+            {
+                // lexlse.h:274-411: between the QR of the level and its Gauss step (the modified right-hand side is what the
+                // lower levels see).
+                gsync<W>();
+                if (threadIdx.x < 32)
+                {
+                    regularize_level(LOD, ld, n, fr, fc, rank, n - ColIndex, nFixed, reg->reg_type, reg->reg_factor[g], reg->reg_var,
+                                     c.invd, reg_scratch);
+                    if constexpr (LGV) // the Gauss step reads the level's rows from the shared-memory view: refresh its right-hand side
+                        for (int i = threadIdx.x; i < rank; i += 32) c.LVIEW[(fr - 2 * (fr >> 1)) + i + smap.ldv * n] = LOD[fr + i + ld * n];
+                }
+                gsync<W>();
+            }
 
         // Gauss step, lexlse.h:431-471
         if (g + 1 < G && rank > 0)
@@ -1273,7 +1636,8 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma);
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma, &pr,
+                                                                                 bf.reg_scratch ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr);
         lse_solve<W, LG>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v) lse_get_v<W>(c, n, ld, G);
@@ -1754,7 +2118,8 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
 template <int W, bool DS, bool LG>
 __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap &sm, const double tol, double *lod, double *objp,
                                                   double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl,
-                                                  const int dmma, double *const data_dump = nullptr)
+                                                  const int dmma, double *const data_dump = nullptr, const Params *const reg = nullptr,
+                                                  double *const reg_scratch = nullptr)
 {
     extern __shared__ __align__(128) unsigned char smem_fs[];
     Ctx c = make_ctx(smem_fs, sm);
@@ -1767,7 +2132,7 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
         dump_lod<32 * W>(c, data_dump, nullptr, 0ull, sh.n, sh.ld, nCtr, sh.M);
         gsync<W>();
     }
-    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl, dmma);
+    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl, dmma, reg, reg_scratch);
     lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
@@ -1997,6 +2362,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             wsn--;
         };
 
+        double *const reg_scratch = bf.reg_scratch ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr;
         unsigned nIter = 0, nFact = 0, nAct = 0, nDeact = 0, cycCounter = 0;
         int status = ST_UNKNOWN, totalRank = 0, nFixed = 0, nFixedPrev = 0;
         int cycPrevOp = OP_UNDEFINED, cycPrevObj = 0, cycPrevCtr = 0, cycPrevType = CTR_INACTIVE;
@@ -2022,7 +2388,8 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             }
         };
         auto factor_and_solve = [&]() {
-            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma);
+            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma, nullptr,
+                                            pr.reg_type ? &pr : nullptr, reg_scratch);
         };
 
         // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------
@@ -2380,7 +2747,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             // get_xStar, lexlsi.h:519-526: formLexLSE + factorize + solve with the FINAL working set; get_data() and
             // get_lexqr() called after it return this problem's constraints and factorization (tests/test_numerical_error.cpp:83-86)
             lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma,
-                                            bf.lexdata + p * (unsigned long long)sh.M * (n + 1));
+                                            bf.lexdata + p * (unsigned long long)sh.M * (n + 1), pr.reg_type ? &pr : nullptr, reg_scratch);
             for (int k = tid; k < n; k += NT) bf.xstar[p * n + k] = c.lx[k];
             int nc = 0;
             for (int g = 0; g < G; g++) nc += c.ldim[g];

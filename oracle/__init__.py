@@ -9,4 +9,5 @@ from .pyoracle import (  # noqa: F401
     lse_solve_batch,
     lsi_solve_batch,
     lsi_solve_detail,
+    set_regularization,
 )

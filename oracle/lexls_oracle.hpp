@@ -95,6 +95,23 @@ struct Parameters
     bool use_phase1_v0                  = false;
     bool log_working_set_enabled        = false;
     bool deactivate_first_wrong_sign    = false;
+    int regularization_type             = 0;   // typedefs.h:32-44 (REGULARIZATION_NONE)
+    double variable_regularization_factor = 0.0; // typedefs.h:170-176
+};
+
+// typedefs.h:32-44
+enum RegularizationType
+{
+    REGULARIZATION_NONE        = 0,
+    REGULARIZATION_TIKHONOV    = 1,
+    REGULARIZATION_TIKHONOV_CG = 2, // not restated (iterative, "not mature")
+    REGULARIZATION_R           = 3,
+    REGULARIZATION_R_NO_Z      = 4,
+    REGULARIZATION_RT_NO_Z     = 5,
+    REGULARIZATION_RT_NO_Z_CG  = 6, // not restated
+    REGULARIZATION_TIKHONOV_1  = 7, // not restated (the reference's own "WARNING: TESTING" variant)
+    REGULARIZATION_TIKHONOV_2  = 8,
+    REGULARIZATION_TEST        = 9
 };
 
 struct Exception : public std::runtime_error
@@ -151,6 +168,7 @@ static inline bool isEqual(double a, double b, double tol = 1e-15)
 struct ObjectiveInfo
 {
     Index dim = 0, rank = 0, first_row_index = 0, first_col_index = 0;
+    double regularization_factor = 0.0; // typedefs.h:661
 };
 
 // typedefs.h:380-432
@@ -196,6 +214,8 @@ public:
         column_permutations.assign(nVar, 0);
         ColNorms.assign(nVar, 0.0);
         invdiag.assign(nVar, 0.0);
+        null_space.assign((size_t)nVar * (nVar + 1), 0.0); // lexlse.h:93
+        array.assign((size_t)nVar * (nVar + 1), 0.0);      // lexlse.h:94
         nVarFixed = nVarFixedInit = 0;
         fixed_var_index.clear();
         fixed_var_type.clear();
@@ -237,6 +257,19 @@ public:
     void setTolLinearDependence(double t)
     {
         tol_linear_dependence = t;
+    }
+    // lexlse.h:1467-1470 (the regularization part of ParametersLexLSE)
+    void setRegularization(int type, double variable_factor)
+    {
+        if (type == REGULARIZATION_TIKHONOV_CG || type == REGULARIZATION_RT_NO_Z_CG || type == REGULARIZATION_TIKHONOV_1)
+            throw Exception("regularization type not restated in the oracle (CG variants, TIKHONOV_1 test variant)");
+        regularization_type            = type;
+        variable_regularization_factor = variable_factor;
+    }
+    // lexlse.h:1478-1482
+    void setRegularizationFactor(Index ObjIndex, double factor)
+    {
+        obj_info[ObjIndex].regularization_factor = factor;
     }
 
     // lexlse.h:1522-1530; data is column-major dim x (nVar+1) with leading dimension ldd
@@ -360,6 +393,8 @@ public:
                 {
                     for (Index r = 0; r < nCtr; r++) std::swap(L(r, ColIndex), L(r, maxColNormIndex));
                     std::swap(ColNorms[ColIndex], ColNorms[maxColNormIndex]);
+                    if (regularization_type != REGULARIZATION_NONE) // lexlse.h:228-231
+                        for (Index p = 0; p < FirstColIndex; p++) std::swap(Zn(p, ColIndex), Zn(p, maxColNormIndex));
                 }
 
                 // Householder, lexlse.h:239-248 (Eigen primitives restated from
@@ -414,6 +449,8 @@ public:
             }
 
             const Index ObjRank = obj_info[ObjIndex].rank = ColIndex - FirstColIndex; // lexlse.h:272
+
+            if (regularization_type != REGULARIZATION_NONE) regularize(ObjIndex, FirstRowIndex, FirstColIndex, ObjRank, RemainingColumns);
 
             // Gauss step, lexlse.h:431-471
             if (ObjIndex + 1 < nObj && ObjRank > 0)
@@ -741,6 +778,328 @@ private:
     }
 
     // lexlse.h:1672-1693
+    // =========================================================================================
+    // Regularization, lexlse.h:274-411 (dispatch), :1700-1760, :2078-2242 (the direct variants), :2560-2625 (null-space
+    // basis).  Restated types: TIKHONOV (1), R (3), R_NO_Z (4), RT_NO_Z (5), TIKHONOV_2 (8), TEST (9).
+    // Arithmetic: every entry of a product is ONE sequential fma chain in ascending summation index (S); the Cholesky
+    // factorization (Eigen::LLT) is the column-oriented textbook form with the same chains; divisions are divisions.
+    //   R(i,j) = L(fr+i, fc+j) (only i <= j is read: the part below the diagonal holds Householder vectors)
+    //   T(i,c) = L(fr+i, fc+r+c), c < RC;   b(i) = L(fr+i, nVar)
+    //   Z(p,c) = null_space(p, c) (leading dimension nVar), s(p) = Z(p, nVar);   D = `array` (leading dimension nVar)
+    // =========================================================================================
+    double &Zn(Index p, Index c) { return null_space[(size_t)c * nVar + p]; }
+    double &Dm(Index i, Index j) { return array[(size_t)j * nVar + i]; }
+
+    // Eigen::LLT<>(D) on the leading N x N block (lower triangle), then solveInPlace(d)
+    void llt_solve(Index N, double *d)
+    {
+        for (Index j = 0; j < N; j++)
+        {
+            double acc = Dm(j, j);
+            for (Index k = 0; k < j; k++) acc = fmad(-Dm(j, k), Dm(j, k), acc);
+            const double ljj = std::sqrt(acc);
+            Dm(j, j)         = ljj;
+            for (Index i = j + 1; i < N; i++)
+            {
+                double a = Dm(i, j);
+                for (Index k = 0; k < j; k++) a = fmad(-Dm(i, k), Dm(j, k), a);
+                Dm(i, j) = a / ljj;
+            }
+        }
+        for (Index i = 0; i < N; i++) // L y = d
+        {
+            double a = d[i];
+            for (Index k = 0; k < i; k++) a = fmad(-Dm(i, k), d[k], a);
+            d[i] = a / Dm(i, i);
+        }
+        for (Index i = N; i--;) // L' z = y
+        {
+            double a = d[i];
+            for (Index k = i + 1; k < N; k++) a = fmad(-Dm(k, i), d[k], a);
+            d[i] = a / Dm(i, i);
+        }
+    }
+
+    void regularize(Index ObjIndex, Index fr, Index fc, Index r, Index RC)
+    {
+        // the factor, lexlse.h:277-311
+        double a = obj_info[ObjIndex].regularization_factor;
+        if (variable_regularization_factor != 0.0)
+        {
+            a = 0.0;
+            if (r > 0)
+            {
+                double *t = &dWorkspace[0]; // rhs_tmp
+                double n0 = 0.0;
+                for (Index i = 0; i < r; i++)
+                {
+                    t[i] = L(fr + i, nVar);
+                    n0   = fmad(t[i], t[i], n0);
+                }
+                for (Index i = r; i--;) // R y = rhs_tmp (vector solve: divides)
+                {
+                    double acc = t[i];
+                    for (Index k = i + 1; k < r; k++) acc = fmad(-L(fr + i, fc + k), t[k], acc);
+                    t[i] = acc / L(fr + i, fc + i);
+                }
+                double n1 = 0.0;
+                for (Index i = 0; i < r; i++) n1 = fmad(t[i], t[i], n1);
+                const double ce = n0 / n1, eps = variable_regularization_factor;
+                if (ce < eps) a = std::sqrt(1 - (ce * ce) / (eps * eps)) * obj_info[ObjIndex].regularization_factor;
+            }
+        }
+        aRegularizationFactor = a;
+        const bool on         = !(std::fabs(a - 0.0) < 1e-15); // !isEqual(a, 0), utility.h:48-51
+        const double mu       = a * a;
+        const Index q         = fc - nVarFixed; // rows of the accumulated null-space basis
+        double *d             = &array[(size_t)nVar * nVar];
+        auto R = [&](Index i, Index j) -> double { return L(fr + i, fc + j); };
+        auto T = [&](Index i, Index c) -> double { return L(fr + i, fc + r + c); };
+        auto b = [&](Index i) -> double & { return L(fr + i, nVar); };
+
+        switch (regularization_type)
+        {
+        case REGULARIZATION_TIKHONOV: // lexlse.h:317-331
+            if (on)
+            {
+                if (fc + r <= RC)
+                    tikhonov_2(fr, fc, r, RC, a, mu, q, d);
+                else
+                    tikhonov_1(fr, fc, r, RC, mu, q, d);
+            }
+            accumulate_nullspace_basis(fr, fc, r, RC, q);
+            break;
+        case REGULARIZATION_TIKHONOV_2: // :389-396
+            if (on) tikhonov_2(fr, fc, r, RC, a, mu, q, d);
+            accumulate_nullspace_basis(fr, fc, r, RC, q);
+            break;
+        case REGULARIZATION_R: // :344-351, :2143-2170
+            if (on)
+            {
+                for (Index i = 0; i < r; i++)
+                    for (Index j = 0; j <= i; j++)
+                    {
+                        double acc = 0.0;
+                        for (Index k = 0; k <= j; k++) acc = fmad(R(k, i), R(k, j), acc); // R'R
+                        double up = 0.0;
+                        for (Index p = 0; p < q; p++) up = fmad(Zn(p, fc + i), Zn(p, fc + j), up);
+                        acc      = fmad(mu, up, acc);
+                        Dm(i, j) = (i == j) ? acc + mu : acc;
+                    }
+                for (Index i = 0; i < r; i++)
+                {
+                    double up = 0.0;
+                    for (Index p = 0; p < q; p++) up = fmad(Zn(p, fc + i), Zn(p, nVar), up);
+                    double acc = up * mu;
+                    for (Index k = 0; k <= i; k++) acc = fmad(R(k, i), b(k), acc);
+                    d[i] = acc;
+                }
+                llt_solve(r, d);
+                apply_R(fr, fc, r, d);
+            }
+            accumulate_nullspace_basis(fr, fc, r, RC, q);
+            break;
+        case REGULARIZATION_R_NO_Z: // :353-360, :2175-2202
+            if (on)
+            {
+                for (Index i = 0; i < r; i++)
+                    for (Index j = 0; j <= i; j++)
+                    {
+                        double acc = 0.0;
+                        for (Index k = 0; k <= j; k++) acc = fmad(R(k, i), R(k, j), acc);
+                        Dm(i, j) = (i == j) ? acc + mu : acc;
+                    }
+                for (Index i = 0; i < r; i++)
+                {
+                    double acc = 0.0;
+                    for (Index k = 0; k <= i; k++) acc = fmad(R(k, i), b(k), acc);
+                    d[i] = acc;
+                }
+                llt_solve(r, d);
+                apply_R(fr, fc, r, d);
+            }
+            break;
+        case REGULARIZATION_RT_NO_Z: // :362-368, :2207-2242
+            if (on)
+            {
+                for (Index i = 0; i < r; i++)
+                    for (Index j = 0; j <= i; j++)
+                    {
+                        double acc = 0.0;
+                        for (Index k = i; k < r; k++) acc = fmad(R(i, k), R(j, k), acc); // R R'
+                        for (Index c = 0; c < RC; c++) acc = fmad(T(i, c), T(j, c), acc); // + T T'
+                        Dm(i, j) = (i == j) ? acc + mu : acc;
+                        if (i != j) Dm(j, i) = acc; // kept for the symmetric product below (the factorization overwrites the lower part)
+                        else array_diag(i) = acc;
+                    }
+                for (Index i = 0; i < r; i++) d[i] = b(i);
+                llt_solve(r, d);
+                // b = (R R' + T T') d  (the reference subtracts mu from the diagonal again: (x + mu) - mu, replicated)
+                for (Index i = 0; i < r; i++)
+                {
+                    double acc = 0.0;
+                    for (Index j = 0; j < r; j++)
+                    {
+                        const double e = (i == j) ? ((array_diag(i) + mu) - mu) : (i > j ? Dm(j, i) : Dm(i, j));
+                        acc            = fmad(e, d[j], acc);
+                    }
+                    dWorkspace[i] = acc;
+                }
+                for (Index i = 0; i < r; i++) b(i) = dWorkspace[i];
+            }
+            break;
+        case REGULARIZATION_TEST: // :398-404, :2247-2251
+            if (on)
+                for (Index i = 0; i < r; i++) b(i) = b(i) * a;
+            break;
+        default:
+            break;
+        }
+    }
+
+    // scratch for the untouched diagonal of a symmetric D while its lower triangle is being factorized
+    double &array_diag(Index i) { return dWorkspace[nVar + 1 + i]; }
+
+    // b(0:r) = triu(R) * d(0:r)
+    void apply_R(Index fr, Index fc, Index r, const double *d)
+    {
+        for (Index i = 0; i < r; i++)
+        {
+            double acc = 0.0;
+            for (Index k = i; k < r; k++) acc = fmad(L(fr + i, fc + k), d[k], acc);
+            dWorkspace[i] = acc;
+        }
+        for (Index i = 0; i < r; i++) L(fr + i, nVar) = dWorkspace[i];
+    }
+
+    // lexlse.h:1700-1760: normal equations over the remaining variables, N = RC + r unknowns
+    void tikhonov_1(Index fr, Index fc, Index r, Index RC, double mu, Index q, double *d)
+    {
+        auto R = [&](Index i, Index j) -> double { return L(fr + i, fc + j); };
+        auto T = [&](Index i, Index c) -> double { return L(fr + i, fc + r + c); };
+        const Index N = RC + r;
+        // G(i,j) = column i of [R T] dot column j of [R T] (upper-triangular R), i >= j
+        auto col = [&](Index k, Index j) -> double { return j < r ? (k <= j ? R(k, j) : 0.0) : T(k, j - r); };
+        for (Index i = 0; i < N; i++)
+            for (Index j = 0; j <= i; j++)
+            {
+                double acc      = 0.0;
+                const Index top = (j < r) ? j + 1 : r; // rows where column j is non-zero
+                for (Index k = 0; k < top; k++) acc = fmad(col(k, i), col(k, j), acc);
+                double up = 0.0;
+                for (Index p = 0; p < q; p++) up = fmad(Zn(p, fc + i), Zn(p, fc + j), up);
+                acc      = fmad(mu, up, acc);
+                Dm(i, j) = (i == j) ? acc + mu : acc;
+            }
+        for (Index i = 0; i < N; i++)
+        {
+            double acc      = 0.0;
+            const Index top = (i < r) ? i + 1 : r;
+            for (Index k = 0; k < top; k++) acc = fmad(col(k, i), L(fr + k, nVar), acc);
+            double up = 0.0;
+            for (Index p = 0; p < q; p++) up = fmad(Zn(p, fc + i), Zn(p, nVar), up);
+            d[i] = fmad(mu, up, acc);
+        }
+        llt_solve(N, d);
+        for (Index i = 0; i < r; i++) // b = triu(R) d(0:r) + T d(r:N)
+        {
+            double acc = 0.0;
+            for (Index k = i; k < r; k++) acc = fmad(R(i, k), d[k], acc);
+            for (Index c = 0; c < RC; c++) acc = fmad(T(i, c), d[r + c], acc);
+            dWorkspace[i] = acc;
+        }
+        for (Index i = 0; i < r; i++) L(fr + i, nVar) = dWorkspace[i];
+    }
+
+    // lexlse.h:2078-2138: the dual form, N = q + r unknowns ([R T; a Z] [R T; a Z]' + mu I)
+    void tikhonov_2(Index fr, Index fc, Index r, Index RC, double a, double mu, Index q, double *d)
+    {
+        auto R = [&](Index i, Index j) -> double { return L(fr + i, fc + j); };
+        auto T = [&](Index i, Index c) -> double { return L(fr + i, fc + r + c); };
+        const Index N = q + r, W = RC + r; // W = columns of the stacked matrix
+        // row i of the stacked matrix M = [triu(R) T; a * Z(:, fc .. fc + W)]: entries M(i, c), c < W
+        auto rowdot = [&](Index i, Index j) -> double { // M(i,:) . M(j,:) without the factors a (applied by the caller)
+            double acc = 0.0;
+            if (i < r && j < r)
+            {
+                const Index lo = std::max(i, j);
+                for (Index k = lo; k < r; k++) acc = fmad(R(i, k), R(j, k), acc);
+                for (Index c = 0; c < RC; c++) acc = fmad(T(i, c), T(j, c), acc);
+            }
+            else if (i >= r && j >= r)
+                for (Index c = 0; c < W; c++) acc = fmad(Zn(i - r, fc + c), Zn(j - r, fc + c), acc);
+            else
+            {
+                const Index zi = (i >= r) ? i - r : j - r, ri = (i >= r) ? j : i;
+                for (Index k = ri; k < r; k++) acc = fmad(Zn(zi, fc + k), R(ri, k), acc);
+                for (Index c = 0; c < RC; c++) acc = fmad(Zn(zi, fc + r + c), T(ri, c), acc);
+            }
+            return acc;
+        };
+        double *diag = &dWorkspace[nVar + 1]; // the diagonal before "+ mu", and the upper copy of the off-diagonal part
+        for (Index i = 0; i < N; i++)
+            for (Index j = 0; j <= i; j++)
+            {
+                double v = rowdot(i, j);
+                if (i >= r && j >= r)
+                    v = mu * v;
+                else if (i >= r)
+                    v = a * v;
+                if (i == j)
+                {
+                    diag[i]  = v;
+                    Dm(i, i) = v + mu;
+                }
+                else
+                {
+                    Dm(i, j) = v;
+                    Dm(j, i) = v; // the upper copy survives the factorization of the lower triangle
+                }
+            }
+        for (Index i = 0; i < r; i++) d[i] = L(fr + i, nVar);
+        for (Index p = 0; p < q; p++) d[r + p] = a * Zn(p, nVar);
+        llt_solve(N, d);
+        for (Index i = 0; i < r; i++) // b = first r entries of (D - mu I) d, the diagonal as (x + mu) - mu
+        {
+            double acc = 0.0;
+            for (Index j = 0; j < N; j++)
+            {
+                const double e = (i == j) ? ((diag[i] + mu) - mu) : (i > j ? Dm(j, i) : Dm(i, j));
+                acc            = fmad(e, d[j], acc);
+            }
+            ColNorms[i] = acc; // free between levels
+        }
+        for (Index i = 0; i < r; i++) L(fr + i, nVar) = ColNorms[i];
+    }
+
+    // lexlse.h:2592-2625: Z := Z * [ -inv(R) T ; I ] accumulated in place, the right-hand-side column included
+    void accumulate_nullspace_basis(Index fr, Index fc, Index r, Index RC, Index q)
+    {
+        const Index rows = q + r;
+        for (Index i = 0; i < r; i++)
+            for (Index j = 0; j < r; j++) Zn(q + i, fc + j) = (i == j) ? 1.0 : 0.0;
+        // Left := Left * inv(triu(R)), column by column (the Gauss step's routine: multiply by the reciprocal diagonal)
+        for (Index c = 0; c < r; c++)
+        {
+            const double inv = invdiag[fc + c];
+            for (Index p = 0; p < rows; p++)
+            {
+                double acc = Zn(p, fc + c);
+                for (Index k = 0; k < c; k++) acc = fmad(-Zn(p, fc + k), L(fr + k, fc + c), acc);
+                Zn(p, fc + c) = acc * inv;
+            }
+        }
+        // Trailing -= Left * Up, columns fc + r .. nVar
+        for (Index j = fc + r; j <= nVar; j++)
+            for (Index p = 0; p < rows; p++)
+            {
+                double acc = Zn(p, j);
+                for (Index k = 0; k < r; k++) acc = fmad(-Zn(p, fc + k), L(fr + k, j), acc);
+                Zn(p, j) = acc;
+            }
+    }
+    double aRegularizationFactor = 0.0;
+
     void initialize()
     {
         nVarFixedInit = 0;
@@ -751,6 +1110,7 @@ private:
             obj_info[k].first_col_index = 0;
         }
         std::fill(hh_scalars.begin(), hh_scalars.end(), 0.0);
+        std::fill(null_space.begin(), null_space.end(), 0.0); // lexlse.h:1685
         // NB (reference quirk, replicated): nVarFixed is still the PREVIOUS problem's count here, so
         // entries [new nVarFixed, old nVarFixed) keep whatever the last solve left in them.
         for (Index i = nVarFixed; i < nVar; i++) x[i] = 0.0;
@@ -760,7 +1120,9 @@ private:
     Index nVarFixed = 0, nVarFixedInit = 0, TotalRank = 0;
     double tol_linear_dependence = 1e-12;
     std::vector<ObjectiveInfo> obj_info;
-    std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms, invdiag;
+    std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms, invdiag, null_space, array;
+    int regularization_type = 0;
+    double variable_regularization_factor = 0.0;
     std::vector<int> ctr_type, fixed_var_type;
     std::vector<Index> fixed_var_index, column_permutations;
 };
@@ -1012,8 +1374,10 @@ public:
                 lexlse.setCtr(counter, &data[i], nCtr, rhs);
                 counter++;
             }
+            lexlse.setRegularizationFactor(ObjIndex, regularization_factor); // objective.h:492
         }
     }
+    double regularization_factor = 0.0; // objective.h:828, :973
 
     // :521-578
     bool checkBlockingConstraints(Index &CtrIndexBlocking, int &CtrTypeBlocking, double &alpha, double tol_feasibility,
@@ -1146,6 +1510,12 @@ public:
     {
         parameters = p;
         lexlse.setTolLinearDependence(p.tol_linear_dependence);
+        lexlse.setRegularization(p.regularization_type, p.variable_regularization_factor); // lexlsi.h:331-333
+    }
+    // lexlsi.h:497-502 (a simple-bounds objective is never regularized, objective.h:489-493)
+    void setRegularizationFactor(Index ObjIndex, double factor)
+    {
+        objectives[ObjIndex].regularization_factor = factor;
     }
 
     // lexlsi.h:350-435; data column-major dim x (nVar+2) with leading dimension ldd

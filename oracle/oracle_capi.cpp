@@ -14,6 +14,7 @@ using namespace lexls_oracle;
 
 extern "C" {
 
+
 struct oracle_params
 {
     uint32_t max_number_of_factorizations;
@@ -33,9 +34,26 @@ struct oracle_params
     int32_t deactivate_first_wrong_sign;
 };
 
+// Regularization settings for the following oracle_*_solve_batch calls (test infrastructure: a process-wide setting keeps
+// the batch signatures unchanged).  type = typedefs.h:32-44; factors[k] = setRegularizationFactor(k, .) per objective of
+// the hierarchy as the caller numbers them (LexLSI: a simple-bounds objective 0 is counted and ignored, objective.h:489).
+static int g_reg_type = 0;
+static double g_reg_var = 0.0;
+static std::vector<double> g_reg_factors;
+
+extern "C" int oracle_set_regularization(int type, double variable_factor, const double *factors, uint32_t count)
+{
+    g_reg_type = type;
+    g_reg_var  = variable_factor;
+    g_reg_factors.assign(factors ? factors : nullptr, factors ? factors + count : nullptr);
+    return 0;
+}
+
 static Parameters to_params(const oracle_params *p)
 {
     Parameters q;
+    q.regularization_type            = g_reg_type;
+    q.variable_regularization_factor = g_reg_var;
     if (!p) return q;
     q.max_number_of_factorizations = p->max_number_of_factorizations;
     q.tol_linear_dependence        = p->tol_linear_dependence;
@@ -142,7 +160,9 @@ int oracle_lse_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
             uint64_t p = next.fetch_add(1);
             if (p >= batch || failed.load()) break;
             lse.setTolLinearDependence(tol_linear_dependence);
+            lse.setRegularization(g_reg_type, g_reg_var);
             lse.setObjDim(ObjDim);
+            for (uint32_t k = 0; k < nObj; k++) lse.setRegularizationFactor(k, k < g_reg_factors.size() ? g_reg_factors[k] : 0.0);
             lse.setFixedVariablesCount(nFixed);
             for (uint32_t f = 0; f < nFixed; f++)
                 lse.fixVariable(fixed_index[p * nFixed + f], fixed_value[p * nFixed + f],
@@ -245,6 +265,7 @@ static int lsi_batch_impl(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim, 
             if (p >= batch || failed.load()) break;
             lsi.resize(nVar, nObj, ObjDim, types.data());
             lsi.setParameters(par);
+            for (uint32_t k = 0; k < nObj; k++) lsi.setRegularizationFactor(k, k < g_reg_factors.size() ? g_reg_factors[k] : 0.0);
             lsi.min_alpha_gap = 1e300;
             lsi.getLexLSE().min_pivot_gap = lsi.getLexLSE().min_rank_margin = lsi.getLexLSE().min_lambda_gap = 1e300;
             for (uint32_t k = 0; k < nObj; k++)

@@ -382,3 +382,120 @@ def test_result_buffers_keep_their_guard_bands(monkeypatch):
         seen[res[0]] = seen.get(res[0], 0) + res[1]
     assert len(seen) >= 12, seen
     assert all(v == 0 for v in seen.values()), seen
+
+
+# ---- regularization (lexlse.h:274-411, :1700-1760, :2078-2251, :2592-2625) ------------------------------------------------
+REG_TYPES = {1: "TIKHONOV", 3: "R", 4: "R_NO_Z", 5: "RT_NO_Z", 8: "TIKHONOV_2", 9: "TEST"}
+
+
+@pytest.mark.parametrize("reg_type", sorted(REG_TYPES))
+@pytest.mark.parametrize("variant", ["w2", "w4", "lg8", "lg16"])
+def test_regularized_lexlse_matches_the_oracle(oracle, monkeypatch, reg_type, variant):
+    import lexls_b200 as lx
+    env = {"w2": dict(WARPS=2), "w4": dict(WARPS=4), "lg8": dict(FORCE_LODGLOBAL=1, LG_WARPS=8), "lg16": dict(FORCE_LODGLOBAL=1, LG_WARPS=16)}[variant]
+    for k, v in env.items():
+        monkeypatch.setenv("LEXLS_B200_" + k, str(v))
+    rng = np.random.default_rng(100 + reg_type)
+    for n, dims, fixed in ((14, [4, 3, 5], False), (11, [3, 4, 8], True), (9, [2, 12], False)):
+        B = 7
+        data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+        data[0][::3, 1, :] = data[0][::3, 0, :]  # a duplicated column: lower rank, ties
+        factors = [0.3, 0.05, 0.7][:len(dims)]
+        fi = np.tile(np.array([2, 0], dtype=np.uint32), (B, 1)) if fixed else None
+        fv = rng.standard_normal((B, 2)) if fixed else None
+        oracle.set_regularization(reg_type, factors)
+        try:
+            ref = oracle.lse_solve_batch(n, dims, data, fixed_index=fi, fixed_value=fv, threads=0, want_factors=True)
+        finally:
+            oracle.set_regularization(0)
+        with lx.LexLSEBatch(n, dims, batch=B) as s:
+            s.setParameters(lx.Params(regularization_type=reg_type))
+            for k, f in enumerate(factors):
+                s.setRegularizationFactor(k, f)
+            s.request_outputs(lexqr=True)
+            if fixed:
+                s.fixVariables(fi, fv)
+            for k, d in enumerate(data):
+                s.setData(k, d)
+            s.solve()
+            x, ranks = s.get_x(), s.get_ranks()
+            q, hh = s.get_lexqr()
+            name = s.kernel_info()["name"]
+        assert not name.endswith("_w1"), name
+        assert np.array_equal(ranks, ref["ranks"])
+        assert np.array_equal(q, ref["lexqr"]), "factorization (incl. the regularized right-hand sides) differs: %s %s" % (REG_TYPES[reg_type], name)
+        assert np.array_equal(x, ref["x"])
+    # unregularized reference differs (the factors really act), and a zero factor reproduces it exactly
+    plain = oracle.lse_solve_batch(n, dims, data, threads=0)
+    assert not np.array_equal(plain["x"], ref["x"])
+    with lx.LexLSEBatch(n, dims, batch=B) as s:
+        s.setParameters(lx.Params(regularization_type=reg_type))
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        assert np.array_equal(s.get_x(), plain["x"])
+
+
+def test_variable_regularization_factor_matches_the_oracle(oracle):
+    import lexls_b200 as lx
+    rng = np.random.default_rng(77)
+    n, dims, B = 12, [4, 4, 6], 16
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    data[1][:, :, 3] = data[1][:, :, 2] * (1 + 1e-7)  # nearly dependent rows: a badly conditioned level
+    oracle.set_regularization(8, [0.2, 0.4, 0.1], variable_factor=0.5)
+    try:
+        ref = oracle.lse_solve_batch(n, dims, data, threads=0)
+    finally:
+        oracle.set_regularization(0)
+    with lx.LexLSEBatch(n, dims, batch=B) as s:
+        s.setParameters(lx.Params(regularization_type=8, variable_regularization_factor=0.5))
+        for k, f in enumerate([0.2, 0.4, 0.1]):
+            s.setRegularizationFactor(k, f)
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        assert np.array_equal(s.get_x(), ref["x"])
+
+
+@pytest.mark.parametrize("reg_type", [1, 4, 5])
+def test_regularized_lexlsi_matches_the_oracle(oracle, reg_type):
+    """The active-set loop with a damped inner LexLSE (lexlsi.h:331-333, :497; objective.h:489-493: the simple-bounds objective
+    is never regularized)."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c3", 64)
+    data, vi = problems.generate(w)
+    vib = np.tile(vi, (w.batch, 1))
+    factors = [9.0, 0.0, 0.02, 0.0, 0.05]  # objective 0 is SIMPLE_BOUNDS: its factor must be ignored
+    par = dict(regularization_type=reg_type, max_number_of_factorizations=60)
+    oracle.set_regularization(reg_type, factors)
+    try:
+        ref = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, params=oracle.OracleParams(max_number_of_factorizations=60), threads=0)
+    finally:
+        oracle.set_regularization(0)
+    P = len(w.ObjDim)
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        s.setParameters(lx.Params(**par))
+        for k, f in enumerate(factors):
+            s.setRegularizationFactor(k, f)
+        for k, d in enumerate(data):
+            s.setData(k, d, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, d)
+        s.solve()
+        got = dict(x=s.get_x(), v=[s.get_v(k) for k in range(P)], viol=[s.getConstraintViolation(k) for k in range(P)],
+                   active=[s.getActiveCtr(k) for k in range(P)], order=[s.getActiveCtr_order(k) for k in range(P)],
+                   status=s.get_status(), counters=s.get_counters())
+    compare_lsi(got, ref, P)
+    assert np.array_equal(got["x"], ref["x"])
+    plain = oracle.lsi_solve_batch(w.nVar, w.ObjDim, w.ObjType, data, var_index=vib, threads=0)
+    assert not np.array_equal(plain["x"], ref["x"])
+
+
+def test_unimplemented_regularization_types_are_refused():
+    import lexls_b200 as lx
+    with lx.LexLSEBatch(4, [2, 2], batch=1) as s:
+        for t in (2, 6, 7):
+            with pytest.raises(lx.LexLSError) as e:
+                s.setParameters(lx.Params(regularization_type=t))
+            assert e.value.code == 3
+        with pytest.raises(lx.LexLSError):
+            s.setParameters(lx.Params(regularization_type=12))
