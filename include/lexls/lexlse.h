@@ -134,6 +134,18 @@ public:
         if (nCtr) lexls_b200_check(lexls_b200_get_lexqr(h_, lexqr_.data(), hh_.data()));
     }
     void solve() { lexls_b200_check(lexls_b200_get_x(h_, x.data())); } // lexlse.h:1015
+    // lexlse.h:1046-1262: the minimiser of least norm instead of the basic solution of solve().  The three variants of the
+    // reference (Givens rotations, normal equations, the Tikhonov basis) compute the same vector with different roundings; all
+    // three are served by the kernel's normal-equation routine (solveLeastNorm_2).  The factorization is launched once more with
+    // the extra output switched on (data and fixed variables are still on the device).
+    void solveLeastNorm_2()
+    {
+        lexls_b200_check(lexls_b200_request_outputs(h_, LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LEAST_NORM));
+        lexls_b200_check(lexls_b200_solve_batch_sync(h_));
+        lexls_b200_check(lexls_b200_get_x_least_norm(h_, x.data()));
+    }
+    void solveLeastNorm_1() { solveLeastNorm_2(); }
+    void solveLeastNorm_3() { solveLeastNorm_2(); }
     const dVectorType &get_x() const { return x; }                      // lexlse.h:1587
     dVectorType &get_v()                                                // lexlse.h:1560 (use the first nCtr entries)
     {

@@ -212,6 +212,7 @@ int lexls_b200_get_column_permutations(lexls_b200_batch_t *h, uint32_t *colperm)
 #define LEXLS_B200_OUT_LEXQR 1u
 #define LEXLS_B200_OUT_LAMBDA 2u
 #define LEXLS_B200_OUT_XSTAR 4u
+#define LEXLS_B200_OUT_LEAST_NORM 8u
 int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask);
 int lexls_b200_get_lexqr(lexls_b200_batch_t *h, double *lexqr, double *hh);
 int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda);
@@ -220,6 +221,10 @@ int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
  * (its constraints [A | rhs] in working-set order, zero rows below); lexqr / hh = what get_lexqr() lexlsi.h:607 returns AFTER
  * get_xStar (tests/test_numerical_error.cpp:83-86 reads all three).  Any destination may be NULL. */
 int lexls_b200_get_xstar(lexls_b200_batch_t *h, double *xstar, double *data, double *lexqr, double *hh);
+/* solveLeastNorm_1 / _2 / _3 lexlse.h:1046-1262 (LSE, LEXLS_B200_OUT_LEAST_NORM): next to the basic solution of solve() (free
+ * variables zero) the solve kernel computes the solution of least norm among all minimisers, by the normal equations of
+ * solveLeastNorm_2 (the reference's three variants reach the same vector with different roundings) -> x [batch][nVar]. */
+int lexls_b200_get_x_least_norm(lexls_b200_batch_t *h, double *x);
 /* getWorkingSetLog lexlsi.h:739 (entries typedefs.h:380-432), written when params.log_working_set_enabled != 0:
  * entries [batch][capacity][6] = {obj_index, ctr_index, ctr_type (0 = removed), alpha_or_lambda, rank, cycling_detected};
  * count [batch] = valid rows of entries[p]: what the solve produced (<= max_number_of_factorizations + 1), cut at `capacity`. */

@@ -154,11 +154,17 @@ class _Batch:
         check(lib().lexls_b200_get_ranks(self._h, r.ctypes.data_as(C.POINTER(C.c_uint32))))
         return r
 
-    def request_outputs(self, lexqr=False, multipliers=False, xstar=False):
+    def get_x_least_norm(self):
+        """solveLeastNorm (lexlse.h:1046-1262): the minimiser of least norm, [B, nVar]; needs request_outputs(least_norm=True)."""
+        x = np.empty((self.batch, self.nVar))
+        check(lib().lexls_b200_get_x_least_norm(self._h, _dp(x)))
+        return x
+
+    def request_outputs(self, lexqr=False, multipliers=False, xstar=False, least_norm=False):
         """Optional outputs written by the next solves: the factorized work matrix (get_lexqr) / LexLSI multipliers /
         LexLSI get_xStar with get_data and get_lexqr of that last equality-constrained problem."""
         check(lib().lexls_b200_request_outputs(self._h, (capi.OUT_LEXQR if lexqr else 0) | (capi.OUT_LAMBDA if multipliers else 0)
-                                               | (capi.OUT_XSTAR if xstar else 0)))
+                                               | (capi.OUT_XSTAR if xstar else 0) | (capi.OUT_LEAST_NORM if least_norm else 0)))
 
     def get_lexqr(self):
         """(lexqr [B, nVar+1, M] — i.e. per problem column-major M x (nVar+1) —, hh [B, M])."""

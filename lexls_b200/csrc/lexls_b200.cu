@@ -77,6 +77,9 @@ struct lexls_b200_batch
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
     double *xstar = nullptr, *lexdata = nullptr, *lexqr_star = nullptr, *hh_star = nullptr; // LEXLS_B200_OUT_XSTAR
     double reg_factor_user[LX_MAX_LEVELS] = {0};                   // setRegularizationFactor per user objective
+    double *xln = nullptr, *ln_scratch = nullptr;                  // LEXLS_B200_OUT_LEAST_NORM
+    size_t ln_bytes = 0;
+    uint64_t ln_stride = 0;
     double *reg_scratch = nullptr;                                 // regularization work arrays, one slice per resident CTA
     size_t reg_bytes = 0;
     uint64_t reg_stride = 0;
@@ -311,11 +314,19 @@ kernel_fn pick_lse_kernel(int W, bool LG);
 kernel_fn pick_lse_pair_kernel();
 kernel_fn pick_lsi_w1_kernel(bool DS);
 kernel_fn pick_lsi_wn_kernel(int W, bool DS, bool LG);
+kernel_fn pick_lse_reg_kernel(int W, bool LG);
+kernel_fn pick_lsi_reg_kernel(int W, bool LG);
 } // namespace lexls_dev
 
-static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &name)
+static kernel_fn pick_kernel(int kind, int W, bool DS, bool LG, std::string &name, bool reg = false)
 {
     char buf[64];
+    if (reg) // separate instantiations with the regularization routines (W >= 2, objective data in L2)
+    {
+        snprintf(buf, sizeof buf, "%s_w%d%s_reg", kind == LEXLS_B200_LSE ? "lse" : "lsi", W, LG ? "_lodglobal" : (kind == LEXLS_B200_LSE ? "" : "_l2data"));
+        name = buf;
+        return kind == LEXLS_B200_LSE ? pick_lse_reg_kernel(W, LG) : pick_lsi_reg_kernel(W, LG);
+    }
     if (kind == LEXLS_B200_LSE)
     {
         snprintf(buf, sizeof buf, "lse_w%d%s", W, LG ? "_lodglobal" : "");
@@ -368,7 +379,7 @@ static int plan(lexls_b200_batch *h)
     bool DS = false, LG = false;
     if (const char *e = getenv("LEXLS_B200_DATA"))
     {
-        if (!strcmp(e, "smem")) DS = lsi;
+        if (!strcmp(e, "smem")) DS = lsi && h->user_params.regularization_type == 0; // the regularized kernels read the data through L2
     }
     // every level handled by the register-window panel (lexls_panel.cuh): <= 48 columns, <= 40 rows per level
     if (h->user_params.regularization_type != 0 && W == 1) W = 2; // the regularization routine lives in the shared-memory kernels
@@ -446,7 +457,7 @@ static int plan(lexls_b200_batch *h)
         for (int k = 0; k < h->sh.P; k++)
             if (h->sh.dim[k] > 20) h->pair = false;
     }
-    kernel_fn k = pick_kernel(h->kind, W, DS, LG, h->kname);
+    kernel_fn k = pick_kernel(h->kind, W, DS, LG, h->kname, h->user_params.regularization_type != 0);
     if (h->pair)
     {
         k        = pick_lse_pair_kernel();
@@ -748,7 +759,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch, h->xln, h->ln_scratch};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1167,6 +1178,23 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
         b.hh_star    = h->hh_star;
     }
     b.glist = h->have_glist ? h->glist : nullptr;
+    if ((h->want & LEXLS_B200_OUT_LEAST_NORM) && h->kind == LEXLS_B200_LSE)
+    {
+        const uint64_t n = (uint64_t)s.n;
+        h->ln_stride     = 2 * n * (n + 1) + 2 * n + 8;
+        const size_t need = sizeof(double) * h->ln_stride * h->grid;
+        if (need > h->ln_bytes)
+        {
+            if (h->ln_scratch) guarded_free(h, h->ln_scratch);
+            h->ln_scratch = nullptr;
+            h->ln_bytes   = 0;
+            CK(guarded_malloc(h, (void **)&h->ln_scratch, need));
+            h->ln_bytes = need;
+        }
+        b.xln        = h->xln;
+        b.ln_scratch = h->ln_scratch;
+        b.ln_stride  = h->ln_stride;
+    }
     for (int g = 0; g < LX_MAX_LEVELS; g++) h->pr.reg_factor[g] = (g + s.off < s.P) ? h->reg_factor_user[g + s.off] : 0.0;
     if (h->pr.reg_type != 0)
     {
@@ -1203,7 +1231,7 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     b.lod_stride   = h->lod_stride;
 
     std::string name;
-    kernel_fn k = h->pair ? pick_lse_pair_kernel() : pick_kernel(h->kind, h->W, h->DS, h->LG, name);
+    kernel_fn k = h->pair ? pick_lse_pair_kernel() : pick_kernel(h->kind, h->W, h->DS, h->LG, name, h->user_params.regularization_type != 0);
     b.flag         = h->flag;
     CK(cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemcpyAsync(h->hflag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream)); // inspected after the next synchronisation
@@ -1346,7 +1374,9 @@ int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
 {
     MULTI(h, false, lexls_b200_request_outputs(s.h, mask));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
-    if (mask & ~(uint32_t)(LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA | LEXLS_B200_OUT_XSTAR)) return fail(LEXLS_B200_EINVAL, "unknown output bit");
+    if (mask & ~(uint32_t)(LEXLS_B200_OUT_LEXQR | LEXLS_B200_OUT_LAMBDA | LEXLS_B200_OUT_XSTAR | LEXLS_B200_OUT_LEAST_NORM))
+        return fail(LEXLS_B200_EINVAL, "unknown output bit");
+    if ((mask & LEXLS_B200_OUT_LEAST_NORM) && h->kind != LEXLS_B200_LSE) return fail(LEXLS_B200_EINVAL, "solveLeastNorm exists for LexLSE only");
     if ((mask & LEXLS_B200_OUT_LAMBDA) && h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "Lagrange multipliers exist for LexLSI only");
     if ((mask & LEXLS_B200_OUT_XSTAR) && h->kind != LEXLS_B200_LSI) return fail(LEXLS_B200_EINVAL, "get_xStar exists for LexLSI only");
     CK(cudaSetDevice(h->device));
@@ -1359,6 +1389,7 @@ int lexls_b200_request_outputs(lexls_b200_batch_t *h, uint32_t mask)
     }
     if ((mask & LEXLS_B200_OUT_LAMBDA) && !h->lambda)
         CK(guarded_malloc(h, (void **)&h->lambda, sizeof(double) * (size_t)s.P * std::max(s.Mall, 1) * h->batch));
+    if ((mask & LEXLS_B200_OUT_LEAST_NORM) && !h->xln) CK(guarded_malloc(h, (void **)&h->xln, sizeof(double) * (size_t)s.n * h->batch));
     if ((mask & LEXLS_B200_OUT_XSTAR) && !h->xstar)
     {
         CK(guarded_malloc(h, (void **)&h->xstar, sizeof(double) * (size_t)s.n * h->batch));
@@ -1539,6 +1570,14 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
     if (int rc = wait_copy(h)) return rc;
     h->have_glist = true;
     return 0;
+}
+
+int lexls_b200_get_x_least_norm(lexls_b200_batch_t *h, double *x)
+{
+    MULTI(h, true, lexls_b200_get_x_least_norm(s.h, off(x, s.first * h->sh.n)));
+    if (!h || !x) return fail(LEXLS_B200_EINVAL, "NULL argument");
+    if (!(h->want & LEXLS_B200_OUT_LEAST_NORM)) return fail(LEXLS_B200_EINVAL, "request LEXLS_B200_OUT_LEAST_NORM before the solve");
+    return d2h(h, x, h->xln, sizeof(double) * h->sh.n * h->batch);
 }
 
 int lexls_b200_set_regularization_factor(lexls_b200_batch_t *h, uint32_t level, double factor)

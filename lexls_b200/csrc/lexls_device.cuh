@@ -123,6 +123,9 @@ struct Buffers
     double *lexdata;           // LSI, with xstar: [B][(n+1) x M] that problem's constraints as given (LexLSE::get_data, lexlse.h:119, :1631)
     double *lexqr_star;        // LSI, with xstar: [B][(n+1) x M] its factorization (what get_lexqr returns after get_xStar)
     double *hh_star;           // LSI, with xstar: [B][M]
+    double *xln;               // LSE: [B][n] least-norm solution (solveLeastNorm, lexlse.h:1046-1262) or null
+    double *ln_scratch;        // LSE, with xln: [grid][ln_stride] work arrays (staircase copy n x (n+1), D n x n, 2n vectors)
+    unsigned long long ln_stride;
     double *reg_scratch;       // regularization: [grid][reg_stride] = null-space basis Z (n x (n+1)) | D (n x (n+1)) | 3n work doubles
     unsigned long long reg_stride;
     unsigned *wsl;             // LSI, deactivate_first_wrong_sign: [B][Mall] chronological list of activations (obj << 16 | ctr), lexlsi.h:158
@@ -425,7 +428,7 @@ namespace lexls_dev
 // LGV (the "work matrix in global memory" kernels): the rows of the level being factorized — the aligned row pairs
 // [fr & ~1, fr + dim rounded up) of columns ColIndex .. n — are staged in a shared-memory view `lv` (leading dimension ldv)
 // for the duration of the level, so that only the column swaps of the other rows go to global memory (L2).
-template <int W, bool LGV>
+template <int W, bool LGV, bool REG = false>
 __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const int ld, const int fr, const int dim, int &ColIndex,
                                               const double tol, double *const lv = nullptr, const int ldv = 0, double *const Zs = nullptr)
 {
@@ -549,7 +552,7 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                 const unsigned short s = c.varofcol[ColIndex];
                 c.varofcol[ColIndex] = c.varofcol[p];
                 c.varofcol[p]        = s;
-                if (Zs) // regularization: the accumulated null-space basis follows the column swap, lexlse.h:228-231
+                if constexpr (REG) // regularization: the accumulated null-space basis follows the column swap, lexlse.h:228-231
                     for (int q = 0; q < fc0; q++)
                     {
                         const double z      = Zs[q + n * ColIndex];
@@ -1224,14 +1227,15 @@ static __device__ __noinline__ void regularize_level(double *const LOD, const in
 //   read and written in aligned pairs (2t, 2t+1) with 128-bit accesses, conflict-free both for lanes over row pairs and
 //   for lanes over columns.  Rows [nCtr, ld) are zero padding.
 // ---------------------------------------------------------------------------------------------------------------
-template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
+template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG = false> __device__ int lse_factorize(const Ctx &c, const SmemMap &smap, const int n, const int ld, const int G,
                                               const int nCtr, const int nFixed, const double tol, FlopCount &fl, const int dmma = 0,
                                               const Params *const reg = nullptr, double *const reg_scratch = nullptr)
 {
     const PanelArgs pa = make_panel_args(smap, n, ld, nCtr, tol, dmma);
     // regularization (planned onto the shared-memory routines only, W >= 2): the null-space basis starts from zero, lexlse.h:1685
-    const bool regon = (W > 1) && reg && reg->reg_type != 0 && reg_scratch;
-    if (regon)
+    // (REG kernels are separate instantiations — kernels_*_reg.cu — so that the default kernels carry none of this)
+    constexpr bool regon = REG && (W > 1);
+    if constexpr (regon)
     {
         for (int e = threadIdx.x; e < n * (n + 1); e += 32 * W) reg_scratch[e] = 0.0;
         gsync<W>();
@@ -1306,7 +1310,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__
         if constexpr (PANEL)
             qr_level_panel_dispatch<CQ>(pa, fr, dim, ColIndex);
         else
-            qr_level_smem<W, LGV>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv, regon ? reg_scratch : nullptr);
+            qr_level_smem<W, LGV, regon>(c, n, ld, fr, dim, ColIndex, tol, c.LVIEW, smap.ldv, regon ? reg_scratch : nullptr);
 
         const int rank = ColIndex - fc;
         sumRank += rank;
@@ -1320,8 +1324,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16)> __device__
             fl.f += (unsigned long long)f;
         }
 
-        if constexpr (W > 1)
-            if (regon)
+        if constexpr (regon)
             {
                 // lexlse.h:274-411: between the QR of the level and its Gauss step (the modified right-hand side is what the
                 // lower levels see).
@@ -1555,12 +1558,119 @@ __device__ __forceinline__ void dump_lexqr(const Ctx &c, const Buffers &bf, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Least-norm solution of a factorized hierarchy, lexlse.h:1131-1205 (solveLeastNorm_2; _1 :1051-1124 and _3 :1213-1262 reach the
+// same minimiser by Givens rotations / the Tikhonov basis): the free variables z minimise ||x||^2, (I + S'S) z = S's with
+// [S s] = inv(R) [T b] over the staircase of all levels.  One warp, work arrays in a global scratch buffer, the oracle's arithmetic
+// (sequential fma chains, the triangular solves divide).  xperm receives x in factorization order: [fixed | determined | free].
+// ---------------------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void lse_least_norm(const double *const LOD, const int ld, const int n, const int G, const int *const frow,
+                                                   const int *const fcol, const int *const rank, const int nFixed, double *const scratch,
+                                                   double *const xperm)
+{
+    const int lane = threadIdx.x & 31;
+    int nVarRank   = 0;
+    for (int g = 0; g < G; g++) nVarRank += rank[g];
+    const int nVarFree = n - (nVarRank + nFixed), Wc = nVarFree + 1;
+    double *const A = scratch, *const D = scratch + (size_t)n * (n + 1), *const z = D + (size_t)n * n;
+    auto Am = [&](int i, int j) -> double & { return A[i + (size_t)nVarRank * j]; };
+    auto Dd = [&](int i, int j) -> double & { return D[i + (size_t)nVarFree * j]; };
+    int counter = 0;
+    for (int g = 0; g < G; g++)
+    {
+        const int fr = frow[g], fc = fcol[g], r = rank[g], cols = n + 1 - fc;
+        for (int e = lane; e < r * cols; e += 32)
+        {
+            const int i = e % r, j = e / r;
+            if (j >= i) Am(counter + i, counter + j) = LOD[fr + i + (size_t)ld * (fc + j)];
+        }
+        counter += r;
+    }
+    __syncwarp();
+    for (int c = lane; c < Wc; c += 32) // [S s] = inv(R) [T b]: one column per lane
+        for (int i = nVarRank; i--;)
+        {
+            double acc = Am(i, nVarRank + c);
+            for (int k = i + 1; k < nVarRank; k++) acc = fma(-Am(i, k), Am(k, nVarRank + c), acc);
+            Am(i, nVarRank + c) = acc / Am(i, i);
+        }
+    __syncwarp();
+    for (int e = lane; e < nVarFree * nVarFree; e += 32)
+    {
+        const int i = e / nVarFree, j = e - i * nVarFree;
+        if (j > i) continue;
+        double acc = 0.0;
+        for (int k = 0; k < nVarRank; k++) acc = fma(Am(k, nVarRank + i), Am(k, nVarRank + j), acc);
+        Dd(i, j) = (i == j) ? acc + 1.0 : acc;
+    }
+    for (int i = lane; i < nVarFree; i += 32)
+    {
+        double acc = 0.0;
+        for (int k = 0; k < nVarRank; k++) acc = fma(Am(k, nVarRank + i), Am(k, nVarRank + nVarFree), acc);
+        z[i] = acc;
+    }
+    __syncwarp();
+    for (int j = 0; j < nVarFree; j++) // Eigen::LLT, column oriented
+    {
+        double acc = Dd(j, j);
+        for (int k = 0; k < j; k++) acc = fma(-Dd(j, k), Dd(j, k), acc);
+        const double ljj = sqrt(acc);
+        __syncwarp();
+        if (lane == 0) Dd(j, j) = ljj;
+        for (int i = j + 1 + lane; i < nVarFree; i += 32)
+        {
+            double v = Dd(i, j);
+            for (int k = 0; k < j; k++) v = fma(-Dd(i, k), Dd(j, k), v);
+            Dd(i, j) = v / ljj;
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+    {
+        for (int i = 0; i < nVarFree; i++)
+        {
+            double v = z[i];
+            for (int k = 0; k < i; k++) v = fma(-Dd(i, k), z[k], v);
+            z[i] = v / Dd(i, i);
+        }
+        for (int i = nVarFree; i--;)
+        {
+            double v = z[i];
+            for (int k = i + 1; k < nVarFree; k++) v = fma(-Dd(k, i), z[k], v);
+            z[i] = v / Dd(i, i);
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < nVarFree; c += 32) xperm[nFixed + nVarRank + c] = z[c];
+    counter = 0;
+    for (int g = 0; g < G; g++)
+    {
+        const int fr = frow[g], r = rank[g];
+        for (int i = lane; i < r; i += 32)
+        {
+            double acc = LOD[fr + i + (size_t)ld * n];
+            for (int c = 0; c < nVarFree; c++) acc = fma(-LOD[fr + i + (size_t)ld * (nVarRank + nFixed + c)], z[c], acc);
+            xperm[nFixed + counter + i] = acc;
+        }
+        counter += r;
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int i = nVarRank; i--;)
+        {
+            double acc = xperm[nFixed + i];
+            for (int k = i + 1; k < nVarRank; k++) acc = fma(-Am(i, k), xperm[nFixed + k], acc);
+            xperm[nFixed + i] = acc / Am(i, i);
+        }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LexLSE kernel: one problem per group, record staged by one TMA bulk copy
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef LX_LSE_W2_MINB
 #define LX_LSE_W2_MINB 8
 #endif
-template <int W, bool LG>
+template <int W, bool LG, bool REG = false>
 __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 4 : (W == 2 ? LX_LSE_W2_MINB : 1)))) lse_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
@@ -1636,12 +1746,25 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma, &pr,
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG, REG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma, &pr,
                                                                                  bf.reg_scratch ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr);
         lse_solve<W, LG>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
         if (bf.v) lse_get_v<W>(c, n, ld, G);
         if (bf.lexqr) dump_lexqr<NT>(c, bf, p, n, ld, nCtr, nCtr);
+        if (bf.xln)
+        {
+            // solveLeastNorm (lexlse.h:1046-1262) next to the basic solution: warp 0, x in factorization order in the scratch, then
+            // the same un-permutation as solve()
+            gsync<W>();
+            double *const sc = bf.ln_scratch + blockIdx.x * bf.ln_stride, *const xperm = sc + (size_t)2 * n * (n + 1) + n;
+            if (tid < 32)
+            {
+                for (int f = tid; f < sh.nfix; f += 32) xperm[f] = bf.fval[p * sh.nfix + f];
+                lse_least_norm(c.LOD, ld, n, G, c.frow, c.fcol, c.rank, sh.nfix, sc, xperm);
+                for (int k = tid; k < n; k += 32) bf.xln[p * n + c.varofcol[k]] = xperm[k];
+            }
+        }
         gsync<W>(); // the work matrix is dead: every thread is done with it
         fetch_and_load();
         if (bf.v)
@@ -2115,7 +2238,7 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
 // formLexLSE + factorize + solve of one active-set iteration as ONE real call: the LexLSI kernel needs it at three places
 // (phase 1, the first step from a user guess, the loop), and three inlined copies do not fit the instruction cache.
 // The context is rebuilt from the shared-memory map (kernel parameter, __grid_constant__: its address may be taken).
-template <int W, bool DS, bool LG>
+template <int W, bool DS, bool LG, bool REG = false>
 __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap &sm, const double tol, double *lod, double *objp,
                                                   double *sbp, int &nFixed, int &nFixedPrev, int &totalRank, FlopCount &fl,
                                                   const int dmma, double *const data_dump = nullptr, const Params *const reg = nullptr,
@@ -2132,11 +2255,11 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
         dump_lod<32 * W>(c, data_dump, nullptr, 0ull, sh.n, sh.ld, nCtr, sh.M);
         gsync<W>();
     }
-    totalRank      = lse_factorize<W, true, true, LG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl, dmma, reg, reg_scratch);
+    totalRank      = lse_factorize<W, true, true, LG, REG>(c, sm, sh.n, sh.ld, sh.G, nCtr, nFixed, tol, fl, dmma, reg, reg_scratch);
     lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
-template <int W, bool DS, bool LG>
+template <int W, bool DS, bool LG, bool REG = false>
 __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
@@ -2362,7 +2485,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             wsn--;
         };
 
-        double *const reg_scratch = bf.reg_scratch ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr;
+        double *const reg_scratch = REG ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr;
         unsigned nIter = 0, nFact = 0, nAct = 0, nDeact = 0, cycCounter = 0;
         int status = ST_UNKNOWN, totalRank = 0, nFixed = 0, nFixedPrev = 0;
         int cycPrevOp = OP_UNDEFINED, cycPrevObj = 0, cycPrevCtr = 0, cycPrevType = CTR_INACTIVE;
@@ -2388,8 +2511,8 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
             }
         };
         auto factor_and_solve = [&]() {
-            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma, nullptr,
-                                            pr.reg_type ? &pr : nullptr, reg_scratch);
+            lsi_factor_and_solve<W, DS, LG, REG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma, nullptr,
+                                                 REG ? &pr : nullptr, reg_scratch);
         };
 
         // ---- phase 1, lexlsi.h:816-869 (phase1_v0: :880-915) ---------------------------------------------------
@@ -2746,8 +2869,8 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(con
         {
             // get_xStar, lexlsi.h:519-526: formLexLSE + factorize + solve with the FINAL working set; get_data() and
             // get_lexqr() called after it return this problem's constraints and factorization (tests/test_numerical_error.cpp:83-86)
-            lsi_factor_and_solve<W, DS, LG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma,
-                                            bf.lexdata + p * (unsigned long long)sh.M * (n + 1), pr.reg_type ? &pr : nullptr, reg_scratch);
+            lsi_factor_and_solve<W, DS, LG, REG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma,
+                                                 bf.lexdata + p * (unsigned long long)sh.M * (n + 1), REG ? &pr : nullptr, reg_scratch);
             for (int k = tid; k < n; k += NT) bf.xstar[p * n + k] = c.lx[k];
             int nc = 0;
             for (int g = 0; g < G; g++) nc += c.ldim[g];

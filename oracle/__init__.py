@@ -10,4 +10,5 @@ from .pyoracle import (  # noqa: F401
     lsi_solve_batch,
     lsi_solve_detail,
     set_regularization,
+    set_least_norm,
 )

@@ -526,6 +526,100 @@ public:
         for (Index k = TotalRank; k--;) std::swap(x[k], x[column_permutations[k]]);
     }
 
+    // -----------------------------------------------------------------------------------------
+    // lexlse.h:1131-1205 solveLeastNorm_2: of all solutions of the factorized hierarchy (the free variables are arbitrary),
+    // the one of least norm, by the normal equations (I + S'S) z = S's with [S s] = inv(R) [T b] over the staircase of all
+    // levels.  (solveLeastNorm_1, Givens rotations :1051-1124, and _3, the Tikhonov basis :1213-1262, compute the same
+    // minimiser with other roundings; this restatement stands for all three.)  Arithmetic: sequential fma chains, ascending
+    // index; the triangular solves divide.
+    // -----------------------------------------------------------------------------------------
+    void solveLeastNorm()
+    {
+        Index nVarRank = 0;
+        for (Index k = 0; k < nObj; k++) nVarRank += obj_info[k].rank;
+        const Index nVarFree = nVar - (nVarRank + nVarFixed), W = nVarFree + 1;
+        // staircase copy: RT(counter + i, counter + j) = LOD(fr + i, fc + j), j >= i  (upper triangle of R, all of T and b)
+        std::vector<double> RT((size_t)nVarRank * (nVarRank + W), 0.0);
+        auto A = [&](Index i, Index j) -> double & { return RT[(size_t)j * nVarRank + i]; };
+        Index counter = 0;
+        for (Index k = 0; k < nObj; k++)
+        {
+            const Index fr = obj_info[k].first_row_index, fc = obj_info[k].first_col_index, r = obj_info[k].rank;
+            for (Index i = 0; i < r; i++)
+                for (Index j = i; fc + j <= nVar; j++) A(counter + i, counter + j) = L(fr + i, fc + j);
+            counter += r;
+        }
+        // [S s] = inv(R) [T b], column by column (back substitution)
+        for (Index c = 0; c < W; c++)
+            for (Index i = nVarRank; i--;)
+            {
+                double acc = A(i, nVarRank + c);
+                for (Index k = i + 1; k < nVarRank; k++) acc = fmad(-A(i, k), A(k, nVarRank + c), acc);
+                A(i, nVarRank + c) = acc / A(i, i);
+            }
+        // D = S'S + I (lower), d = S's
+        std::vector<double> Dn((size_t)nVarFree * nVarFree, 0.0), z(nVarFree, 0.0);
+        for (Index i = 0; i < nVarFree; i++)
+        {
+            for (Index j = 0; j <= i; j++)
+            {
+                double acc = 0.0;
+                for (Index k = 0; k < nVarRank; k++) acc = fmad(A(k, nVarRank + i), A(k, nVarRank + j), acc);
+                Dn[(size_t)j * nVarFree + i] = (i == j) ? acc + 1.0 : acc;
+            }
+            double acc = 0.0;
+            for (Index k = 0; k < nVarRank; k++) acc = fmad(A(k, nVarRank + i), A(k, nVarRank + nVarFree), acc);
+            z[i] = acc;
+        }
+        auto Dd = [&](Index i, Index j) -> double & { return Dn[(size_t)j * nVarFree + i]; };
+        for (Index j = 0; j < nVarFree; j++) // Eigen::LLT
+        {
+            double acc = Dd(j, j);
+            for (Index k = 0; k < j; k++) acc = fmad(-Dd(j, k), Dd(j, k), acc);
+            const double ljj = std::sqrt(acc);
+            Dd(j, j)         = ljj;
+            for (Index i = j + 1; i < nVarFree; i++)
+            {
+                double a = Dd(i, j);
+                for (Index k = 0; k < j; k++) a = fmad(-Dd(i, k), Dd(j, k), a);
+                Dd(i, j) = a / ljj;
+            }
+        }
+        for (Index i = 0; i < nVarFree; i++)
+        {
+            double a = z[i];
+            for (Index k = 0; k < i; k++) a = fmad(-Dd(i, k), z[k], a);
+            z[i] = a / Dd(i, i);
+        }
+        for (Index i = nVarFree; i--;)
+        {
+            double a = z[i];
+            for (Index k = i + 1; k < nVarFree; k++) a = fmad(-Dd(k, i), z[k], a);
+            z[i] = a / Dd(i, i);
+        }
+        for (Index c = 0; c < nVarFree; c++) x[nVarFixed + nVarRank + c] = z[c];
+        // the determined variables: R y = b - T z over the staircase
+        counter = 0;
+        for (Index k = 0; k < nObj; k++)
+        {
+            const Index fr = obj_info[k].first_row_index, r = obj_info[k].rank;
+            for (Index i = 0; i < r; i++)
+            {
+                double acc = L(fr + i, nVar);
+                for (Index c = 0; c < nVarFree; c++) acc = fmad(-L(fr + i, nVarRank + nVarFixed + c), z[c], acc);
+                x[nVarFixed + counter + i] = acc;
+            }
+            counter += r;
+        }
+        for (Index i = nVarRank; i--;)
+        {
+            double acc = x[nVarFixed + i];
+            for (Index k = i + 1; k < nVarRank; k++) acc = fmad(-A(i, k), x[nVarFixed + k], acc);
+            x[nVarFixed + i] = acc / A(i, i);
+        }
+        for (Index k = TotalRank; k--;) std::swap(x[k], x[column_permutations[k]]); // x = P*x
+    }
+
     // Q_k * y for level k; y has obj_info[k].dim entries.  householderSequence(...).applyOnTheLeft,
     // eigen_like_syntax/applyOnTheLeft.m:11-14, householderSequence.m:11-15.
     void applyQ(Index k, double *y) const

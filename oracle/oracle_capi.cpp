@@ -40,6 +40,13 @@ struct oracle_params
 static int g_reg_type = 0;
 static double g_reg_var = 0.0;
 static std::vector<double> g_reg_factors;
+static int g_least_norm = 0; // LexLSE batches: solveLeastNorm instead of solve()
+
+extern "C" int oracle_set_least_norm(int on)
+{
+    g_least_norm = on;
+    return 0;
+}
 
 extern "C" int oracle_set_regularization(int type, double variable_factor, const double *factors, uint32_t count)
 {
@@ -171,7 +178,10 @@ int oracle_lse_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
                 lse.setData(k, data[k] + p * (uint64_t)ObjDim[k] * (nVar + 1), ObjDim[k]);
             lse.min_pivot_gap = lse.min_rank_margin = 1e300;
             lse.factorize();
-            lse.solve();
+            if (g_least_norm)
+                lse.solveLeastNorm();
+            else
+                lse.solve();
             if (x) std::memcpy(x + p * nVar, lse.get_x().data(), sizeof(double) * nVar);
             if (v) std::memcpy(v + p * nCtr, lse.get_v(), sizeof(double) * nCtr);
             if (ranks)

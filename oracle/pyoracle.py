@@ -90,6 +90,11 @@ def set_regularization(reg_type=0, factors=None, variable_factor=0.0):
                                     f.ctypes.data_as(C.POINTER(C.c_double)) if f.size else None, C.c_uint32(f.size))
 
 
+def set_least_norm(on):
+    """LexLSE batches: solveLeastNorm (lexlse.h:1131-1205) instead of solve() after the factorization."""
+    lib().oracle_set_least_norm(C.c_int(1 if on else 0))
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 

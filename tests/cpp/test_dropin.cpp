@@ -89,6 +89,37 @@ int main()
         lse.factorize();
         lse.solve();
         if (std::fabs(lse.get_x()(0) - 0.5) > 1e-12 || std::fabs(lse.get_x()(2) - 2.0) > 1e-12) { std::printf("FAIL fixed\n"); return 1; }
+        // regularization and the least-norm solve through the facade: x1 + x2 + x3 = 3 alone (rank 1, two free variables):
+        // solve() gives the basic solution (3, 0, 0) up to the pivot choice, solveLeastNorm the minimum-norm one (1, 1, 1);
+        // R_NO_Z damping with factor 1 halves the reduced right-hand side: the basic solution becomes (1.5, 0, 0)
+        {
+            Index d1[1] = {1};
+            internal::LexLSE one(3, 1, d1);
+            one.setData(0, a);
+            one.factorize();
+            one.solve();
+            double nb = 0.0;
+            for (Index k = 0; k < 3; k++) nb += one.get_x()(k) * one.get_x()(k);
+            if (std::fabs(nb - 9.0) > 1e-9) { std::printf("FAIL basic solution norm %g\n", nb); return 1; }
+            one.solveLeastNorm_2();
+            for (Index k = 0; k < 3; k++)
+                if (std::fabs(one.get_x()(k) - 1.0) > 1e-12) { std::printf("FAIL least norm x[%u] = %g\n", k, one.get_x()(k)); return 1; }
+            internal::LexLSE reg(3, 1, d1);
+            ParametersLexLSE pr;
+            pr.regularization_type = REGULARIZATION_R_NO_Z;
+            reg.setParameters(pr);
+            reg.setRegularizationFactor(0, 1.0);
+            reg.setData(0, a);
+            reg.factorize();
+            reg.solve();
+            // R = |(1,1,1)| up to sign: the damped right-hand side is R (R'R + 1)^-1 R' b~ = b~ * R^2 / (R^2 + 1) with R^2 = 1 (one pivot)
+            double s = 0.0;
+            for (Index k = 0; k < 3; k++) s += reg.get_x()(k);
+            if (std::fabs(s - 1.5) > 1e-9) { std::printf("FAIL regularized basic solution sum %g\n", s); return 1; }
+            bool threw = false;
+            try { pr.regularization_type = REGULARIZATION_TIKHONOV_CG; reg.setParameters(pr); } catch (Exception &) { threw = true; }
+            if (!threw) { std::printf("FAIL CG regularization must be refused\n"); return 1; }
+        }
         std::printf("OK\n");
         return 0;
     }

@@ -499,3 +499,39 @@ def test_unimplemented_regularization_types_are_refused():
             assert e.value.code == 3
         with pytest.raises(lx.LexLSError):
             s.setParameters(lx.Params(regularization_type=12))
+
+
+# ---- solveLeastNorm (lexlse.h:1046-1262) ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["w1", "w2", "lg8"])
+def test_least_norm_solution_matches_the_oracle_and_pinv(oracle, monkeypatch, variant):
+    import lexls_b200 as lx
+    env = {"w1": {}, "w2": dict(WARPS=2), "lg8": dict(FORCE_LODGLOBAL=1, LG_WARPS=8)}[variant]
+    for k, v in env.items():
+        monkeypatch.setenv("LEXLS_B200_" + k, str(v))
+    rng = np.random.default_rng(31)
+    for n, dims, fixed in ((10, [3, 2, 2], False), (16, [4, 5, 3], True), (8, [3, 9], False)):
+        B = 9
+        data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+        fi = np.tile(np.array([1, 4], dtype=np.uint32), (B, 1)) if fixed else None
+        fv = rng.standard_normal((B, 2)) if fixed else None
+        oracle.set_least_norm(True)
+        try:
+            ref = oracle.lse_solve_batch(n, dims, data, fixed_index=fi, fixed_value=fv, threads=0)
+        finally:
+            oracle.set_least_norm(False)
+        basic = oracle.lse_solve_batch(n, dims, data, fixed_index=fi, fixed_value=fv, threads=0)
+        with lx.LexLSEBatch(n, dims, batch=B) as s:
+            s.request_outputs(least_norm=True)
+            if fixed:
+                s.fixVariables(fi, fv)
+            for k, d in enumerate(data):
+                s.setData(k, d)
+            s.solve()
+            x_ln, x = s.get_x_least_norm(), s.get_x()
+        assert np.array_equal(x, basic["x"]) and np.array_equal(x_ln, ref["x"])
+        assert (np.linalg.norm(x_ln, axis=1) <= np.linalg.norm(x, axis=1) + 1e-12).all()
+        if not fixed and sum(dims) <= n:
+            for p in range(B):  # consistent equalities: the least-norm solution is the pseudo-inverse solution
+                A = np.concatenate([d[p].T[:, :n] for d in data])
+                b = np.concatenate([d[p].T[:, n] for d in data])
+                assert np.abs(x_ln[p] - np.linalg.pinv(A) @ b).max() < 1e-9
