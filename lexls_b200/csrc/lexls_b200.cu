@@ -77,6 +77,8 @@ struct lexls_b200_batch
     double *lexqr = nullptr, *hhout = nullptr, *lambda = nullptr; // optional outputs (lexls_b200_request_outputs)
     double *xstar = nullptr, *lexdata = nullptr, *lexqr_star = nullptr, *hh_star = nullptr; // LEXLS_B200_OUT_XSTAR
     double reg_factor_user[LX_MAX_LEVELS] = {0};                   // setRegularizationFactor per user objective
+    double *vec_scratch = nullptr;                                 // SmemMap::vecg: iteration vectors of the resident problems
+    size_t vec_bytes = 0;
     double *xln = nullptr, *ln_scratch = nullptr;                  // LEXLS_B200_OUT_LEAST_NORM
     size_t ln_bytes = 0;
     uint64_t ln_stride = 0;
@@ -231,7 +233,7 @@ static unsigned align_up(unsigned v, unsigned a)
     return (v + a - 1) / a * a;
 }
 
-static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel_only = false)
+static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel_only = false, bool vecg = false)
 {
     SmemMap m{};
     unsigned o = 0;
@@ -269,7 +271,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.hh = take((M + 1) * 8, 8);
     m.wsp = alias_tmp ? 0 : take((2 * m0 + M + n + 2) * 8, 8);
     if (alias_cn) m.colnorm = m.wsp;
-    const unsigned vecs = lsi ? Mall + 1 : 1;
+    const unsigned vecs = (lsi && !vecg) ? Mall + 1 : 1; // vecg: the four iteration vectors live in a global scratch slice
     m.v = take(vecs * 8, 8);
     m.dv = take(vecs * 8, 8);
     m.Ax = take(vecs * 8, 8);
@@ -296,6 +298,7 @@ static SmemMap build_map(const Shape &sh, bool lsi, bool DS, bool LG, bool panel
     m.scal = take(8 * 4, 8);
     m.mbar = take(8, 8);
     m.total = align_up(o, 128);
+    m.vecg  = (lsi && vecg) ? 1 : 0;
     return m;
 }
 
@@ -420,6 +423,13 @@ static int plan(lexls_b200_batch *h)
                 W    = w;
             }
         }
+    }
+    if (lsi && !LG && getenv("LEXLS_B200_VECG"))
+    {
+        // experiment knob (measured: no gain on C3, see lexls_device.cuh at LX_LSI_W2_MINB): moving v, dv, Ax, Adx out of shared
+        // memory when it lets one more problem become resident per SM
+        const SmemMap mg = build_map(h->sh, lsi, DS, LG, panel_only, true);
+        if (m.total <= max_smem && fit(mg) > fit(m)) m = mg;
     }
     bool auto_lg = false;
     // (a batch that fits one wave of the shared-memory kernel stays there: 2.7 vs 3.0 ms for one test_01.dat problem)
@@ -759,7 +769,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
-                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch, h->xln, h->ln_scratch};
+                    h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch, h->xln, h->ln_scratch, h->vec_scratch};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1178,6 +1188,20 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
         b.hh_star    = h->hh_star;
     }
     b.glist = h->have_glist ? h->glist : nullptr;
+    if (h->sm.vecg)
+    {
+        b.vec_stride      = (uint64_t)((s.Mall + 2) | 1); // odd: the four vectors of a problem do not share cache-line phases
+        const size_t need = sizeof(double) * 4 * b.vec_stride * h->grid;
+        if (need > h->vec_bytes)
+        {
+            if (h->vec_scratch) guarded_free(h, h->vec_scratch);
+            h->vec_scratch = nullptr;
+            h->vec_bytes   = 0;
+            CK(guarded_malloc(h, (void **)&h->vec_scratch, need));
+            h->vec_bytes = need;
+        }
+        b.vec_scratch = h->vec_scratch;
+    }
     if ((h->want & LEXLS_B200_OUT_LEAST_NORM) && h->kind == LEXLS_B200_LSE)
     {
         const uint64_t n = (uint64_t)s.n;

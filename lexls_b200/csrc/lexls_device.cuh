@@ -89,6 +89,7 @@ struct SmemMap
     unsigned active, inactive, atype, alltype, ctype, fidx, ftype, colperm, varofcol, sbidx;
     unsigned ldim, frow, fcol, rank, nact, ninact, scal, mbar, total;
     int ldv; // leading dimension of the level view of the global-memory variants
+    int vecg; // LexLSI: v, dv, Ax, Adx live in a global scratch slice (vec_scratch) instead of shared memory: one more problem per SM
 };
 
 struct Buffers
@@ -123,6 +124,8 @@ struct Buffers
     double *lexdata;           // LSI, with xstar: [B][(n+1) x M] that problem's constraints as given (LexLSE::get_data, lexlse.h:119, :1631)
     double *lexqr_star;        // LSI, with xstar: [B][(n+1) x M] its factorization (what get_lexqr returns after get_xStar)
     double *hh_star;           // LSI, with xstar: [B][M]
+    double *vec_scratch;       // LSI, SmemMap::vecg: [grid][4 * vec_stride] v | dv | Ax | Adx of the resident problem
+    unsigned long long vec_stride;
     double *xln;               // LSE: [B][n] least-norm solution (solveLeastNorm, lexlse.h:1046-1262) or null
     double *ln_scratch;        // LSE, with xln: [grid][ln_stride] work arrays (staircase copy n x (n+1), D n x n, 2n vectors)
     unsigned long long ln_stride;
@@ -2259,14 +2262,31 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
+// two-warp LexLSI kernel (C3).  Measured (profiles/r2_experiments.json): nine problems per SM (iteration vectors in the global
+// scratch, SmemMap::vecg, and a register cap of 112 = LX_LSI_W2_MINB 9) are not faster than eight (13.47 / 3.20 ms vs 13.26 / 3.04 ms
+// cold / warm): the kernel is bound by instruction fetch (85-108 KB of code run once or twice per problem against a 32 KB
+// instruction cache: 20 % of the stall samples) and by its barriers, not by residency.  So no minimum block count.
+#ifndef LX_LSI_W2_MINB
+#define LX_LSI_W2_MINB 0
+#endif
 template <int W, bool DS, bool LG, bool REG = false>
-__global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : 0) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
+__global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W == 2) ? LX_LSI_W2_MINB : 0)) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,
                                                       const __grid_constant__ SmemMap sm, const __grid_constant__ Buffers bf)
 {
     constexpr int NT = 32 * W;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ctx c = make_ctx(smem_raw, sm);
     if constexpr (LG) c.LOD = bf.lod_scratch + blockIdx.x * bf.lod_stride;
+    if (sm.vecg)
+    {
+        // the four iteration vectors are touched a few times per active-set iteration only: from an L2-resident slice they cost
+        // nothing measurable, and the 3.2 KB they free let a ninth C3 problem become resident per SM
+        double *const vs = bf.vec_scratch + (size_t)blockIdx.x * 4 * bf.vec_stride;
+        c.v   = vs;
+        c.dv  = vs + bf.vec_stride;
+        c.Ax  = vs + 2 * bf.vec_stride;
+        c.Adx = vs + 3 * bf.vec_stride;
+    }
     const int tid = threadIdx.x, lane = tid & 31;
     const int n = sh.n, ld = sh.ld, G = sh.G, P = sh.P;
     // the set_* calls found invalid input (lb > ub, duplicate VarIndex): the reference throws in setData; here the solve is
