@@ -345,7 +345,7 @@ def measure(name, args, torch, dist, rank, world, local, steps, e2e_steps, batch
     for _ in range(2):
         with_gather(r.e2e_step)()
     legs["plain"] = timed(torch, dist, world, with_gather(r.e2e_step), e2e_steps)
-    chunks = args.e2e_chunks if w.kind == "lse" else min(args.e2e_chunks, 2)
+    chunks = args.e2e_chunks
     if chunks > 1:
         r.make_pipeline(chunks, local)
         for _ in range(2):

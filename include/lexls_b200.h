@@ -178,6 +178,11 @@ int lexls_b200_synchronize(lexls_b200_batch_t *h);
 /* waits for the set_* calls issued so far and reports what their device-side checks found: EBOUNDS for lb > ub
  * (lexlsi.h:430, :474), EINVAL for duplicate / out-of-range VarIndex (lexlsi.h:485); the offending data must be set again */
 int lexls_b200_validate(lexls_b200_batch_t *h);
+/* By default a host set_* call returns once the caller's buffer has been consumed (the reference copies in setData).  With
+ * async copies enabled the calls only ENQUEUE their copy: the caller keeps every input buffer valid and unmodified until
+ * the next synchronising call (synchronize, solve_batch_sync, get_*).  For pinned host buffers this removes every host
+ * wait between the set_* calls of a batch (lexls_b200.PipelinedBatch uses it). */
+int lexls_b200_set_async_copies(lexls_b200_batch_t *h, int enabled);
 
 /* ---- results (host destinations; each call synchronises the handle's stream) -----------------------------------
  * get_x: get_x lexlse.h:1587 / lexlsi.h:508 -> [batch][nVar]

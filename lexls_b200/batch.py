@@ -48,9 +48,26 @@ class _Batch:
                                                 C.c_uint64(self.batch), C.c_int(self.device), C.byref(h)))
         self._h = h
 
+    def set_async_copies(self, enabled=True):
+        """Host set* calls only enqueue their copies; the caller keeps the input arrays alive and unmodified until the next
+        synchronising call (solve(), synchronize(), get_*)."""
+        check(lib().lexls_b200_set_async_copies(self._h, C.c_int(1 if enabled else 0)))
+        self._async = bool(enabled)
+        self._keep = []
+
+    def _hold(self, *arrays):
+        """async copies: the converted input arrays must outlive the enqueued copy (released at the next synchronisation)."""
+        if getattr(self, "_async", False):
+            self._keep.extend(arrays)
+
+    def _release(self):
+        if getattr(self, "_async", False):
+            self._keep = []
+
     def validate(self):
         """Waits for the set* calls issued so far and raises what their device-side checks found (lexlsi.h:430, :474, :485)."""
         check(lib().lexls_b200_validate(self._h))
+        self._release()
 
     def check_guard_bands(self):
         """LEXLS_B200_CANARY=1: number of device buffers whose trailing guard band was written into (0 = clean)."""
@@ -107,6 +124,7 @@ class _Batch:
         if a.shape != (self.batch, cols, m):
             raise ValueError("level %d: expected shape %s, got %s" % (level, (self.batch, cols, m), a.shape))
         check(lib().lexls_b200_set_data(self._h, C.c_uint32(level), _dp(a), C.c_uint32(max(m, 1)), C.c_uint64(m * cols)))
+        self._hold(a)
         if self.strict:
             self.validate()
 
@@ -123,6 +141,7 @@ class _Batch:
 
     def synchronize(self):
         check(lib().lexls_b200_synchronize(self._h))
+        self._release()
 
     # ---- results ------------------------------------------------------------------------------------------------
     def get_x(self, out=None):
@@ -131,6 +150,7 @@ class _Batch:
         if x.shape != (self.batch, self.nVar) or x.dtype != np.float64 or not x.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 [B, nVar] array")
         check(lib().lexls_b200_get_x(self._h, _dp(x)))
+        self._release()
         return x
 
     def get_v(self, level):
@@ -238,6 +258,7 @@ class LexLSIBatch(_Batch):
             check(lib().lexls_b200_set_simple_bounds(self._h, vi.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                      C.c_uint64(0 if shared else m), _dp(a), C.c_uint32(max(m, 1)),
                                                      C.c_uint64(2 * m)))
+            self._hold(a, vi)
             if self.strict:
                 self.validate()
         else:
@@ -251,6 +272,7 @@ class LexLSIBatch(_Batch):
         if t.shape != (self.batch, self.ObjDim[level]):
             raise ValueError("guess must be [B, m]")
         check(lib().lexls_b200_set_active_guess(self._h, C.c_uint32(level), t.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._hold(t)
 
     def set_active_guess_ordered(self, obj, ctr, types):
         """api_activate calls in CALL order (lexlsi.h:120-136): obj, ctr, types are [B, count]; type 0 pads ragged lists."""
@@ -285,6 +307,7 @@ class LexLSIBatch(_Batch):
         if a.shape != (self.batch, self.nVar):
             raise ValueError("x0 must be [B, nVar]")
         check(lib().lexls_b200_set_x0(self._h, _dp(a)))
+        self._hold(a)
 
     def set_v0(self, level, v0):
         a = np.ascontiguousarray(v0, dtype=np.float64)

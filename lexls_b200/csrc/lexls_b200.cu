@@ -95,6 +95,7 @@ struct lexls_b200_batch
     unsigned want = 0;
     int *status = nullptr, *flag = nullptr;
     int *hflag = nullptr;          // pinned host copy of `flag`, refreshed by every solve_batch (no extra synchronisation)
+    bool async_copies = false;     // lexls_b200_set_async_copies: host set_* calls return without waiting for their copy
     bool flag_pending = false;     // a solve has been enqueued whose flag copy has not been inspected yet
     cudaEvent_t ev_copy = nullptr; // completion of the last host -> staging copy (the caller's buffer is then free)
     uint64_t nfix_cap = 0;         // elements allocated in fidx / fval / ftype
@@ -141,6 +142,7 @@ static void guarded_free(lexls_b200_batch *h, void *p)
 static int ensure_stage(lexls_b200_batch *h, size_t bytes)
 {
     if (h->stage_bytes >= bytes) return 0;
+    if (h->stage) CK(cudaStreamSynchronize(h->stream)); // an earlier (asynchronous) copy or repack may still use the old buffer
     if (h->stage) guarded_free(h, h->stage);
     h->stage       = nullptr;
     h->stage_bytes = 0;
@@ -866,6 +868,7 @@ static int check_pending_flag(lexls_b200_batch *h)
 // host inputs: returns once the caller's buffer has been consumed (copied into the staging buffer)
 static int wait_copy(lexls_b200_batch *h)
 {
+    if (h->async_copies) return 0; // the caller keeps its buffers valid until the next synchronisation
     CK(cudaEventRecord(h->ev_copy, h->stream));
     CK(cudaEventSynchronize(h->ev_copy));
     return 0;
@@ -1593,6 +1596,14 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
     CK(cudaMemcpyAsync(h->glist, packed.data(), sizeof(unsigned) * packed.size(), cudaMemcpyHostToDevice, h->stream));
     if (int rc = wait_copy(h)) return rc;
     h->have_glist = true;
+    return 0;
+}
+
+int lexls_b200_set_async_copies(lexls_b200_batch_t *h, int enabled)
+{
+    MULTI(h, false, lexls_b200_set_async_copies(s.h, enabled));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    h->async_copies = enabled != 0;
     return 0;
 }
 

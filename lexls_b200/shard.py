@@ -134,6 +134,8 @@ class PipelinedBatch:
         for lo, hi in self.ranges:
             kw = dict(batch=hi - lo, device=device, strict=False)
             self.parts.append((lo, hi, cls(nVar, ObjDim, ObjType, **kw) if ObjType is not None else cls(nVar, ObjDim, **kw)))
+        for _, _, s in self.parts:
+            s.set_async_copies(True)  # solve_host keeps the caller's arrays alive until every chunk has delivered its x
         self._lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=len(self.parts))
 
@@ -172,6 +174,7 @@ class PipelinedBatch:
                         s.set_active_guess(k, g[lo:hi])
                 if x0 is not None:
                     s.set_x0(x0[lo:hi])
+                s.validate()  # the one wait of this chunk: its copies are done before the next chunk gets the link
             s.solve(sync=False)
             s.get_x(out=x_out[lo:hi])
 
