@@ -19,17 +19,13 @@ for ln in sass.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m and cur_fn and ksub in cur_fn:
         addr2line[int(m.group(1), 16)] = cur_line
-# function ranges from the sources (a line belongs to the last function header above it)
+# function ranges from the sources: the same ranges scripts/ncu_by_range.py uses (scripts/ncu_ranges.py)
 fn_of = {}
-for f in ("lexls_device.cuh", "lexls_panel.cuh"):
-    lines = open(os.path.join(root, "lexls_b200", "csrc", f)).read().splitlines()
-    cur = "?"
-    for i, t in enumerate(lines, 1):
-        m = re.match(r"^(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__)[^;(]*?\b(\w+)\s*\($", t.strip()) or \
-            re.match(r"^(?:static\s+)?(?:__device__|__global__).*?\b(\w+)\s*\(", t.strip())
-        if m and not t.startswith(" "):
-            cur = m.group(1)
-        fn_of[(f, i)] = cur
+for item in subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_ranges.py")], capture_output=True, text=True).stdout.split():
+    f, name, rng = item.split(":")
+    lo, hi = rng.split("-")
+    for i in range(int(lo), int(hi) + 1):
+        fn_of[(f, i)] = name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]

@@ -3,7 +3,7 @@
 import os, re
 root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lexls_b200", "csrc")
 out = []
-for f in ("lexls_device.cuh", "lexls_panel.cuh", "lexls_pair.cuh"):
+for f in ("lexls_device.cuh", "lexls_panel.cuh"):
     lines = open(os.path.join(root, f)).read().splitlines()
     starts = []
     for i, ln in enumerate(lines, 1):
