@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblexls_b200.so")
+SO_PATH = os.environ.get("LEXLS_B200_LIB") or os.path.join(_HERE, "liblexls_b200.so")  # the variable: scripts/build_variants.py
 
 # every symbol include/lexls_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [

@@ -10,9 +10,10 @@ kernel_fn pick_lse_pair_kernel()
     return nullptr; // experiment not compiled into the product library (build with -DLEXLS_B200_WITH_PAIR)
 #endif
 }
+kernel_fn pick_lse_lg_kernel(int W); // kernels_lg.cu
 kernel_fn pick_lse_kernel(int W, bool LG)
 {
-    if (LG) return W == 8 ? (kernel_fn)lse_kernel<8, true> : (kernel_fn)lse_kernel<16, true>;
+    if (LG) return pick_lse_lg_kernel(W);
     switch (W)
     {
     case 1: return (kernel_fn)lse_kernel<1, false>;

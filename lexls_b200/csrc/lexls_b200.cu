@@ -479,6 +479,17 @@ static int plan(lexls_b200_batch *h)
     int per_sm  = 0;
     if (int rc = occupancy_of(k, 32 * W, h->smem, &per_sm)) return rc;
     if (per_sm < 1) return fail(LEXLS_B200_ECAPACITY, "kernel does not fit on an SM");
+    if (const char *e = getenv("LEXLS_B200_PER_SM"))
+    {
+        // experiment knob (profiles/r2_experiments.json): throughput against the number of resident problems per SM — the
+        // dynamic shared memory is padded until the occupancy drops to the requested value
+        const int cap = atoi(e);
+        while (cap >= 1 && per_sm > cap && h->smem + 1024 <= max_smem)
+        {
+            h->smem += 1024;
+            if (int rc = occupancy_of(k, 32 * W, h->smem, &per_sm)) return rc;
+        }
+    }
     h->per_sm = per_sm;
     unsigned long long g = (unsigned long long)prop.multiProcessorCount * per_sm;
     if (g > h->batch) g = h->batch;

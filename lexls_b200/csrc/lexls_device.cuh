@@ -23,6 +23,9 @@ namespace lexls_dev
 #ifndef LX_LSE_COMPACT_QR
 #define LX_LSE_COMPACT_QR false
 #endif
+#ifndef LX_LSE_COMPACT_GS
+#define LX_LSE_COMPACT_GS false
+#endif
 
 enum
 {
@@ -1248,7 +1251,9 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
     double *const LOD = c.LOD;
     const int hp      = ld >> 1; // row pairs per column
 
+#pragma unroll 1
     for (int k = tid; k < n; k += NT) c.varofcol[k] = (unsigned short)k;
+#pragma unroll 1
     for (int g = tid; g < G; g += NT)
     {
         c.rank[g] = 0;
@@ -1263,6 +1268,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
         {
             const int coeff = c.fidx[k];
             if (k != coeff)
+#pragma unroll 1
                 for (int t = tid; t < hp; t += NT)
                 {
                     const double2 a = ld2(LOD + ld * k + 2 * t);
@@ -1289,6 +1295,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
             gsync<W>();
         }
         // RHS -= LOD[:, 0:nFixed] * x[0:nFixed]   (S)
+#pragma unroll 1
         for (int r = tid; r < nCtr; r += NT)
         {
             double acc = LOD[r + ld * n];
@@ -1337,6 +1344,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
                     regularize_level(LOD, ld, n, fr, fc, rank, n - ColIndex, nFixed, reg->reg_type, reg->reg_factor[g], reg->reg_var,
                                      c.invd, reg_scratch);
                     if constexpr (LGV) // the Gauss step reads the level's rows from the shared-memory view: refresh its right-hand side
+#pragma unroll 1
                         for (int i = threadIdx.x; i < rank; i += 32) c.LVIEW[(fr - 2 * (fr >> 1)) + i + smap.ldv * n] = LOD[fr + i + ld * n];
                 }
                 gsync<W>();
@@ -1511,12 +1519,14 @@ __device__ __forceinline__ void apply_Q(const Ctx &c, const int ld, const int g,
         if (len == 1 || tau == 0.0) continue;
         const double *col = c.LOD + fr + ld * (fc + i);
         double acc        = 0.0;
+#pragma unroll 1
         for (int r = i + 1 + ((lane - (i + 1)) & 31); r < dim; r += 32) acc = fma(col[r], y[r], acc);
         acc             = bfly_sum(acc);
         const double yi = y[i];
         const double w  = tau * (acc + yi);
         __syncwarp();
         if (lane == 0) y[i] = yi - w;
+#pragma unroll 1
         for (int r = i + 1 + lane; r < dim; r += 32) y[r] = fma(-col[r], w, y[r]);
         __syncwarp();
     }
@@ -1531,6 +1541,7 @@ template <int W> __device__ void lse_get_v(const Ctx &c, const int n, const int 
         for (int g = 0; g < G; g++)
         {
             const int fr = c.frow[g], dim = c.ldim[g], rank = c.rank[g];
+#pragma unroll 1
             for (int i = lane; i < dim; i += 32) c.wsp[fr + i] = (i < rank) ? 0.0 : -c.LOD[fr + i + ld * n];
             __syncwarp();
             if (rank < dim) apply_Q(c, ld, g, c.wsp + fr, lane); // full row rank: Q * 0 = 0 exactly
@@ -1545,12 +1556,14 @@ __device__ __forceinline__ void dump_lod(const Ctx &c, double *const qbase, doub
                                          const int ld, const int nCtr, const int M)
 {
     double *dst = qbase + p * (unsigned long long)M * (n + 1);
+#pragma unroll 1
     for (int e = threadIdx.x; e < M * (n + 1); e += NT)
     {
         const int r = e % M, col = e / M;
         dst[e]      = (r < nCtr) ? c.LOD[r + ld * col] : 0.0;
     }
     if (hbase)
+#pragma unroll 1
         for (int k = threadIdx.x; k < M; k += NT) hbase[p * M + k] = (k < nCtr) ? c.hh[k] : 0.0;
 }
 template <int NT>
@@ -1749,7 +1762,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
 
         FlopCount fl;
         fl.f                = 0;
-        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, false, LG, REG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma, &pr,
+        const int totalRank = lse_factorize<W, LX_LSE_COMPACT_QR, LX_LSE_COMPACT_GS, LG, REG>(c, sm, n, ld, G, nCtr, sh.nfix, pr.tol_lindep, fl, pr.dmma, &pr,
                                                                                  bf.reg_scratch ? bf.reg_scratch + blockIdx.x * bf.reg_stride : nullptr);
         lse_solve<W, LG>(c, n, ld, G, sm.ldv);
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.lx[k];
@@ -2057,6 +2070,7 @@ template <int W, bool DS> __device__ __forceinline__ void obj_form_dv(const Ctx 
     for (int k = 0; k < sh.P; k++)
     {
         const int o = sh.uoff[k];
+#pragma unroll 1
         for (int i = tid; i < sh.dim[k]; i += NT)
         {
             const int t = c.alltype[o + i];
@@ -2090,16 +2104,20 @@ __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, co
         }
         nCtr += d;
     }
+#pragma unroll 1
     for (int k = tid; k < nCtr; k += NT) c.hh[k] = 0.0;
+#pragma unroll 1
     for (int k = nFixedPrev + tid; k < n; k += NT) c.lx[k] = 0.0;
     // rows are processed in aligned pairs: the partner of the last row must be a zero row, not a stale one
     if (nCtr & 1)
+#pragma unroll 1
         for (int col = tid; col <= n; col += NT) c.LOD[nCtr + ld * col] = 0.0;
     gsync<W>();
     nFixed = 0;
     if (sh.off)
     {
         nFixed = c.nact[0];
+#pragma unroll 1
         for (int a = tid; a < nFixed; a += NT)
         {
             const int i = c.active[a], t = c.atype[a];
@@ -2111,6 +2129,7 @@ __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, co
     for (int g = 0; g < sh.G; g++)
     {
         const int k = g + sh.off, o = sh.uoff[k], go = sh.goff[g], fr = c.frow[g], d = c.ldim[g];
+#pragma unroll 1
         for (int a = tid; a < d; a += NT)
         {
             const int i = c.active[o + a], t = c.atype[o + a];
@@ -2331,17 +2350,21 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 fence_proxy_async();
                 tma_load_record(c.obj, gobj, (unsigned)(bf.obj_stride * sizeof(double)), c.mbar);
             }
+#pragma unroll 1
             for (int i = tid; i < 2 * sh.m0; i += NT) c.sb[i] = gsb[i];
         }
+#pragma unroll 1
         for (int i = tid; i < sh.m0; i += NT) c.sbidx[i] = (unsigned short)bf.sbidx[p * bf.sbidx_stride + i];
         const bool have_x0 = bf.x0 != nullptr;
         const bool have_v0 = bf.v0 != nullptr;
+#pragma unroll 1
         for (int k = tid; k < n; k += NT)
         {
             c.x[k]  = have_x0 ? bf.x0[p * n + k] : 0.0;
             c.dx[k] = 0.0;
             c.lx[k] = 0.0;
         }
+#pragma unroll 1
         for (int i = tid; i < sh.Mall; i += NT)
         {
             c.v[i]       = have_v0 ? bf.v0[p * sh.Mall + i] : 0.0;
@@ -2351,6 +2374,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
         for (int k = 0; k < P; k++)
         {
             const int o = sh.uoff[k];
+#pragma unroll 1
             for (int i = tid; i < sh.dim[k]; i += NT) c.inactive[o + i] = (unsigned short)i;
             if (tid == 0)
             {
@@ -2373,6 +2397,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             for (int k = 0; k < P; k++)
             {
                 const int o = sh.uoff[k];
+#pragma unroll 1
                 for (int i = tid; i < sh.dim[k]; i += NT)
                 {
                     const double bl = ov.lb(k, i), bu = ov.ub(k, i);
@@ -2402,10 +2427,12 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             // The working sets of different levels do not interact: one warp per level replays its level's part of the
             // reference's sequence (all equalities in ascending order, then the guess).  A level of equalities only — the
             // usual case — ends with active = 0, 1, 2, ... and nothing inactive: filled in parallel.  Mixed levels replay.
+#pragma unroll 1
             for (int k = tid >> 5; k < P; k += W)
             {
                 const int o = sh.uoff[k], m = sh.dim[k];
                 bool alleq = true, anyeq = false, anyguess = false;
+#pragma unroll 1
                 for (int i = lane; i < m; i += 32)
                 {
                     const bool e = eqflag[o + i] != 0;
@@ -2419,6 +2446,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 anyguess = (__any_sync(0xffffffffu, anyguess) && bf.guess != nullptr) || bf.glist != nullptr;
                 if (alleq && m > 0)
                 {
+#pragma unroll 1
                     for (int i = lane; i < m; i += 32)
                     {
                         c.active[o + i]  = (unsigned short)i;
@@ -2462,6 +2490,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 __syncwarp();
             }
             gsync<W>();
+#pragma unroll 1
             for (int i = tid; i < sh.Mall; i += NT) c.dv[i] = 0.0;
             gsync<W>();
         }
@@ -2543,6 +2572,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
         if (!pr.phase1_v0 && !have_x0)
         {
             factor_and_solve();
+#pragma unroll 1
             for (int k = tid; k < n; k += NT) c.x[k] = c.lx[k];
             gsync<W>();
         }
@@ -2612,6 +2642,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                     if (k == 0 && sh.off && pr.mod_x)
                     {
                         // ensureZeroCtrViolationForSimpleBounds, objective.h:73-103; then every Ax is rebuilt from the new x
+#pragma unroll 1
                         for (int i = tid; i < sh.m0; i += NT)
                         {
                             const int t = c.alltype[i];
@@ -2634,6 +2665,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             for (int k = 0; k < P; k++)
             {
                 const int o = sh.uoff[k];
+#pragma unroll 1
                 for (int i = tid; i < sh.dim[k]; i += NT)
                 {
                     const int t     = c.alltype[o + i];
@@ -2667,6 +2699,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             if (have_x0)
             {
                 factor_and_solve();
+#pragma unroll 1
                 for (int k = tid; k < n; k += NT) c.dx[k] = c.lx[k] - c.x[k];
                 gsync<W>();
             }
@@ -2684,6 +2717,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             if (nIter != 0)
             {
                 factor_and_solve();
+#pragma unroll 1
                 for (int k = tid; k < n; k += NT) c.dx[k] = c.lx[k] - c.x[k];
                 gsync<W>();
                 obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
@@ -2702,6 +2736,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             for (int k = 0; k < P; k++)
             {
                 const int o = sh.uoff[k], ni = c.ninact[k];
+#pragma unroll 1
                 for (int q = lane; q < ni; q += 32)
                 {
                     const int i      = c.inactive[o + q];
@@ -2826,7 +2861,9 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             // step, lexlsi.h:1243-1250, objective.h:585-589
             if (alpha > 0)
             {
+#pragma unroll 1
                 for (int k = tid; k < n; k += NT) c.x[k] = fma(alpha, c.dx[k], c.x[k]);
+#pragma unroll 1
                 for (int i = tid; i < sh.Mall; i += NT)
                 {
                     c.v[i]  = fma(alpha, c.dv[i], c.v[i]);
@@ -2895,6 +2932,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             // get_lexqr() called after it return this problem's constraints and factorization (tests/test_numerical_error.cpp:83-86)
             lsi_factor_and_solve<W, DS, LG, REG>(sh, sm, pr.tol_lindep, c.LOD, ov.obj, ov.sb, nFixed, nFixedPrev, totalRank, fl, pr.dmma,
                                                  bf.lexdata + p * (unsigned long long)sh.M * (n + 1), REG ? &pr : nullptr, reg_scratch);
+#pragma unroll 1
             for (int k = tid; k < n; k += NT) bf.xstar[p * n + k] = c.lx[k];
             int nc = 0;
             for (int g = 0; g < G; g++) nc += c.ldim[g];
@@ -2904,6 +2942,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
         if (bf.lambda)
         {
             double *lam = bf.lambda + p * (unsigned long long)P * sh.Mall;
+#pragma unroll 1
             for (int e = tid; e < P * sh.Mall; e += NT) lam[e] = 0.0;
             // lexlsi.h:566-571: the working set changed after the last factorization (unless get_xStar just redid it)
             if (status != ST_SOLVED && !bf.xstar) factor_and_solve();
@@ -2918,10 +2957,12 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 gsync<W>();
                 // workspace = [Lambda of the fixed variables | Lambda of LexLSE rows 0 .. frow[j] + ldim[j])
                 double *col = lam + (unsigned long long)(sh.off + j) * sh.Mall;
+#pragma unroll 1
                 for (int a = tid; a < nFixed; a += NT) col[c.active[a]] = c.wsp[a];
                 for (int g = 0; g <= j; g++)
                 {
                     const int o = sh.uoff[g + sh.off], fr = c.frow[g];
+#pragma unroll 1
                     for (int a = tid; a < c.ldim[g]; a += NT) col[o + c.active[o + a]] = c.wsp[nFixed + fr + a];
                 }
                 gsync<W>();
@@ -2929,12 +2970,14 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
         }
 
         // ---- results ------------------------------------------------------------------------------------------
+#pragma unroll 1
         for (int k = tid; k < n; k += NT) bf.x[p * n + k] = c.x[k];
         unsigned nActive = 0;
         for (int k = 0; k < P; k++)
         {
             const int o = sh.uoff[k];
             nActive += c.nact[k];
+#pragma unroll 1
             for (int i = tid; i < sh.dim[k]; i += NT)
             {
                 const unsigned long long gi = p * sh.Mall + o + i;
@@ -2949,17 +2992,20 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 }
             }
         }
+#pragma unroll 1
         for (int g = tid; g < G; g += NT) bf.ranks[p * G + g] = c.rank[g];
         if constexpr (DS)
         {
             // relaxed bounds (cycling handling) belong to the solver-owned copy of the data, objective.h:774-788
             if (pr.cycling && cycCounter > 0)
             {
+#pragma unroll 1
                 for (int r = tid; r < sh.M; r += NT)
                 {
                     gobj[r + sh.ldo * n]       = c.obj[r + sh.ldo * n];
                     gobj[r + sh.ldo * (n + 1)] = c.obj[r + sh.ldo * (n + 1)];
                 }
+#pragma unroll 1
                 for (int i = tid; i < 2 * sh.m0; i += NT) gsb[i] = c.sb[i];
             }
         }

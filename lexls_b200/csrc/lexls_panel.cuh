@@ -27,6 +27,10 @@ namespace lexls_dev
 {
 
 #define LX_PANEL_MAXRH 20
+// experiment switch (profiles/r2_experiments.json): one column-slot count for every level (less code, idle slots)
+#ifndef LX_PANEL_ONE_S
+#define LX_PANEL_ONE_S 0
+#endif
 // Schur update of the warp-per-problem Gauss step on the FP64 tensor cores: measured SLOWER than the row-per-lane DFMA code
 // on C2 (3.40 -> 3.53 ms: 15 small tiles per level do not amortise the fragment loads), so it is compiled in on request only
 #ifndef LX_PANEL_DMMA
@@ -644,10 +648,13 @@ __device__ __forceinline__ bool qr_level_panel_dispatch(const PanelArgs &pa, con
     const int ncols = pa.n + 1 - ColIndex;
     const int S     = (ncols + 15) >> 4;
     if (dim < 1) return true; // empty level: rank 0
+    if (ColIndex >= pa.n) return true; // every variable is eliminated: rank 0, nothing moves (the level keeps its RHS column)
     if (S > 3 || dim > 40) return false;
 #define LX_QR(NGv)                                                                                                      \
     {                                                                                                                   \
-        if (S == 1)                                                                                                     \
+        if (LX_PANEL_ONE_S)                                                                                             \
+            ColIndex = qr_level_win<NGv, 3, COMPACT>(pa, fr, dim, ColIndex);                                            \
+        else if (S == 1)                                                                                                     \
             ColIndex = qr_level_win<NGv, 1, COMPACT>(pa, fr, dim, ColIndex);                                            \
         else if (S == 2)                                                                                                \
             ColIndex = qr_level_win<NGv, 2, COMPACT>(pa, fr, dim, ColIndex);                                            \
