@@ -317,10 +317,27 @@ __device__ __forceinline__ void tma_load_record(void *dst, const void *src, unsi
 // ---------------------------------------------------------------------------------------------------------------
 // flop accounting: the algorithmic count of BASELINE.md / SURVEY.md 8(d), evaluated with the ACTUAL dims and ranks
 // ---------------------------------------------------------------------------------------------------------------
+// algorithmic flop counter.  A double: every term is an integer far below 2^53, so the arithmetic is exact, and the
+// FP64 pipe is idle where the 64-bit integer multiplies of the closed forms were ~100 instructions per level.
 struct FlopCount
 {
-    unsigned long long f;
+    double f;
 };
+// flops of the column-pivoted QR of one level: m rows, cc open columns, rank r
+__device__ __forceinline__ double qr_level_flops(const int dim, const int ncols, const int rank)
+{
+    const int rpi  = (rank < dim) ? rank : dim - 1;
+    const double m = dim, cc = ncols, r = rank, rp = rpi;
+    const double R1 = r * (r - 1.0) * 0.5;
+    double f        = 2.0 * m * cc + 2.0 * (r * m - R1) + 2.0 * (r * (cc - 1.0) - R1);
+    if (rpi > 0)
+    {
+        const double T1 = rp * (rp - 1.0) * 0.5;
+        const double T2 = (double)((unsigned long long)((unsigned)(rpi - 1) * (unsigned)rpi) * (unsigned)(2 * rpi - 1) / 6ull);
+        f += 3.0 * (rp * m - T1) + 4.0 * rp + 4.0 * (rp * m * cc - (m + cc) * T1 + T2);
+    }
+    return f;
+}
 
 // aligned 2-double accesses (rows 2t, 2t+1 of one column): LDS.128 / STS.128 in shared memory
 __device__ __forceinline__ double2 ld2(const double *p)
@@ -1325,14 +1342,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
         const int rank = ColIndex - fc;
         sumRank += rank;
         if (tid == 0) c.rank[g] = rank;
-        {
-            // algorithmic flops of this level's QR in closed form
-            const long long m = dim, cc = n - fc, r = rank, rp = (r < m) ? r : m - 1;
-            const long long T1 = rp * (rp - 1) / 2, T2 = (rp - 1) * rp * (2 * rp - 1) / 6, R1 = r * (r - 1) / 2;
-            long long f = 2 * m * cc + 2 * (r * m - R1) + 2 * (r * (cc - 1) - R1);
-            if (rp > 0) f += 3 * (rp * m - T1) + 4 * rp + 4 * (rp * m * cc - (m + cc) * T1 + T2);
-            fl.f += (unsigned long long)f;
-        }
+        fl.f += qr_level_flops(dim, n - fc, rank);
 
         if constexpr (regon)
             {
@@ -1358,7 +1368,8 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
                 gauss_step_panel_dispatch<CG>(pa, fr, dim, fc, rank, ColIndex);
             else
                 gauss_step_smem<W, LGV>(c, n, ld, nCtr, fr, dim, fc, rank, ColIndex, smap.ldv, dmma);
-            fl.f += (unsigned long long)Rows * rank * rank + 2ull * Rows * rank * (n - ColIndex + 1);
+            const double rr = (double)Rows * (double)rank;
+            fl.f += rr * (double)rank + 2.0 * rr * (double)(n - ColIndex + 1);
         }
 
         if (ColIndex == n) // lexlse.h:475-490
@@ -1369,7 +1380,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
         }
     }
     gsync<W>();
-    fl.f += (unsigned long long)sumRank * sumRank;
+    fl.f += (double)sumRank * (double)sumRank;
     return nFixed + sumRank;
 }
 
@@ -1796,7 +1807,7 @@ __global__ void __launch_bounds__(32 * W, W == 1 ? 10 : (W == 8 ? 2 : (W == 4 ? 
             cnt[1] = cnt[2] = cnt[3] = cnt[4] = 0;
             cnt[5]                            = (unsigned)totalRank;
             cnt[6]                            = (unsigned)nCtr;
-            cnt[7]                            = (unsigned)((fl.f + 500) / 1000);
+            cnt[7]                            = (unsigned)(((unsigned long long)fl.f + 500ull) / 1000ull);
         }
         gsync<W>();
         p = *(unsigned long long *)c.scal;
@@ -1938,7 +1949,7 @@ __global__ void __launch_bounds__(32, 5) lse_pair_kernel(const __grid_constant__
         if (cl == 0)
         {
             ch.scal[4]                        = totalRank;
-            *(unsigned long long *)(ch.scal + 6) = fl.f;
+            *(unsigned long long *)(ch.scal + 6) = (unsigned long long)fl.f;
         }
         __syncwarp();
         (void)p;
@@ -2085,6 +2096,46 @@ template <int W, bool DS> __device__ __forceinline__ void obj_form_dv(const Ctx 
     }
 }
 
+// Real calls for what the LexLSI kernel needs at several places (inlined copies cost instruction-cache misses, see build.py):
+// the context is rebuilt from the shared-memory map; vectors that may live outside shared memory (SmemMap::vecg) are passed in.
+static __device__ __noinline__ void ws_activate_call(const Shape &sh, const SmemMap &sm, int k, int i, int type)
+{
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    const Ctx c = make_ctx(smem_ws, sm);
+    ws_activate(c, sh, k, i, type);
+}
+static __device__ __noinline__ void ws_deactivate_call(const Shape &sh, const SmemMap &sm, int k, int a)
+{
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    const Ctx c = make_ctx(smem_ws, sm);
+    ws_deactivate(c, sh, k, a);
+}
+template <int W, bool DS>
+__device__ __noinline__ void obj_multiply_call(const Shape &sh, const SmemMap &sm, double *objp, double *sbp, const unsigned vec_off, double *out)
+{
+    extern __shared__ __align__(128) unsigned char smem_om[];
+    const Ctx c = make_ctx(smem_om, sm);
+    const ObjView<DS> ov{c, sh, objp, sbp};
+    obj_multiply<W, DS>(c, sh, ov, (const double *)(smem_om + vec_off), out);
+}
+// Adx = A dx and dv (formStep, objective.h:288-338) of the current direction dx
+template <int W, bool DS>
+__device__ __noinline__ void lsi_direction(const Shape &sh, const SmemMap &sm, double *objp, double *sbp, double *v, double *dv, double *Ax,
+                                           double *Adx)
+{
+    extern __shared__ __align__(128) unsigned char smem_om[];
+    Ctx c = make_ctx(smem_om, sm);
+    c.v   = v;
+    c.dv  = dv;
+    c.Ax  = Ax;
+    c.Adx = Adx;
+    const ObjView<DS> ov{c, sh, objp, sbp};
+    obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
+    gsync<W>();
+    obj_form_dv<W, DS>(c, sh, ov);
+    gsync<W>();
+}
+
 // LexLSI::formLexLSE + Objective::formLexLSE, lexlsi.h:968-982, objective.h:434-494; returns nCtr, sets nFixed
 template <int W, bool DS>
 __device__ __forceinline__ int lsi_form_lexlse(const Ctx &c, const Shape &sh, const ObjView<DS> &ov, int &nFixed, const int nFixedPrev)
@@ -2179,20 +2230,80 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
     best.v   = 0.0;        // maxAbsValue starts at 0 (lexlse.h:618); candidates are strictly below -tol_wrong
     best.pos = 0x7fffffff; // scan position: (group order << 16) | k
 
-    auto sign_test = [&](int order, int first, int dim, const double *lam, unsigned char *types) {
-        // findDescentDirection, lexlse.h:935-987
-        for (int k = lane; k < dim; k += 32)
+    // One loop over the groups in scan order — objective j (order 0), the objectives above it (order j - k), the fixed
+    // variables (order j + 1, "k = -1") — so that the Householder sequence, the transposed product and the sign test exist
+    // ONCE in the code (the kernel is bound by instruction fetch); the two products of a group are independent of its sign test.
+    for (int k = j; k >= -1; k--)
+    {
+        int first, dim;
+        const double *lam;
+        unsigned char *types;
+        if (k >= 0)
         {
-            const int t = types[first + k];
+            const int fr = c.frow[k], fc = c.fcol[k], rank = c.rank[k];
+            dim = c.ldim[k];
+            if (k == j) // residual of objective j below its rank: Lambda_j = Q [0; -b2], lexlse.h:640-648
+            {
+#pragma unroll 1
+                for (int i = rank + lane; i < dim; i += 32) Lambda[fr + i] = -c.LOD[fr + i + ld * n];
+            }
+            else
+            {
+#pragma unroll 1
+                for (int i = lane; i < rank; i += 32) Lambda[fr + i] = rhs[fc + i];
+            }
+            __syncwarp();
+            apply_Q(c, ld, k, Lambda + fr, lane);
+            if (j > 0)
+            {
+                // rhs[0:fc] -= LOD(fr.., 0:fc)^T * Lambda[fr..]   (S) per column
+#pragma unroll 1
+                for (int col = lane; col < fc; col += 32)
+                {
+                    const double *colp = c.LOD + ld * col + fr;
+                    double acc         = rhs[col];
+#pragma unroll 4
+                    for (int i = 0; i < dim; i++) acc = fma(-colp[i], Lambda[fr + i], acc);
+                    rhs[col] = acc;
+                }
+            }
+            first = fr;
+            lam   = Lambda;
+            types = c.ctype;
+        }
+        else
+        {
+            if (nFixed <= 0) break;
+#pragma unroll 1
+            for (int f = lane; f < nFixed; f += 32)
+            {
+                const double *colp = c.LOD + ld * f;
+                double acc         = 0.0;
+#pragma unroll 4
+                for (int i = 0; i < nLambda; i++) acc = fma(colp[i], Lambda[i], acc);
+                LambdaFixed[f] = -acc;
+            }
+            __syncwarp();
+            first = 0;
+            dim   = nFixed;
+            lam   = LambdaFixed;
+            types = c.ftype;
+        }
+        // findDescentDirection, lexlse.h:935-987
+        const int order = j - k;
+#pragma unroll 1
+        for (int q = lane; q < dim; q += 32)
+        {
+            const int t = types[first + q];
             if (t != CTR_ACTIVE_EQ && t != CORRECT_SIGN_OF_LAMBDA)
             {
-                double a = lam[first + k];
+                double a = lam[first + q];
                 if (t == CTR_ACTIVE_LB) a = -a;
                 if (a > tol_correct)
-                    types[first + k] = CORRECT_SIGN_OF_LAMBDA;
+                    types[first + q] = CORRECT_SIGN_OF_LAMBDA;
                 else if (a < -tol_wrong)
                 {
-                    const int pos = (order << 16) | k;
+                    const int pos = (order << 16) | q;
                     if (a < best.v || (a == best.v && pos < best.pos))
                     {
                         best.v   = a;
@@ -2201,51 +2312,7 @@ __device__ __forceinline__ bool lse_sensitivity(const Ctx &c, const int n, const
                 }
             }
         }
-    };
-    auto sub_transpose = [&](int ColDim, int fr, int dim) {
-        // rhs[0:ColDim] -= LOD(fr.., 0:ColDim)^T * Lambda[fr..]   (S) per column
-        for (int col = lane; col < ColDim; col += 32)
-        {
-            const double *colp = c.LOD + ld * col + fr;
-            double acc         = rhs[col];
-            for (int i = 0; i < dim; i++) acc = fma(-colp[i], Lambda[fr + i], acc);
-            rhs[col] = acc;
-        }
-    };
-
-    {
-        const int fr = c.frow[j], dim = c.ldim[j], rank = c.rank[j];
-        for (int i = rank + lane; i < dim; i += 32) Lambda[fr + i] = -c.LOD[fr + i + ld * n];
         __syncwarp();
-        apply_Q(c, ld, j, Lambda + fr, lane);
-        sign_test(0, fr, dim, Lambda, c.ctype);
-        if (j > 0)
-        {
-            sub_transpose(c.fcol[j], fr, dim);
-            __syncwarp();
-        }
-    }
-    for (int k = j; k--;)
-    {
-        const int fr = c.frow[k], fc = c.fcol[k], dim = c.ldim[k], rank = c.rank[k];
-        for (int i = lane; i < rank; i += 32) Lambda[fr + i] = rhs[fc + i];
-        __syncwarp();
-        apply_Q(c, ld, k, Lambda + fr, lane);
-        sub_transpose(fc, fr, dim);
-        sign_test(j - k, fr, dim, Lambda, c.ctype);
-        __syncwarp();
-    }
-    if (nFixed > 0)
-    {
-        for (int f = lane; f < nFixed; f += 32)
-        {
-            const double *colp = c.LOD + ld * f;
-            double acc         = 0.0;
-            for (int i = 0; i < nLambda; i++) acc = fma(colp[i], Lambda[i], acc);
-            LambdaFixed[f] = -acc;
-        }
-        __syncwarp();
-        sign_test(j + 1, 0, nFixed, LambdaFixed, c.ftype);
     }
     best = bfly_argmin(best);
     __syncwarp();
@@ -2463,7 +2530,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 {
                     if (anyeq)
                         for (int i = 0; i < m; i++)
-                            if (eqflag[o + i]) ws_activate(c, sh, k, i, CTR_ACTIVE_EQ);
+                            if (eqflag[o + i]) ws_activate_call(sh, sm, k, i, CTR_ACTIVE_EQ);
                     if (bf.glist)
                     {
                         // api_activate in the caller's CALL order (lexlsi.h:120-136 -> workingset.h:67-77): the order fixes
@@ -2476,7 +2543,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                             if (w == 0xFFFFFFFFu) break;
                             const int ko = (int)(w >> 24), t = (int)((w >> 16) & 0xffu), i = (int)(w & 0xffffu);
                             if (ko == k && i < m && (t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[o + i] == CTR_INACTIVE)
-                                ws_activate(c, sh, k, i, t);
+                                ws_activate_call(sh, sm, k, i, t);
                         }
                     }
                     else if (anyguess)
@@ -2484,7 +2551,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                         {
                             const int t = gs[o + i];
                             if ((t == CTR_ACTIVE_LB || t == CTR_ACTIVE_UB) && c.alltype[o + i] == CTR_INACTIVE)
-                                ws_activate(c, sh, k, i, t); // api_activate, lexlsi.h:120-136 (level-major, row ascending)
+                                ws_activate_call(sh, sm, k, i, t); // api_activate, lexlsi.h:120-136 (level-major, row ascending)
                         }
                 }
                 __syncwarp();
@@ -2577,7 +2644,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             gsync<W>();
         }
         // Objective::phase1 for every level, objective.h:353-374
-        obj_multiply<W, DS>(c, sh, ov, c.x, c.Ax);
+        obj_multiply_call<W, DS>(sh, sm, ov.obj, ov.sb, sm.x, c.Ax);
         gsync<W>();
         if (!have_v0)
         {
@@ -2597,12 +2664,12 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                             {
                                 if (ax <= ov.lb(k, i))
                                 {
-                                    ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                    ws_activate_call(sh, sm, k, i, CTR_ACTIVE_LB);
                                     track_add(k, i);
                                 }
                                 else if (ax >= ov.ub(k, i))
                                 {
-                                    ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                    ws_activate_call(sh, sm, k, i, CTR_ACTIVE_UB);
                                     track_add(k, i);
                                 }
                             }
@@ -2612,11 +2679,11 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                                 {
                                     int a = 0;
                                     while (c.active[o + a] != i) a++;
-                                    ws_deactivate(c, sh, k, a);
+                                    ws_deactivate_call(sh, sm, k, a);
                                     track_del(k, i);
                                     if (ax >= ov.ub(k, i))
                                     {
-                                        ws_activate(c, sh, k, i, CTR_ACTIVE_UB);
+                                        ws_activate_call(sh, sm, k, i, CTR_ACTIVE_UB);
                                         track_add(k, i);
                                     }
                                 }
@@ -2627,11 +2694,11 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                                 {
                                     int a = 0;
                                     while (c.active[o + a] != i) a++;
-                                    ws_deactivate(c, sh, k, a);
+                                    ws_deactivate_call(sh, sm, k, a);
                                     track_del(k, i);
                                     if (ax <= ov.lb(k, i))
                                     {
-                                        ws_activate(c, sh, k, i, CTR_ACTIVE_LB);
+                                        ws_activate_call(sh, sm, k, i, CTR_ACTIVE_LB);
                                         track_add(k, i);
                                     }
                                 }
@@ -2656,7 +2723,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                             c.x[c.sbidx[i]] = val;
                         }
                         gsync<W>();
-                        obj_multiply<W, DS>(c, sh, ov, c.x, c.Ax);
+                        obj_multiply_call<W, DS>(sh, sm, ov.obj, ov.sb, sm.x, c.Ax);
                         gsync<W>();
                     }
                 }
@@ -2705,10 +2772,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             }
             nFact++;
         }
-        obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
-        gsync<W>();
-        obj_form_dv<W, DS>(c, sh, ov);
-        gsync<W>();
+        lsi_direction<W, DS>(sh, sm, ov.obj, ov.sb, c.v, c.dv, c.Ax, c.Adx);
 
         // ---- active-set loop, lexlsi.h:223-244; body = verifyWorkingSet :1144-1265 ------------------------------
         for (;;)
@@ -2720,10 +2784,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
 #pragma unroll 1
                 for (int k = tid; k < n; k += NT) c.dx[k] = c.lx[k] - c.x[k];
                 gsync<W>();
-                obj_multiply<W, DS>(c, sh, ov, c.dx, c.Adx);
-                gsync<W>();
-                obj_form_dv<W, DS>(c, sh, ov);
-                gsync<W>();
+                lsi_direction<W, DS>(sh, sm, ov.obj, ov.sb, c.v, c.dv, c.Ax, c.Adx);
                 nFact++;
             }
             else if (pr.phase1_v0)
@@ -2783,7 +2844,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 gsync<W>();
                 if (tid == 0)
                 {
-                    ws_activate(c, sh, idObj, idCtr, idType);
+                    ws_activate_call(sh, sm, idObj, idCtr, idType);
                     track_add(idObj, idCtr);
                 }
                 log_entry(idObj, idCtr, idType, alpha);
@@ -2848,7 +2909,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                     gsync<W>();
                     if (tid == 0)
                     {
-                        ws_deactivate(c, sh, idObj, c.scal[3]);
+                        ws_deactivate_call(sh, sm, idObj, c.scal[3]);
                         track_del(idObj, idCtr);
                     }
                     nDeact++;
@@ -3021,7 +3082,7 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
             cnt[4]        = cycCounter;
             cnt[5]        = (unsigned)totalRank;
             cnt[6]        = nActive;
-            cnt[7]        = (unsigned)((fl.f + 500) / 1000);
+            cnt[7]        = (unsigned)(((unsigned long long)fl.f + 500ull) / 1000ull);
         }
         gsync<W>();
     }
