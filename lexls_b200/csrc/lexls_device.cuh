@@ -659,36 +659,8 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const bool apply  = tau != 0.0;
             const double *vp  = c.vv + 2 * pb;
             const int np      = pe - pb;
-            if constexpr (LGV || W >= 4)
-            {
-                // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
-                const int par = tid & 1;
-                for (int jb = ColIndex + 1 + ((tid & ~31) >> 1); jb <= n; jb += NT / 2) // warp-uniform trip count
-                {
-                    const int j      = jb + (lane >> 1);
-                    const bool valid = j <= n;
-                    double *cp       = P(valid ? j : n, pb) + par;
-                    const double *vq = vp + par;
-                    double acc       = 0.0;
-                    if (apply && valid)
-                    {
-#pragma unroll 4
-                        for (int q = 0; q < np; q++) acc = fma(vq[2 * q], cp[2 * q], acc);
-                    }
-                    const double w = tau * (acc + __shfl_xor_sync(0xffffffffu, acc, 1));
-                    if (apply && valid)
-                    {
-#pragma unroll 4
-                        for (int q = 0; q < np; q++) cp[2 * q] = fma(-vq[2 * q], w, cp[2 * q]);
-                    }
-                    if (valid && j < n && par == (row & 1))
-                    {
-                        const double a0 = *E(j, row);
-                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
-                    }
-                }
-            }
-            else
+            // one thread per column: both parity chains of (S2) in one thread
+            auto apply_thread_per_column = [&]() {
             for (int j = ColIndex + 1 + tid; j <= n; j += NT)
             {
                 double *cp = P(j, pb);
@@ -719,6 +691,45 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                     c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
                 }
             }
+            };
+            if constexpr (LGV || W >= 4)
+            {
+                // more open columns than thread pairs: one pass with one thread per column instead of two passes with two
+                // (same sums: the pair adds its two chains, the single thread adds the same two chains)
+                if (n - ColIndex > NT / 2)
+                    apply_thread_per_column();
+                else
+            {
+                // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
+                const int par = tid & 1;
+                for (int jb = ColIndex + 1 + ((tid & ~31) >> 1); jb <= n; jb += NT / 2) // warp-uniform trip count
+                {
+                    const int j      = jb + (lane >> 1);
+                    const bool valid = j <= n;
+                    double *cp       = P(valid ? j : n, pb) + par;
+                    const double *vq = vp + par;
+                    double acc       = 0.0;
+                    if (apply && valid)
+                    {
+#pragma unroll 4
+                        for (int q = 0; q < np; q++) acc = fma(vq[2 * q], cp[2 * q], acc);
+                    }
+                    const double w = tau * (acc + __shfl_xor_sync(0xffffffffu, acc, 1));
+                    if (apply && valid)
+                    {
+#pragma unroll 4
+                        for (int q = 0; q < np; q++) cp[2 * q] = fma(-vq[2 * q], w, cp[2 * q]);
+                    }
+                    if (valid && j < n && par == (row & 1))
+                    {
+                        const double a0 = *E(j, row);
+                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
+                    }
+                }
+            }
+            }
+            else
+                apply_thread_per_column();
         }
         ColIndex++;
         gsync<W>();
