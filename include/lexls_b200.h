@@ -183,6 +183,12 @@ int lexls_b200_validate(lexls_b200_batch_t *h);
  * the next synchronising call (synchronize, solve_batch_sync, get_*).  For pinned host buffers this removes every host
  * wait between the set_* calls of a batch (lexls_b200.PipelinedBatch uses it). */
 int lexls_b200_set_async_copies(lexls_b200_batch_t *h, int enabled);
+/* Asynchronous-copies mode also DEFERS the device-side repack of every host input to the next call that needs the device
+ * records (solve_batch, validate, synchronize, a result read, a *_dev setter): the inputs of a round cross the host link back
+ * to back, each into its own slice of a staging arena (extra device memory: one round of inputs).  wait_copies returns when
+ * every copy enqueued so far has left the caller's buffers — the point at which a pipelined caller hands the link to the next
+ * handle — without waiting for repacks or solves. */
+int lexls_b200_wait_copies(lexls_b200_batch_t *h);
 
 /* ---- results (host destinations; each call synchronises the handle's stream) -----------------------------------
  * get_x: get_x lexlse.h:1587 / lexlsi.h:508 -> [batch][nVar]

@@ -69,6 +69,12 @@ class _Batch:
         check(lib().lexls_b200_validate(self._h))
         self._release()
 
+    def wait_copies(self):
+        """async copies: returns when every enqueued host->device copy has left the caller's arrays (the device-side repacks
+        are deferred to the next solve / read); the point at which a pipelined caller hands the host link to the next handle."""
+        check(lib().lexls_b200_wait_copies(self._h))
+        self._release()
+
     def check_guard_bands(self):
         """LEXLS_B200_CANARY=1: number of device buffers whose trailing guard band was written into (0 = clean)."""
         v = C.c_uint32()

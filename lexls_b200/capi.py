@@ -20,7 +20,7 @@ SYMBOLS = [
     "lexls_b200_get_lambda", "lexls_b200_get_working_set_log", "lexls_b200_validate", "lexls_b200_create_batch_multi",
     "lexls_b200_shard_count", "lexls_b200_get_shard", "lexls_b200_get_xstar", "lexls_b200_set_active_guess_ordered",
     "lexls_b200_check_guard_bands", "lexls_b200_set_regularization_factor",
-    "lexls_b200_get_x_least_norm", "lexls_b200_set_async_copies",
+    "lexls_b200_get_x_least_norm", "lexls_b200_set_async_copies", "lexls_b200_wait_copies",
 ]
 OUT_LEXQR, OUT_LAMBDA, OUT_XSTAR, OUT_LEAST_NORM = 1, 2, 4, 8
 

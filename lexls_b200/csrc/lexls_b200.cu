@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -103,9 +104,15 @@ struct lexls_b200_batch
     unsigned long long *queue = nullptr;
     uint64_t lod_stride = 0;
     size_t lod_bytes = 0;
-    // staging for host inputs
+    // staging for host inputs.  Default: one slot, every set_* call copies into it, waits for the copy and launches its repack
+    // kernel.  With lexls_b200_set_async_copies the slot becomes an ARENA: every call takes its own slice, the copy is enqueued
+    // and the repack launch is DEFERRED (pending) to the next call that needs the device records (solve, validate, a result
+    // read, a *_dev setter ...).  A round of host inputs then crosses the link back to back — in stream order a copy would
+    // otherwise wait for the repack kernel of the previous level, and that kernel for SM slots beside another handle's
+    // persistent solve (the pipelined end-to-end path) — and the caller can wait for the copies alone (lexls_b200_wait_copies).
     void *stage = nullptr;
-    size_t stage_bytes = 0;
+    size_t stage_bytes = 0, stage_cursor = 0, round_bytes = 0, round_peak = 0;
+    std::vector<std::function<int()>> pending;
 };
 
 
@@ -148,6 +155,54 @@ static int ensure_stage(lexls_b200_batch *h, size_t bytes)
     h->stage_bytes = 0;
     CK(guarded_malloc(h, (void **)&h->stage, bytes));
     h->stage_bytes = bytes;
+    return 0;
+}
+
+// enqueue the deferred repack launches (stream order: after the copies they read)
+static int flush_pending(lexls_b200_batch *h)
+{
+    if (h->pending.empty()) return 0;
+    std::vector<std::function<int()>> todo;
+    todo.swap(h->pending);
+    int rc = 0;
+    for (auto &f : todo)
+        if (!rc) rc = f();
+    return rc;
+}
+// launch now, or with the next flush (asynchronous-copies mode)
+static int run_or_defer(lexls_b200_batch *h, std::function<int()> launch)
+{
+    if (!h->async_copies) return launch();
+    h->pending.push_back(std::move(launch));
+    return 0;
+}
+// staging memory for one host input: the single slot, or a fresh slice of the arena
+static int stage_take(lexls_b200_batch *h, size_t bytes, void **p)
+{
+    if (!h->async_copies)
+    {
+        if (int rc = ensure_stage(h, bytes)) return rc;
+        *p = h->stage;
+        return 0;
+    }
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (h->stage_cursor + bytes > h->stage_bytes)
+    {
+        // wrap: the repacks that read the arena are enqueued first, so the copies that follow are ordered behind them by the
+        // stream; the arena grows towards one full round of inputs (a few warm-up rounds), after which nothing wraps
+        if (int rc = flush_pending(h)) return rc;
+        if (getenv("LEXLS_B200_DEBUG_STAGE"))
+            fprintf(stderr, "[stage %p] wrap: cursor %zu + %zu > %zu (round %zu)\n", (void *)h, h->stage_cursor, bytes, h->stage_bytes, h->round_bytes);
+        h->stage_cursor = 0;
+        // what this round has taken so far, or what the largest finished round took: with 1/8 of headroom the arena holds a
+        // full round after the second one and never wraps again (a reallocation synchronises the whole device)
+        const size_t want = std::max(h->round_bytes + bytes, h->round_peak);
+        if (want > h->stage_bytes)
+            if (int rc = ensure_stage(h, want + want / 8 + (1u << 20))) return rc;
+    }
+    *p = (char *)h->stage + h->stage_cursor;
+    h->stage_cursor += bytes;
+    h->round_bytes += bytes;
     return 0;
 }
 
@@ -800,6 +855,7 @@ int lexls_b200_reset(lexls_b200_batch_t *h)
     MULTI(h, false, lexls_b200_reset(s.h));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
     h->have_x0    = false;
     h->have_guess = false;
     h->have_glist = false;
@@ -840,6 +896,7 @@ int lexls_b200_set_stream(lexls_b200_batch_t *h, void *cuda_stream)
     cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     if (next != h->stream)
     {
+        if (int rc = flush_pending(h)) return rc; // deferred repacks belong behind their copies, on the old stream
         // work already enqueued for this handle (the zero fill of create_batch, earlier set_* calls or solves) must be ordered
         // before whatever the caller enqueues on the new stream
         CK(cudaSetDevice(h->device));
@@ -906,21 +963,26 @@ static int set_data_impl(lexls_b200_batch *h, uint32_t level, const double *data
     if (!on_device)
     {
         const size_t bytes = sizeof(double) * (stride * (h->batch - 1) + (uint64_t)ld * (cols - 1) + m);
-        if (int rc = ensure_stage(h, bytes)) return rc;
-        CK(cudaMemcpyAsync(h->stage, data, bytes, cudaMemcpyHostToDevice, h->stream));
+        void *slot = nullptr;
+        if (int rc = stage_take(h, bytes, &slot)) return rc;
+        CK(cudaMemcpyAsync(slot, data, bytes, cudaMemcpyHostToDevice, h->stream));
         if (int rc = wait_copy(h)) return rc;
-        src = (const double *)h->stage;
+        src = (const double *)slot;
     }
-    const unsigned long long work = (unsigned long long)m * cols * h->batch;
-    if (lsi)
-        repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->obj, h->obj_stride, s.ldo, s.goff[g], src, stride, (int)ld, m,
-                                                                     cols, h->batch, s.n, s.n + 1, h->flag);
-    else
-        repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->rec, h->rec_stride, s.ld, s.goff[g], src, stride, (int)ld, m,
-                                                                     cols, h->batch, -1, -1, h->flag);
-    CK(cudaGetLastError());
+    else if (int rc = flush_pending(h))
+        return rc;
     h->data_set[level] = 1; // lb > ub is reported by lexls_b200_validate / after the solve (see flag_error)
-    return 0;
+    const unsigned long long work = (unsigned long long)m * cols * h->batch;
+    return run_or_defer(h, [=]() -> int {
+        if (lsi)
+            repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->obj, h->obj_stride, h->sh.ldo, h->sh.goff[g], src, stride,
+                                                                         (int)ld, m, cols, h->batch, h->sh.n, h->sh.n + 1, h->flag);
+        else
+            repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->rec, h->rec_stride, h->sh.ld, h->sh.goff[g], src, stride,
+                                                                         (int)ld, m, cols, h->batch, -1, -1, h->flag);
+        CK(cudaGetLastError());
+        return 0;
+    });
 }
 
 int lexls_b200_set_data(lexls_b200_batch_t *h, uint32_t level, const double *data, uint32_t ld, uint64_t problem_stride)
@@ -956,33 +1018,34 @@ static int set_sb_impl(lexls_b200_batch *h, const unsigned *var_index, uint64_t 
     {
         const size_t dbytes = sizeof(double) * (stride * (h->batch - 1) + (uint64_t)ld + m);
         const size_t ibytes = sizeof(unsigned) * nidx;
-        if (int rc = ensure_stage(h, dbytes + ibytes + 16)) return rc;
-        CK(cudaMemcpyAsync(h->stage, lbub, dbytes, cudaMemcpyHostToDevice, h->stream));
-        char *ip = (char *)h->stage + ((dbytes + 15) & ~(size_t)15);
+        void *slot = nullptr;
+        if (int rc = stage_take(h, dbytes + ibytes + 16, &slot)) return rc;
+        CK(cudaMemcpyAsync(slot, lbub, dbytes, cudaMemcpyHostToDevice, h->stream));
+        char *ip = (char *)slot + ((dbytes + 15) & ~(size_t)15);
         CK(cudaMemcpyAsync(ip, var_index, ibytes, cudaMemcpyHostToDevice, h->stream));
         if (int rc = wait_copy(h)) return rc;
-        src  = (const double *)h->stage;
+        src  = (const double *)slot;
         isrc = (const unsigned *)ip;
     }
-    repack_level_kernel<<<blocks_for((unsigned long long)m * 2 * h->batch), 256, 0, h->stream>>>(h->sb, 2ull * m, m, 0, src, stride, (int)ld,
-                                                                                                 m, 2, h->batch, 0, 1, h->flag, 8);
-    CK(cudaGetLastError());
-    if (index_stride)
-    {
-        CK(cudaMemcpy2DAsync(h->sbidx, sizeof(unsigned) * m, isrc, sizeof(unsigned) * index_stride, sizeof(unsigned) * m, h->batch,
-                             cudaMemcpyDeviceToDevice, h->stream));
-        h->sbidx_stride = m;
-    }
-    else
-    {
-        CK(cudaMemcpyAsync(h->sbidx, isrc, sizeof(unsigned) * m, cudaMemcpyDeviceToDevice, h->stream));
-        h->sbidx_stride = 0;
-    }
-    const unsigned long long cnt = index_stride ? h->batch : 1;
-    check_unique_kernel<<<blocks_for(cnt), 256, 0, h->stream>>>(h->sbidx, h->sbidx_stride, m, (unsigned)s.n, cnt, h->flag);
-    CK(cudaGetLastError());
-    h->data_set[0] = 1; // lb > ub / duplicate indices are reported by lexls_b200_validate / after the solve (see flag_error)
-    return 0;
+    else if (int rc = flush_pending(h))
+        return rc;
+    h->sbidx_stride = index_stride ? m : 0;
+    h->data_set[0]  = 1; // lb > ub / duplicate indices are reported by lexls_b200_validate / after the solve (see flag_error)
+    const unsigned nvar = (unsigned)s.n;
+    return run_or_defer(h, [=]() -> int {
+        repack_level_kernel<<<blocks_for((unsigned long long)m * 2 * h->batch), 256, 0, h->stream>>>(h->sb, 2ull * m, m, 0, src, stride,
+                                                                                                     (int)ld, m, 2, h->batch, 0, 1, h->flag, 8);
+        CK(cudaGetLastError());
+        if (index_stride)
+            CK(cudaMemcpy2DAsync(h->sbidx, sizeof(unsigned) * m, isrc, sizeof(unsigned) * index_stride, sizeof(unsigned) * m, h->batch,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+        else
+            CK(cudaMemcpyAsync(h->sbidx, isrc, sizeof(unsigned) * m, cudaMemcpyDeviceToDevice, h->stream));
+        const unsigned long long cnt = index_stride ? h->batch : 1;
+        check_unique_kernel<<<blocks_for(cnt), 256, 0, h->stream>>>(h->sbidx, h->sbidx_stride, m, nvar, cnt, h->flag);
+        CK(cudaGetLastError());
+        return 0;
+    });
 }
 int lexls_b200_set_simple_bounds(lexls_b200_batch_t *h, const uint32_t *var_index, uint64_t index_stride, const double *lbub,
                                  uint32_t ld, uint64_t problem_stride)
@@ -1065,15 +1128,21 @@ static int scatter_level(lexls_b200_batch *h, T **dstbuf, uint32_t level, const 
     if (!on_device)
     {
         const size_t bytes = sizeof(T) * m * h->batch;
-        if (int rc = ensure_stage(h, bytes)) return rc;
-        CK(cudaMemcpyAsync(h->stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
-        dsrc = (const T *)h->stage;
+        void *slot = nullptr;
+        if (int rc = stage_take(h, bytes, &slot)) return rc;
+        CK(cudaMemcpyAsync(slot, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = wait_copy(h)) return rc; // no-op in asynchronous-copies mode
+        dsrc = (const T *)slot;
     }
-    scatter_level_kernel<T><<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>(*dstbuf, dsrc, s.Mall, s.uoff[level], m,
-                                                                                                 h->batch);
-    CK(cudaGetLastError());
-    if (!on_device) CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    else if (int rc = flush_pending(h))
+        return rc;
+    T *const dst = *dstbuf;
+    const int Mall = s.Mall, uoff = s.uoff[level];
+    return run_or_defer(h, [=]() -> int {
+        scatter_level_kernel<T><<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>(dst, dsrc, Mall, uoff, m, h->batch);
+        CK(cudaGetLastError());
+        return 0;
+    });
 }
 
 extern "C" {
@@ -1159,6 +1228,10 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     const Shape &s = h->sh;
     for (int k = 0; k < s.P; k++)
         if (!h->data_set[k] && s.dim[k] > 0) return fail(LEXLS_B200_EINVAL, "setData has not been called for every objective");
+    if (int rc = flush_pending(h)) return rc; // the deferred repacks of this round (asynchronous-copies mode)
+    h->stage_cursor = 0;                      // the next round's copies are ordered behind them by the stream
+    h->round_peak   = std::max(h->round_peak, h->round_bytes);
+    h->round_bytes  = 0;
     if (int rc = plan(h)) return rc;
 
     // hot_start_related_tests, lexlsi.h:758-793: v0 is honoured only if given for ALL levels AND x0 is given
@@ -1303,14 +1376,25 @@ int lexls_b200_synchronize(lexls_b200_batch_t *h)
     MULTI(h, false, lexls_b200_synchronize(s.h));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return check_pending_flag(h);
+}
+int lexls_b200_wait_copies(lexls_b200_batch_t *h)
+{
+    MULTI(h, false, lexls_b200_wait_copies(s.h));
+    if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev_copy, h->stream)); // the deferred repacks are not enqueued yet: this is the end of the copies
+    CK(cudaEventSynchronize(h->ev_copy));
+    return 0;
 }
 int lexls_b200_validate(lexls_b200_batch_t *h)
 {
     MULTI(h, false, lexls_b200_validate(s.h));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
     CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1328,6 +1412,7 @@ int lexls_b200_solve_batch_sync(lexls_b200_batch_t *h)
 static int d2h(lexls_b200_batch *h, void *dst, const void *src, size_t bytes)
 {
     CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return check_pending_flag(h);
@@ -1353,6 +1438,7 @@ template <typename T> static int get_level(lexls_b200_batch *h, uint32_t level, 
     if (m == 0) return 0;
     CK(cudaSetDevice(h->device));
     const size_t bytes = sizeof(T) * m * h->batch;
+    if (int rc = flush_pending(h)) return rc; // the slot is also the arena of the deferred host inputs
     if (int rc = ensure_stage(h, bytes)) return rc;
     slice_level_kernel<T><<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>((T *)h->stage, src, width, off, m, h->batch);
     CK(cudaGetLastError());
@@ -1461,6 +1547,7 @@ int lexls_b200_get_lambda(lexls_b200_batch_t *h, uint32_t level, double *lambda)
     CK(cudaSetDevice(h->device));
     const unsigned long long cols = (unsigned long long)h->batch * s.P; // one slice per (problem, objective column)
     const size_t bytes            = sizeof(double) * m * cols;
+    if (int rc = flush_pending(h)) return rc; // the slot is also the arena of the deferred host inputs
     if (int rc = ensure_stage(h, bytes)) return rc;
     slice_level_kernel<double><<<blocks_for((unsigned long long)m * cols), 256, 0, h->stream>>>((double *)h->stage, h->lambda, s.Mall,
                                                                                                s.uoff[level], m, cols);
@@ -1493,6 +1580,8 @@ int lexls_b200_device_results(lexls_b200_batch_t *h, const double **x, const int
 {
     MULTI_REFUSE(h, "device_results");
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
     if (x) *x = h->x;
     if (status) *status = h->status;
     if (counters) *counters = h->counters;
@@ -1614,6 +1703,11 @@ int lexls_b200_set_async_copies(lexls_b200_batch_t *h, int enabled)
 {
     MULTI(h, false, lexls_b200_set_async_copies(s.h, enabled));
     if (!h) return fail(LEXLS_B200_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    if (int rc = flush_pending(h)) return rc;
+    if (h->async_copies && !enabled) CK(cudaStreamSynchronize(h->stream)); // back to one slot: nothing may still read the arena
+    h->stage_cursor = 0;
+    h->round_bytes  = 0;
     h->async_copies = enabled != 0;
     return 0;
 }

@@ -7,6 +7,8 @@ Two ways to use several GPUs:
   * one process per GPU (torchrun): every rank solves ``shard_range(batch, world, rank)`` with a plain
     LexLSEBatch / LexLSIBatch and calls :func:`gather_to_rank0` on the result arrays.
 """
+import os
+
 import numpy as np
 
 
@@ -174,7 +176,8 @@ class PipelinedBatch:
                         s.set_active_guess(k, g[lo:hi])
                 if x0 is not None:
                     s.set_x0(x0[lo:hi])
-                s.validate()  # the one wait of this chunk: its copies are done before the next chunk gets the link
+                (s.validate if os.environ.get("LEXLS_B200_PIPE_WAIT") == "validate" else s.wait_copies)()  # the one wait of this chunk: its copies are done before the next chunk gets the link (the
+                #                  repacks are deferred to the solve below; bad inputs surface with get_x)
             s.solve(sync=False)
             s.get_x(out=x_out[lo:hi])
 

@@ -240,6 +240,70 @@ def test_sharded_batch_python(oracle, ndev):
     assert np.array_equal(x, ref["x"]) and np.array_equal(ranks, ref["ranks"])
 
 
+# ---- asynchronous copies: staging arena + deferred repacks ------------------------------------------------------------
+@pytest.mark.gpu
+def test_async_copies_defer_the_repacks_and_give_the_same_bits():
+    """set_async_copies: every host input goes into its own arena slice and its repack is launched by the next solve / read.
+    Several rounds (the arena grows and wraps during the first ones), results equal the default mode bit for bit; a repeated
+    setData of one level between solves, a result read with inputs pending, invalid inputs, and the switch back."""
+    import lexls_b200 as lx
+    from lexls_b200 import problems
+    w = problems.workload("c3", 300)
+    data, vi = problems.generate(w)
+    rounds = [data, problems.perturb(w, data), data, problems.perturb(w, problems.perturb(w, data))]
+    nl = len(w.ObjDim)
+
+    def feed(s, d):
+        for k, a in enumerate(d):
+            s.setData(k, a, var_index=vi) if w.ObjType[k] == 1 else s.setData(k, a)
+
+    ref = []
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        for d in rounds:
+            feed(s, d)
+            s.solve()
+            ref.append((s.get_x(), s.get_status(), [s.getActiveCtr(k) for k in range(nl)]))
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch, strict=False) as s:
+        s.set_async_copies(True)
+        for r, d in enumerate(rounds):
+            feed(s, d)
+            if r == 1:
+                s.setData(1, rounds[0][1])  # the same level twice in one round: the later call wins
+                s.setData(1, d[1])
+            s.wait_copies()
+            if r == 2:
+                assert s.get_status().shape == (w.batch,)  # a read with inputs pending flushes them first
+            s.solve()
+            x, st = s.get_x(), s.get_status()
+            assert np.array_equal(x, ref[r][0]) and np.array_equal(st, ref[r][1])
+            for k in range(nl):
+                assert np.array_equal(s.getActiveCtr(k), ref[r][2][k])
+        # warm start through the arena (guess + x0 are host inputs too)
+        feed(s, rounds[1])
+        for k in range(nl):
+            s.set_active_guess(k, ref[0][2][k])
+        s.set_x0(ref[0][0])
+        s.solve()
+        xw = s.get_x()
+        bad = rounds[0][1].copy()
+        bad[7, w.nVar, 0], bad[7, w.nVar + 1, 0] = 2.0, 1.0  # lb > ub in one problem
+        s.setData(1, bad)
+        with pytest.raises(lx.LexLSError):
+            s.solve()
+        s.set_async_copies(False)
+        s.reset()  # forget the guess and x0 of the warm start above
+        feed(s, rounds[0])
+        s.solve()
+        assert np.array_equal(s.get_x(), ref[0][0])
+    with lx.LexLSIBatch(w.nVar, w.ObjDim, w.ObjType, batch=w.batch) as s:
+        feed(s, rounds[1])
+        for k in range(nl):
+            s.set_active_guess(k, ref[0][2][k])
+        s.set_x0(ref[0][0])
+        s.solve()
+        assert np.array_equal(s.get_x(), xw)
+
+
 # ---- deferred validation: one synchronisation per batch ---------------------------------------------------------------
 def test_deferred_validation_reports_at_solve():
     import lexls_b200 as lx
