@@ -390,6 +390,7 @@ def measure(name, args, torch, dist, rank, world, local, steps, e2e_steps, batch
                     "pipelined_value": rate(legs["pipelined"]) if "pipelined" in legs else None,
                     "device_inputs_value": rate(legs["device_inputs"]),
                     "device_inputs_api": "set_data_dev (device pointers), solve, get_x into pinned host memory",
+                    "numa": ("rank bound to the %d CPUs local to its GPU before its pinned buffers were allocated" % args.numa_cpus) if getattr(args, "numa_cpus", 0) else "not bound",
                     "final_gather": "lexls_b200.shard.gather_to_rank0(x): shards GPU to GPU over NCCL into one device buffer on rank 0, one D2H into a pinned [global_batch, nVar] buffer; inside the timed region" if world > 1 else "single rank: x lands in the caller's pinned buffer",
                     "host_link": {"h2d_gbs_per_gpu_all_ranks_copying": link_gbs,
                                   "ceiling_problems_per_s": global_batch / (r.h2d_bytes / (link_gbs * 1e9)),
@@ -517,6 +518,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — lexls_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # every rank copies through its own host link at once: keep its pinned buffers on the GPU's NUMA node
+        from lexls_b200.shard import bind_to_gpu_numa_node
+        args.numa_cpus = bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import lexls_b200 as lx

@@ -12,6 +12,25 @@ import os
 import numpy as np
 
 
+def bind_to_gpu_numa_node(device):
+    """Pins the calling process to the CPUs that are local to `device` (NVML's ideal CPU affinity) so that the pinned host
+    buffers it allocates afterwards are first-touched on the GPU's NUMA node: with several ranks copying at once the host
+    link otherwise saturates on one socket's memory.  Returns the number of CPUs bound to, or 0 when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def shard_range(batch, world, rank):
     """Contiguous range [lo, hi) of rank `rank`; the first (batch % world) ranks get one extra problem."""
     base, extra = divmod(int(batch), int(world))
