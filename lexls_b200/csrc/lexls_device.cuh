@@ -2376,16 +2376,16 @@ __device__ __noinline__ void lsi_factor_and_solve(const Shape &sh, const SmemMap
     lse_solve<W, LG>(c, sh.n, sh.ld, sh.G, sm.ldv);
 }
 
-// two-warp LexLSI kernel (C3): compiled for <= 112 registers (minimum block count 9; ptxas settles on 96).  Shared memory keeps
-// eight problems per SM, so 8 x 64 x 96 registers leave a quarter of the register file free: the repack kernels of the NEXT
-// sub-batch (PipelinedBatch) become resident beside the persistent solve CTAs and its host->device copies overlap the solve —
-// end to end 1.65 M -> 1.89 M problems/s on C3, for 2.5 % of kernel time (13.26 / 3.04 -> 13.49 / 3.12 ms cold / warm against the
-// 128 registers ptxas takes when unconstrained).  A ninth resident problem (iteration vectors in the global scratch,
-// SmemMap::vecg, LEXLS_B200_VECG=1) was measured too: no gain (13.47 / 3.20 ms) — the kernel is bound by instruction fetch
-// (85-108 KB of code run once or twice per problem against a 32 KB instruction cache: 20 % of the stall samples) and by its
-// barriers (27 %), not by residency (profiles/r2_lsi_c3_w2_full.txt).
+// two-warp LexLSI kernel (C3): shared memory keeps eight problems per SM, and eight is also the minimum block count the kernel
+// is compiled for (ptxas takes 126 registers).  History, because it was measured both ways: while every host input of the
+// pipelined end-to-end path was repacked right behind its copy, a cap of 96 registers (minimum block count 9) paid — the free
+// quarter of the register file let the NEXT chunk's repack kernels run beside the persistent solve CTAs (end to end 1.65 ->
+// 1.89 M problems/s on C3 for 2.5 % of kernel time).  Since the repacks are deferred to the chunk's own solve
+// (lexls_b200_wait_copies) the end-to-end number no longer depends on it (2.16 M either way) and the uncapped kernel is 3 %
+// faster (cold 11.06 -> 10.68 ms, warm 2.55 -> 2.48 ms, fewer spills).  A ninth resident problem
+// (iteration vectors in the global scratch, SmemMap::vecg, LEXLS_B200_VECG=1) needs the 96-register build.
 #ifndef LX_LSI_W2_MINB
-#define LX_LSI_W2_MINB 9
+#define LX_LSI_W2_MINB 8
 #endif
 template <int W, bool DS, bool LG, bool REG = false>
 __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W == 2) ? LX_LSI_W2_MINB : 0)) lsi_kernel(const __grid_constant__ Shape sh, const __grid_constant__ Params pr,

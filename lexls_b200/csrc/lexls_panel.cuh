@@ -27,6 +27,10 @@ namespace lexls_dev
 {
 
 #define LX_PANEL_MAXRH 20
+// the level routines are real calls; -DLX_PANEL_CALL=__forceinline__ inlines them (experiment: no callee-saved register traffic)
+#ifndef LX_PANEL_CALL
+#define LX_PANEL_CALL __noinline__
+#endif
 // experiment switch (profiles/r2_experiments.json): one column-slot count for every level (less code, idle slots)
 #ifndef LX_PANEL_ONE_S
 #define LX_PANEL_ONE_S 0
@@ -279,7 +283,7 @@ __device__ __forceinline__ bool qr_win_step(double (&a)[2 * NG][S], double (&cn)
 // QR of one level in registers.  cb = first not yet eliminated column on entry; returns ColIndex (rank = result - cb).
 // ---------------------------------------------------------------------------------------------------------------
 template <int NG, int S, bool COMPACT>
-__device__ __noinline__ int qr_level_win(const PanelArgs pa, const int fr, const int dim, const int cb)
+__device__ LX_PANEL_CALL int qr_level_win(const PanelArgs pa, const int fr, const int dim, const int cb)
 {
     constexpr int RH = 2 * NG;
     LX_PANEL_PTRS
@@ -500,7 +504,7 @@ static __device__ __noinline__ void gauss_rows_dyn(const PanelArgs pa, const int
 // or the zero pad behind LOD), always multiplied by l = 0.
 // ---------------------------------------------------------------------------------------------------------------
 template <int NB, bool ODD>
-__device__ __noinline__ void gauss_rows_win(const PanelArgs pa, const int r0, const int rows, const int frg, const int fc,
+__device__ LX_PANEL_CALL void gauss_rows_win(const PanelArgs pa, const int r0, const int rows, const int frg, const int fc,
                                             const int rank, const int ColIndex)
 {
     constexpr int NK = 4 * NB;
