@@ -67,6 +67,7 @@ public:
         lexls_b200_default_params(&p);
         p.regularization_type            = static_cast<int32_t>(par.regularization_type);
         p.variable_regularization_factor = par.variable_regularization_factor;
+        p.max_number_of_cg_iterations    = static_cast<uint32_t>(par.max_number_of_CG_iterations);
         p.max_number_of_factorizations = par.max_number_of_factorizations;
         p.tol_linear_dependence        = par.tol_linear_dependence;
         p.tol_wrong_sign_lambda        = par.tol_wrong_sign_lambda;
@@ -267,6 +268,7 @@ public:
         lexls_b200_default_params(&p);
         p.regularization_type            = static_cast<int32_t>(par.regularization_type);
         p.variable_regularization_factor = par.variable_regularization_factor;
+        p.max_number_of_cg_iterations    = static_cast<uint32_t>(par.max_number_of_CG_iterations);
         p.tol_linear_dependence = par.tol_linear_dependence;
         internal::lexls_b200_check(lexls_b200_set_params(h_, &p));
     }

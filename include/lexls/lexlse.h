@@ -175,6 +175,7 @@ private:
         p.tol_linear_dependence          = parameters.tol_linear_dependence;
         p.regularization_type            = static_cast<int32_t>(parameters.regularization_type);
         p.variable_regularization_factor = parameters.variable_regularization_factor;
+        p.max_number_of_cg_iterations    = static_cast<uint32_t>(parameters.max_number_of_CG_iterations);
         lexls_b200_check(lexls_b200_set_params(h_, &p)); // the conjugate-gradient variants and TIKHONOV_1 are refused here
         for (Index k = 0; k < nObj && k < reg_factor.size(); k++) lexls_b200_check(lexls_b200_set_regularization_factor(h_, k, reg_factor[k]));
     }

@@ -244,6 +244,7 @@ private:
         p.log_working_set_enabled      = parameters.log_working_set_enabled;
         p.deactivate_first_wrong_sign  = parameters.deactivate_first_wrong_sign;
         p.variable_regularization_factor = parameters.variable_regularization_factor;
+        p.max_number_of_cg_iterations    = static_cast<uint32_t>(parameters.max_number_of_CG_iterations);
         lexls_b200_check(lexls_b200_set_params(h_, &p));
     }
     lexls_b200_batch_t *h_;

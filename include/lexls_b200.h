@@ -70,9 +70,11 @@ extern "C" {
 #define LEXLS_B200_MAX_NUMBER_OF_FACTORIZATIONS_EXCEEDED 2
 
 /* POD mirror of ParametersLexLSI (typedefs.h:127-295; defaults :268-294) and ParametersLexLSE (:78-125).
- * regularization_type (typedefs.h:32-44): 0 NONE, 1 TIKHONOV, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 8 TIKHONOV_2, 9 TEST are implemented
- * (lexlse.h:274-411, :1700-1760, :2078-2251, :2592-2625); 2 / 6 (conjugate-gradient variants) and 7 (the reference's own
- * test variant) are EUNSUPPORTED.  Regularized batches run on the shared-memory kernels (two or more warps per problem). */
+ * regularization_type (typedefs.h:32-44): 0 NONE, 1 TIKHONOV, 2 TIKHONOV_CG, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 6 RT_NO_Z_CG,
+ * 7 TIKHONOV_1, 8 TIKHONOV_2, 9 TEST (lexlse.h:274-411, :1700-1760, :2078-2251, :2256-2357, :2367-2550, :2592-2625).  The two
+ * conjugate-gradient types run CGLS from x = 0 for at most max_number_of_cg_iterations steps (tolerance 1e-12, as the
+ * reference); type 7 regularizes exactly as the reference's regularize_tikhonov_1_test does (its X_mu / residual_mu
+ * diagnostics are not produced).  Regularized batches run on the shared-memory kernels (two or more warps per problem). */
 typedef struct lexls_b200_params
 {
     uint32_t max_number_of_factorizations; /* 200   */
@@ -92,6 +94,7 @@ typedef struct lexls_b200_params
     int32_t log_working_set_enabled;       /* 0     */
     int32_t deactivate_first_wrong_sign;   /* 0; 1 = lexlsi.h:1063-1105 (EUNSUPPORTED with a simple-bounds objective: undefined in the reference) */
     double variable_regularization_factor; /* 0.0: use the objectives' factors as they are; else typedefs.h:170-176 (lexlse.h:281-310) */
+    uint32_t max_number_of_cg_iterations;  /* 10 (typedefs.h:91, :167): regularization types 2 and 6 */
 } lexls_b200_params_t;
 
 typedef struct lexls_b200_batch lexls_b200_batch_t; /* opaque */

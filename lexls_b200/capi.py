@@ -50,6 +50,7 @@ class Params(C.Structure):
         ("log_working_set_enabled", C.c_int32),
         ("deactivate_first_wrong_sign", C.c_int32),
         ("variable_regularization_factor", C.c_double),
+        ("max_number_of_cg_iterations", C.c_uint32),
     ]
 
     def __init__(self, **kw):

@@ -574,7 +574,7 @@ static int plan(lexls_b200_batch *h)
     if (h->user_params.regularization_type != 0)
     {
         const uint64_t n = (uint64_t)h->sh.n;
-        h->reg_stride    = 2 * n * (n + 1) + 3 * n + 8;
+        h->reg_stride    = 2 * n * (n + 1) + 12 * n + 8; // Z, D, d, two work vectors, nine for the conjugate-gradient types
         const size_t need = sizeof(double) * h->reg_stride * h->grid;
         if (need > h->reg_bytes)
         {
@@ -661,6 +661,7 @@ void lexls_b200_default_params(lexls_b200_params_t *p)
     p->log_working_set_enabled      = 0;
     p->deactivate_first_wrong_sign  = 0;
     p->variable_regularization_factor = 0.0;
+    p->max_number_of_cg_iterations    = 10; // typedefs.h:121, :282
 }
 int lexls_b200_device_count(int *count)
 {
@@ -693,6 +694,7 @@ static void to_dev_params(const lexls_b200_params_t &u, Params &p)
     p.dfirst       = u.deactivate_first_wrong_sign;
     p.reg_type     = u.regularization_type;
     p.reg_var      = u.variable_regularization_factor;
+    p.reg_cg_iter  = u.max_number_of_cg_iterations;
     // Gauss step on the FP64 tensor cores (mma.sync m8n8k4, bit-identical to the DFMA chain: profiles/r2_dmma_order.json);
     // LEXLS_B200_DMMA=0 selects the DFMA version for A/B measurements
     const char *e = getenv("LEXLS_B200_DMMA");
@@ -874,9 +876,6 @@ int lexls_b200_set_params(lexls_b200_batch_t *h, const lexls_b200_params_t *p)
     {
         const int t = p->regularization_type; // typedefs.h:32-44
         if (t < 0 || t > 9) return fail(LEXLS_B200_EINVAL, "unknown regularization type");
-        if (t == 2 || t == 6 || t == 7)
-            return fail(LEXLS_B200_EUNSUPPORTED, "REGULARIZATION_TIKHONOV_CG, RT_NO_Z_CG (iterative) and TIKHONOV_1 (the reference's test variant) are "
-                                                 "not implemented; TIKHONOV, TIKHONOV_2, R, R_NO_Z, RT_NO_Z and TEST are");
         if ((h->user_params.regularization_type != 0) != (t != 0)) h->planned = false; // regularized solves run on the shared-memory routines
     }
     if (p->deactivate_first_wrong_sign && h->kind == LEXLS_B200_LSI && h->sh.off)

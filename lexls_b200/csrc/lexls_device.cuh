@@ -78,7 +78,9 @@ struct Params
     unsigned cyc_max;
     double cyc_step;
     int mod_x, mod_active, mod_inactive, min_viol, phase1_v0;
-    int reg_type;       // RegularizationType, typedefs.h:32-44 (0 = none; 1 TIKHONOV, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 8 TIKHONOV_2, 9 TEST)
+    int reg_type;       // RegularizationType, typedefs.h:32-44 (0 = none; 1 TIKHONOV, 2 TIKHONOV_CG, 3 R, 4 R_NO_Z, 5 RT_NO_Z, 6 RT_NO_Z_CG,
+                        // 7 TIKHONOV_1, 8 TIKHONOV_2, 9 TEST)
+    unsigned reg_cg_iter; // max_number_of_CG_iterations, typedefs.h:91 (types 2 and 6)
     double reg_var;     // variable_regularization_factor, typedefs.h:170-176
     double reg_factor[LX_MAX_LEVELS]; // setRegularizationFactor per LexLSE level (lexlse.h:1478, objective.h:492)
     int dfirst; // deactivate_first_wrong_sign (lexlsi.h:1048-1105): drop the wrong-sign constraint that was activated first
@@ -936,11 +938,11 @@ __device__ __forceinline__ void gauss_step_smem(const Ctx &c, const int n, const
 // ---------------------------------------------------------------------------------------------------------------
 static __device__ __noinline__ void regularize_level(double *const LOD, const int ld, const int n, const int fr, const int fc, const int r,
                                               const int RC, const int nFixed, const int type, const double factor, const double var_eps,
-                                              const double *const invd, double *const scratch)
+                                              const double *const invd, double *const scratch, const unsigned cg_iterations = 10)
 {
     const int lane = threadIdx.x & 31;
     double *const Z = scratch, *const D = scratch + (size_t)n * (n + 1), *const d = D + (size_t)n * n, *const w0 = D + (size_t)n * (n + 1),
-                 *const w1 = w0 + n;
+                 *const w1 = w0 + n, *const cgw = w1 + n; // cgw: 9 n doubles for the conjugate-gradient types
     auto L  = [&](int row, int col) -> double & { return LOD[row + (size_t)ld * col]; };
     auto Rm = [&](int i, int j) -> double { return LOD[fr + i + (size_t)ld * (fc + j)]; };
     auto Tm = [&](int i, int c) -> double { return LOD[fr + i + (size_t)ld * (fc + r + c)]; };
@@ -1139,8 +1141,102 @@ static __device__ __noinline__ void regularize_level(double *const LOD, const in
         __syncwarp();
     };
 
+    // CGLS on  min || [triu(R) T; a S; a I] x - [y; a s; 0] ||  from x = 0 (cg_tikhonov lexlse.h:2367-2461: S = Z(:, fc..fc+N),
+    // s = Z(:, n); cg_RT :2472-2550: no null-space rows), at most cg_iterations steps or until ||s|| <= 1e-12, then
+    // y := [triu(R) T] x.  One lane per output entry ((S) chains from 0, partial products added afterwards), squared norms
+    // lane-strided + butterfly = the oracle's tree32 order.
+    auto cgls = [&](const int qz) {
+        const int N = r + RC, NR = r + qz + N;
+        double *const rv = cgw, *const qv = cgw + 3 * n, *const sv = cgw + 6 * n, *const pv = cgw + 7 * n, *const xv = cgw + 8 * n;
+        for (int i = lane; i < NR; i += 32) rv[i] = (i < r) ? L(fr + i, n) : (i < r + qz ? Zn(i - r, n) * a : 0.0);
+        for (int c = lane; c < N; c += 32) xv[c] = 0.0;
+        __syncwarp();
+        auto form_s = [&]() {
+            for (int c = lane; c < N; c += 32)
+            {
+                double t = 0.0;
+                for (int p = 0; p < qz; p++) t = fma(Zn(p, fc + c), rv[r + p], t);
+                t        = (t + rv[r + qz + c]) * a;
+                double u = 0.0;
+                if (c < r)
+                    for (int k = 0; k <= c; k++) u = fma(Rm(k, c), rv[k], u);
+                else
+                    for (int k = 0; k < r; k++) u = fma(Tm(k, c - r), rv[k], u);
+                sv[c] = t + u;
+            }
+            __syncwarp();
+        };
+        auto sqnorm = [&](const double *v, const int len) {
+            double acc = 0.0;
+            for (int i = lane; i < len; i += 32) acc = fma(v[i], v[i], acc);
+            return bfly_sum(acc);
+        };
+        form_s();
+        for (int c = lane; c < N; c += 32) pv[c] = sv[c];
+        __syncwarp();
+        double gamma  = sqnorm(sv, N);
+        unsigned iter = 0;
+        while (sqrt(gamma) > 1e-12 && iter < cg_iterations)
+        {
+            for (int i = lane; i < NR; i += 32)
+            {
+                double v;
+                if (i < r)
+                {
+                    double t = 0.0, u = 0.0;
+                    for (int c = 0; c < RC; c++) t = fma(Tm(i, c), pv[r + c], t);
+                    for (int k = i; k < r; k++) u = fma(Rm(i, k), pv[k], u);
+                    v = t + u;
+                }
+                else if (i < r + qz)
+                {
+                    double t = 0.0;
+                    for (int c = 0; c < N; c++) t = fma(Zn(i - r, fc + c), pv[c], t);
+                    v = t * a;
+                }
+                else
+                    v = a * pv[i - r - qz];
+                qv[i] = v;
+            }
+            __syncwarp();
+            const double alpha = gamma / sqnorm(qv, NR);
+            for (int c = lane; c < N; c += 32) xv[c] = fma(alpha, pv[c], xv[c]);
+            for (int i = lane; i < NR; i += 32) rv[i] = fma(-alpha, qv[i], rv[i]);
+            __syncwarp();
+            form_s();
+            const double gamma_previous = gamma;
+            gamma                       = sqnorm(sv, N);
+            const double beta           = gamma / gamma_previous;
+            for (int c = lane; c < N; c += 32) pv[c] = fma(beta, pv[c], sv[c]);
+            __syncwarp();
+            iter++;
+        }
+        for (int i = lane; i < r; i += 32)
+        {
+            double t = 0.0, u = 0.0;
+            for (int k = i; k < r; k++) t = fma(Rm(i, k), xv[k], t);
+            for (int c = 0; c < RC; c++) u = fma(Tm(i, c), xv[r + c], u);
+            w0[i] = t + u;
+        }
+        __syncwarp();
+        for (int i = lane; i < r; i += 32) L(fr + i, n) = w0[i];
+        __syncwarp();
+    };
+
     switch (type)
     {
+    case 7: // REGULARIZATION_TIKHONOV_1: regularize_tikhonov_1_test = tikhonov_1 on the solution path (lexlse.h:378-387; its X_mu /
+        //     residual_mu by-products are diagnostics nothing on the path reads)
+        if (on) tikhonov_1();
+        accumulate();
+        break;
+    case 2: // REGULARIZATION_TIKHONOV_CG
+        if (on) cgls(q);
+        accumulate();
+        break;
+    case 6: // REGULARIZATION_RT_NO_Z_CG
+        if (on) cgls(0);
+        break;
     case 1: // REGULARIZATION_TIKHONOV
         if (on)
         {
@@ -1363,7 +1459,7 @@ template <int W, bool CQ = false, bool CG = CQ, bool LGV = (W == 16), bool REG =
                 if (threadIdx.x < 32)
                 {
                     regularize_level(LOD, ld, n, fr, fc, rank, n - ColIndex, nFixed, reg->reg_type, reg->reg_factor[g], reg->reg_var,
-                                     c.invd, reg_scratch);
+                                     c.invd, reg_scratch, reg->reg_cg_iter);
                     if constexpr (LGV) // the Gauss step reads the level's rows from the shared-memory view: refresh its right-hand side
 #pragma unroll 1
                         for (int i = threadIdx.x; i < rank; i += 32) c.LVIEW[(fr - 2 * (fr >> 1)) + i + smap.ldv * n] = LOD[fr + i + ld * n];

@@ -97,6 +97,7 @@ struct Parameters
     bool deactivate_first_wrong_sign    = false;
     int regularization_type             = 0;   // typedefs.h:32-44 (REGULARIZATION_NONE)
     double variable_regularization_factor = 0.0; // typedefs.h:170-176
+    Index max_number_of_CG_iterations     = 10;  // typedefs.h:91, :167 (the conjugate-gradient regularization types)
 };
 
 // typedefs.h:32-44
@@ -259,12 +260,11 @@ public:
         tol_linear_dependence = t;
     }
     // lexlse.h:1467-1470 (the regularization part of ParametersLexLSE)
-    void setRegularization(int type, double variable_factor)
+    void setRegularization(int type, double variable_factor, Index max_cg_iterations = 10)
     {
-        if (type == REGULARIZATION_TIKHONOV_CG || type == REGULARIZATION_RT_NO_Z_CG || type == REGULARIZATION_TIKHONOV_1)
-            throw Exception("regularization type not restated in the oracle (CG variants, TIKHONOV_1 test variant)");
         regularization_type            = type;
         variable_regularization_factor = variable_factor;
+        max_number_of_CG_iterations    = max_cg_iterations;
     }
     // lexlse.h:1478-1482
     void setRegularizationFactor(Index ObjIndex, double factor)
@@ -967,6 +967,18 @@ private:
             if (on) tikhonov_2(fr, fc, r, RC, a, mu, q, d);
             accumulate_nullspace_basis(fr, fc, r, RC, q);
             break;
+        case REGULARIZATION_TIKHONOV_1: // :378-387: regularize_tikhonov_1_test = tikhonov_1 on the solution path (its X_mu /
+            //                             residual_mu by-products are diagnostics that nothing on the path reads)
+            if (on) tikhonov_1(fr, fc, r, RC, mu, q, d);
+            accumulate_nullspace_basis(fr, fc, r, RC, q);
+            break;
+        case REGULARIZATION_TIKHONOV_CG: // :335-342, :2256-2279 (start from x = 0), cg_tikhonov :2367-2461
+            if (on) cgls(fr, fc, r, RC, a, q, true);
+            accumulate_nullspace_basis(fr, fc, r, RC, q);
+            break;
+        case REGULARIZATION_RT_NO_Z_CG: // :370-376, :2331-2357 (start from x = 0), cg_RT :2472-2550
+            if (on) cgls(fr, fc, r, RC, a, 0, false);
+            break;
         case REGULARIZATION_R: // :344-351, :2143-2170
             if (on)
             {
@@ -1049,6 +1061,73 @@ private:
         default:
             break;
         }
+    }
+
+    // CGLS on  min || [triu(R) T; a S; a I] x - [y; a s; 0] ||  from x = 0 (lexlse.h:2367-2461 with the null-space rows S =
+    // Z(:, fc .. fc+N), s = Z(:, nVar); :2472-2550 without them), at most max_number_of_CG_iterations steps or until
+    // ||s|| <= 1e-12, then y := [triu(R) T] x (:2276-2278).  Fixed orders: every matrix-vector entry is one (S) chain from 0,
+    // two partial products are added afterwards (as Eigen's "+=" of a product does); squared norms are (T) tree32 over the index.
+    void cgls(Index fr, Index fc, Index r, Index RC, double a, Index qz, bool with_null_space)
+    {
+        const Index N = r + RC, NR = r + qz + N;
+        auto R = [&](Index i, Index j) -> double { return L(fr + i, fc + j); };
+        auto T = [&](Index i, Index c) -> double { return L(fr + i, fc + r + c); };
+        std::vector<double> rv(NR, 0.0), qv(NR, 0.0), sv(N, 0.0), pv(N, 0.0), xv(N, 0.0);
+        (void)with_null_space; // qz = 0 drops the null-space rows
+        for (Index i = 0; i < r; i++) rv[i] = L(fr + i, nVar);              // y - [R T] 0
+        for (Index p = 0; p < qz; p++) rv[r + p] = Zn(p, nVar) * a;          // a (s - S 0)
+        auto form_s = [&]() {
+            for (Index c = 0; c < N; c++)
+            {
+                double t = 0.0;
+                for (Index p = 0; p < qz; p++) t = fmad(Zn(p, fc + c), rv[r + p], t); // S' r2
+                t = (t + rv[r + qz + c]) * a;                                          // (+ r3) * a
+                double u = 0.0;
+                if (c < r)
+                    for (Index k = 0; k <= c; k++) u = fmad(R(k, c), rv[k], u); // triu(R)' r1
+                else
+                    for (Index k = 0; k < r; k++) u = fmad(T(k, c - r), rv[k], u); // T' r1
+                sv[c] = t + u;
+            }
+        };
+        form_s();
+        for (Index c = 0; c < N; c++) pv[c] = sv[c];
+        double gamma = tree32_dot(N, sv.data(), 1, sv.data(), 1, 0);
+        Index iter   = 0;
+        while (std::sqrt(gamma) > 1e-12 && iter < max_number_of_CG_iterations)
+        {
+            for (Index i = 0; i < r; i++)
+            {
+                double t = 0.0, u = 0.0;
+                for (Index c = 0; c < RC; c++) t = fmad(T(i, c), pv[r + c], t);
+                for (Index k = i; k < r; k++) u = fmad(R(i, k), pv[k], u);
+                qv[i] = t + u;
+            }
+            for (Index p = 0; p < qz; p++)
+            {
+                double t = 0.0;
+                for (Index c = 0; c < N; c++) t = fmad(Zn(p, fc + c), pv[c], t);
+                qv[r + p] = t * a;
+            }
+            for (Index c = 0; c < N; c++) qv[r + qz + c] = a * pv[c];
+            const double alpha = gamma / tree32_dot(NR, qv.data(), 1, qv.data(), 1, 0);
+            for (Index c = 0; c < N; c++) xv[c] = fmad(alpha, pv[c], xv[c]);
+            for (Index i = 0; i < NR; i++) rv[i] = fmad(-alpha, qv[i], rv[i]);
+            form_s();
+            const double gamma_previous = gamma;
+            gamma                       = tree32_dot(N, sv.data(), 1, sv.data(), 1, 0);
+            const double beta           = gamma / gamma_previous;
+            for (Index c = 0; c < N; c++) pv[c] = fmad(beta, pv[c], sv[c]);
+            iter++;
+        }
+        for (Index i = 0; i < r; i++)
+        {
+            double t = 0.0, u = 0.0;
+            for (Index k = i; k < r; k++) t = fmad(R(i, k), xv[k], t);
+            for (Index c = 0; c < RC; c++) u = fmad(T(i, c), xv[r + c], u);
+            dWorkspace[i] = t + u;
+        }
+        for (Index i = 0; i < r; i++) L(fr + i, nVar) = dWorkspace[i];
     }
 
     // scratch for the untouched diagonal of a symmetric D while its lower triangle is being factorized
@@ -1217,6 +1296,7 @@ private:
     std::vector<double> x, hh_scalars, LOD, PROBLEM_DATA, dWorkspace, ColNorms, invdiag, null_space, array;
     int regularization_type = 0;
     double variable_regularization_factor = 0.0;
+    Index max_number_of_CG_iterations = 10;
     std::vector<int> ctr_type, fixed_var_type;
     std::vector<Index> fixed_var_index, column_permutations;
 };
@@ -1604,7 +1684,7 @@ public:
     {
         parameters = p;
         lexlse.setTolLinearDependence(p.tol_linear_dependence);
-        lexlse.setRegularization(p.regularization_type, p.variable_regularization_factor); // lexlsi.h:331-333
+        lexlse.setRegularization(p.regularization_type, p.variable_regularization_factor, p.max_number_of_CG_iterations); // lexlsi.h:331-333
     }
     // lexlsi.h:497-502 (a simple-bounds objective is never regularized, objective.h:489-493)
     void setRegularizationFactor(Index ObjIndex, double factor)

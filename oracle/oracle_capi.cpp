@@ -38,6 +38,7 @@ struct oracle_params
 // the batch signatures unchanged).  type = typedefs.h:32-44; factors[k] = setRegularizationFactor(k, .) per objective of
 // the hierarchy as the caller numbers them (LexLSI: a simple-bounds objective 0 is counted and ignored, objective.h:489).
 static int g_reg_type = 0;
+static unsigned g_reg_cg_iterations = 10;
 static double g_reg_var = 0.0;
 static std::vector<double> g_reg_factors;
 static int g_least_norm = 0; // LexLSE batches: solveLeastNorm instead of solve()
@@ -55,12 +56,18 @@ extern "C" int oracle_set_regularization(int type, double variable_factor, const
     g_reg_factors.assign(factors ? factors : nullptr, factors ? factors + count : nullptr);
     return 0;
 }
+extern "C" int oracle_set_cg_iterations(uint32_t max_iterations)
+{
+    g_reg_cg_iterations = max_iterations;
+    return 0;
+}
 
 static Parameters to_params(const oracle_params *p)
 {
     Parameters q;
     q.regularization_type            = g_reg_type;
     q.variable_regularization_factor = g_reg_var;
+    q.max_number_of_CG_iterations    = g_reg_cg_iterations;
     if (!p) return q;
     q.max_number_of_factorizations = p->max_number_of_factorizations;
     q.tol_linear_dependence        = p->tol_linear_dependence;
@@ -167,7 +174,7 @@ int oracle_lse_solve_batch(uint32_t nVar, uint32_t nObj, const uint32_t *ObjDim,
             uint64_t p = next.fetch_add(1);
             if (p >= batch || failed.load()) break;
             lse.setTolLinearDependence(tol_linear_dependence);
-            lse.setRegularization(g_reg_type, g_reg_var);
+            lse.setRegularization(g_reg_type, g_reg_var, g_reg_cg_iterations);
             lse.setObjDim(ObjDim);
             for (uint32_t k = 0; k < nObj; k++) lse.setRegularizationFactor(k, k < g_reg_factors.size() ? g_reg_factors[k] : 0.0);
             lse.setFixedVariablesCount(nFixed);

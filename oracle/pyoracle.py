@@ -82,9 +82,11 @@ def lib():
     return _lib
 
 
-def set_regularization(reg_type=0, factors=None, variable_factor=0.0):
-    """Regularization for the following *_solve_batch calls (lexlse.h:274-411): type 1 TIKHONOV, 3 R, 4 R_NO_Z, 5 RT_NO_Z,
-    8 TIKHONOV_2, 9 TEST; factors[k] per objective (setRegularizationFactor); reg_type=0 switches it off again."""
+def set_regularization(reg_type=0, factors=None, variable_factor=0.0, cg_iterations=10):
+    """Regularization for the following *_solve_batch calls (lexlse.h:274-411): type 1 TIKHONOV, 2 TIKHONOV_CG, 3 R, 4 R_NO_Z,
+    5 RT_NO_Z, 6 RT_NO_Z_CG, 7 TIKHONOV_1, 8 TIKHONOV_2, 9 TEST; factors[k] per objective (setRegularizationFactor);
+    cg_iterations = max_number_of_CG_iterations (typedefs.h:91); reg_type=0 switches it off again."""
+    lib().oracle_set_cg_iterations(C.c_uint32(int(cg_iterations)))
     f = np.ascontiguousarray(factors if factors is not None else [], dtype=np.float64)
     lib().oracle_set_regularization(C.c_int(int(reg_type)), C.c_double(float(variable_factor)),
                                     f.ctypes.data_as(C.POINTER(C.c_double)) if f.size else None, C.c_uint32(f.size))

@@ -449,7 +449,7 @@ def test_result_buffers_keep_their_guard_bands(monkeypatch):
 
 
 # ---- regularization (lexlse.h:274-411, :1700-1760, :2078-2251, :2592-2625) ------------------------------------------------
-REG_TYPES = {1: "TIKHONOV", 3: "R", 4: "R_NO_Z", 5: "RT_NO_Z", 8: "TIKHONOV_2", 9: "TEST"}
+REG_TYPES = {1: "TIKHONOV", 2: "TIKHONOV_CG", 3: "R", 4: "R_NO_Z", 5: "RT_NO_Z", 6: "RT_NO_Z_CG", 7: "TIKHONOV_1", 8: "TIKHONOV_2", 9: "TEST"}
 
 
 @pytest.mark.parametrize("reg_type", sorted(REG_TYPES))
@@ -521,7 +521,7 @@ def test_variable_regularization_factor_matches_the_oracle(oracle):
         assert np.array_equal(s.get_x(), ref["x"])
 
 
-@pytest.mark.parametrize("reg_type", [1, 4, 5])
+@pytest.mark.parametrize("reg_type", [1, 2, 4, 5, 6])
 def test_regularized_lexlsi_matches_the_oracle(oracle, reg_type):
     """The active-set loop with a damped inner LexLSE (lexlsi.h:331-333, :497; objective.h:489-493: the simple-bounds objective
     is never regularized)."""
@@ -554,15 +554,42 @@ def test_regularized_lexlsi_matches_the_oracle(oracle, reg_type):
     assert not np.array_equal(plain["x"], ref["x"])
 
 
-def test_unimplemented_regularization_types_are_refused():
+def test_unknown_regularization_types_are_refused():
     import lexls_b200 as lx
     with lx.LexLSEBatch(4, [2, 2], batch=1) as s:
-        for t in (2, 6, 7):
-            with pytest.raises(lx.LexLSError) as e:
+        for t in (-1, 10, 12):
+            with pytest.raises(lx.LexLSError):
                 s.setParameters(lx.Params(regularization_type=t))
-            assert e.value.code == 3
-        with pytest.raises(lx.LexLSError):
-            s.setParameters(lx.Params(regularization_type=12))
+
+
+def test_conjugate_gradient_iteration_cap_matches_the_oracle(oracle):
+    """max_number_of_CG_iterations (typedefs.h:91): 1, 3 and 40 steps of the two CGLS types give the oracle's bits, and the
+    long run reaches the direct variant (TIKHONOV / RT_NO_Z) to 1e-9."""
+    import lexls_b200 as lx
+    rng = np.random.default_rng(77)
+    n, dims, B = 13, [4, 3, 5], 9
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    factors = [0.3, 0.05, 0.7]
+
+    def gpu(reg_type, it):
+        with lx.LexLSEBatch(n, dims, batch=B) as s:
+            s.setParameters(lx.Params(regularization_type=reg_type, max_number_of_cg_iterations=it))
+            for k, f in enumerate(factors):
+                s.setRegularizationFactor(k, f)
+            for k, d in enumerate(data):
+                s.setData(k, d)
+            s.solve()
+            return s.get_x()
+
+    for cg, direct in ((2, 1), (6, 5)):
+        for it in (1, 3, 40):
+            oracle.set_regularization(cg, factors, cg_iterations=it)
+            try:
+                ref = oracle.lse_solve_batch(n, dims, data, threads=0)
+            finally:
+                oracle.set_regularization(0)
+            assert np.array_equal(gpu(cg, it), ref["x"]), (cg, it)
+        assert np.abs(gpu(cg, 400) - gpu(direct, 10)).max() < 1e-9
 
 
 # ---- solveLeastNorm (lexlse.h:1046-1262) ----------------------------------------------------------------------------------

@@ -187,3 +187,53 @@ def test_oracle_rejects_bad_bounds(oracle):
     d[0, 3, :] = 0.0   # ub < lb
     with pytest.raises(RuntimeError):
         oracle.lsi_solve_batch(2, [2], [0], [d])
+
+
+def _two_level(rng, B, n, m1, m2):
+    A1, b1 = rng.standard_normal((B, m1, n)), rng.standard_normal((B, m1))
+    A2, b2 = rng.standard_normal((B, m2, n)), rng.standard_normal((B, m2))
+    lv = lambda A, b: np.ascontiguousarray(np.concatenate([A, b[:, :, None]], axis=2).transpose(0, 2, 1))
+    return A1, b1, A2, b2, [lv(A1, b1), lv(A2, b2)]
+
+
+def test_tikhonov_regularization_is_the_constrained_ridge_solution(oracle):
+    """REGULARIZATION_TIKHONOV / TIKHONOV_2 / TIKHONOV_1 (lexlse.h:317-331, :378-396) on {A1 x = b1 (full row rank)} >
+    {A2 x = b2, factor a}: x = x1 + Z z with z = argmin |A2 (x1 + Z z) - b2|^2 + a^2 |x1 + Z z|^2, Z = null(A1), x1 = pinv(A1) b1."""
+    rng = np.random.default_rng(5)
+    B, n, m1, m2, a = 20, 7, 3, 6, 0.35
+    A1, b1, A2, b2, data = _two_level(rng, B, n, m1, m2)
+    for reg_type in (1, 7, 8):
+        oracle.set_regularization(reg_type, [0.0, a])
+        try:
+            r = oracle.lse_solve_batch(n, [m1, m2], data)
+        finally:
+            oracle.set_regularization(0)
+        for p in range(B):
+            x1 = np.linalg.pinv(A1[p]) @ b1[p]
+            Z = np.linalg.svd(A1[p])[2][m1:].T
+            M = np.vstack([A2[p] @ Z, a * Z])
+            rhs = np.concatenate([b2[p] - A2[p] @ x1, -a * x1])
+            z = np.linalg.lstsq(M, rhs, rcond=None)[0]
+            assert np.abs(r["x"][p] - (x1 + Z @ z)).max() < 1e-11, reg_type
+
+
+def test_conjugate_gradient_regularization_converges_to_the_direct_variants(oracle):
+    """REGULARIZATION_TIKHONOV_CG solves the TIKHONOV problem and RT_NO_Z_CG the RT_NO_Z problem by CGLS
+    (lexlse.h:2256-2279, :2331-2357, :2367-2550): with enough iterations they return the direct solutions; with the default
+    cap of 10 they stop early (typedefs.h:121) and differ."""
+    rng = np.random.default_rng(6)
+    B, n, m1, m2 = 12, 9, 3, 4
+    _, _, _, _, data = _two_level(rng, B, n, m1, m2)
+    factors = [0.2, 0.5]
+
+    def run(reg_type, it=10):
+        oracle.set_regularization(reg_type, factors, cg_iterations=it)
+        try:
+            return oracle.lse_solve_batch(n, [m1, m2], data)["x"]
+        finally:
+            oracle.set_regularization(0)
+
+    for cg, direct in ((2, 1), (6, 5)):
+        xd = run(direct)
+        assert np.abs(run(cg, 400) - xd).max() < 1e-9
+        assert np.abs(run(cg, 1) - xd).max() > 1e-6  # one step is not the solution: the cap is honoured
