@@ -191,8 +191,6 @@ static int stage_take(lexls_b200_batch *h, size_t bytes, void **p)
         // wrap: the repacks that read the arena are enqueued first, so the copies that follow are ordered behind them by the
         // stream; the arena grows towards one full round of inputs (a few warm-up rounds), after which nothing wraps
         if (int rc = flush_pending(h)) return rc;
-        if (getenv("LEXLS_B200_DEBUG_STAGE"))
-            fprintf(stderr, "[stage %p] wrap: cursor %zu + %zu > %zu (round %zu)\n", (void *)h, h->stage_cursor, bytes, h->stage_bytes, h->round_bytes);
         h->stage_cursor = 0;
         // what this round has taken so far, or what the largest finished round took: with 1/8 of headroom the arena holds a
         // full round after the second one and never wraps again (a reallocation synchronises the whole device)

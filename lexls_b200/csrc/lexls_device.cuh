@@ -663,46 +663,39 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
             const int np      = pe - pb;
             // one thread per column: both parity chains of (S2) in one thread
             auto apply_thread_per_column = [&]() {
-            for (int j = ColIndex + 1 + tid; j <= n; j += NT)
-            {
-                double *cp = P(j, pb);
-                if (apply)
+                for (int j = ColIndex + 1 + tid; j <= n; j += NT)
                 {
-                    double ae = 0.0, ao = 0.0;
-#pragma unroll 2
-                    for (int q = 0; q < np; q++)
+                    double *cp = P(j, pb);
+                    if (apply)
                     {
-                        const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
-                        ae = fma(v.x, a.x, ae);
-                        ao = fma(v.y, a.y, ao);
+                        double ae = 0.0, ao = 0.0;
+#pragma unroll 2
+                        for (int q = 0; q < np; q++)
+                        {
+                            const double2 v = ld2(vp + 2 * q), a = ld2(cp + 2 * q);
+                            ae = fma(v.x, a.x, ae);
+                            ao = fma(v.y, a.y, ao);
+                        }
+                        const double w = tau * (ae + ao);
+#pragma unroll 2
+                        for (int q = 0; q < np; q++)
+                        {
+                            const double2 v = ld2(vp + 2 * q);
+                            double2 a       = ld2(cp + 2 * q);
+                            a.x             = fma(-v.x, w, a.x);
+                            a.y             = fma(-v.y, w, a.y);
+                            st2(cp + 2 * q, a);
+                        }
                     }
-                    const double w = tau * (ae + ao);
-#pragma unroll 2
-                    for (int q = 0; q < np; q++)
+                    if (j < n)
                     {
-                        const double2 v = ld2(vp + 2 * q);
-                        double2 a       = ld2(cp + 2 * q);
-                        a.x             = fma(-v.x, w, a.x);
-                        a.y             = fma(-v.y, w, a.y);
-                        st2(cp + 2 * q, a);
+                        const double a0 = *E(j, row);
+                        c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
                     }
                 }
-                if (j < n)
-                {
-                    const double a0 = *E(j, row);
-                    c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
-                }
-            }
             };
-            if constexpr (LGV || W >= 4)
-            {
-                // more open columns than thread pairs: one pass with one thread per column instead of two passes with two
-                // (same sums: the pair adds its two chains, the single thread adds the same two chains)
-                if (n - ColIndex > NT / 2)
-                    apply_thread_per_column();
-                else
-            {
-                // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
+            // two threads per column, one per row parity: each runs one of the two (S2) chains, the pair adds them
+            auto apply_thread_pair_per_column = [&]() {
                 const int par = tid & 1;
                 for (int jb = ColIndex + 1 + ((tid & ~31) >> 1); jb <= n; jb += NT / 2) // warp-uniform trip count
                 {
@@ -728,7 +721,15 @@ __device__ __forceinline__ void qr_level_smem(const Ctx &c, const int n, const i
                         c.colnorm[j]    = fma(-a0, a0, c.colnorm[j]);
                     }
                 }
-            }
+            };
+            if constexpr (LGV || W >= 4)
+            {
+                // more open columns than thread pairs: one pass with one thread per column instead of two passes with two
+                // (same sums: the pair adds its two chains, the single thread adds the same two chains)
+                if (n - ColIndex > NT / 2)
+                    apply_thread_per_column();
+                else
+                    apply_thread_pair_per_column();
             }
             else
                 apply_thread_per_column();
