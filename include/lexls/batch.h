@@ -7,6 +7,11 @@
 #pragma once
 
 #include <algorithm>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 
 #include <lexls/lexlsi.h>
 
@@ -26,6 +31,13 @@ inline void pack_level(const std::vector<dMatrixType> &per_problem, Index rows, 
         std::copy(m.data(), m.data() + static_cast<size_t>(rows) * cols, packed.begin() + q * static_cast<size_t>(rows) * cols);
     }
 }
+} // namespace internal
+
+namespace internal
+{
+// A set_* call whose source is a temporary (a packed scratch vector) must not return before the copy has left it: a no-op in
+// the default mode (the C-ABI has waited already), one event wait in asynchronous-copies mode.
+inline void lexls_b200_release_temporary(lexls_b200_batch_t *h) { lexls_b200_check(lexls_b200_wait_copies(h)); }
 } // namespace internal
 
 class LexLSIBatch
@@ -93,6 +105,7 @@ public:
         if (type[ObjIndex] == static_cast<int32_t>(SIMPLE_BOUNDS_OBJECTIVE)) throw Exception("setData: use the VarIndex overload for simple bounds");
         internal::pack_level(per_problem, dim[ObjIndex], nVar + 2, scratch);
         setDataPacked(ObjIndex, scratch.data(), dim[ObjIndex], static_cast<uint64_t>(dim[ObjIndex]) * (nVar + 2));
+        internal::lexls_b200_release_temporary(h_);
     }
     // already packed host data: problem q at data + q * problem_stride, column-major with leading dimension ld
     void setDataPacked(Index ObjIndex, const RealScalar *data, Index ld, uint64_t problem_stride)
@@ -108,6 +121,7 @@ public:
         internal::pack_level(per_problem, dim[0], 2, scratch);
         internal::lexls_b200_check(lexls_b200_set_simple_bounds(h_, VarIndex, 0, scratch.data(), dim[0] > 0 ? dim[0] : 1,
                                                                 static_cast<uint64_t>(dim[0]) * 2));
+        internal::lexls_b200_release_temporary(h_);
         solved = false;
     }
     // warm start: the api_activate calls of problem q as one type per row (CTR_INACTIVE = no call), lexlsi.h:120
@@ -121,6 +135,7 @@ public:
             for (Index i = 0; i < dim[ObjIndex]; i++) t[q * dim[ObjIndex] + i] = static_cast<uint8_t>(per_problem[q][i]);
         }
         internal::lexls_b200_check(lexls_b200_set_active_guess(h_, ObjIndex, t.data()));
+        internal::lexls_b200_release_temporary(h_);
         solved = false;
     }
     // warm start in CALL ORDER: calls[q] = the api_activate(obj, ctr, type) sequence of problem q (lexlsi.h:120-136)
@@ -144,6 +159,7 @@ public:
                 t[q * cnt + e] = static_cast<uint8_t>(calls[q][e].ctr_type);
             }
         internal::lexls_b200_check(lexls_b200_set_active_guess_ordered(h_, static_cast<uint32_t>(cnt), o.data(), c.data(), t.data(), cnt));
+        internal::lexls_b200_release_temporary(h_);
         solved = false;
     }
     void set_x0(const std::vector<dVectorType> &x0) // lexlsi.h:306
@@ -156,6 +172,7 @@ public:
             std::copy(x0[q].data(), x0[q].data() + nVar, p.begin() + q * nVar);
         }
         internal::lexls_b200_check(lexls_b200_set_x0(h_, p.data()));
+        internal::lexls_b200_release_temporary(h_);
         solved = false;
     }
     void reset() // lexlsi.h:88 (keeps data and parameters)
@@ -278,6 +295,7 @@ public:
         if (per_problem.size() != batch) throw Exception("one matrix per problem of the batch is expected");
         internal::pack_level(per_problem, dim[ObjIndex], nVar + 1, scratch);
         setDataPacked(ObjIndex, scratch.data(), dim[ObjIndex], static_cast<uint64_t>(dim[ObjIndex]) * (nVar + 1));
+        internal::lexls_b200_release_temporary(h_);
     }
     void setDataPacked(Index ObjIndex, const RealScalar *data, Index ld, uint64_t problem_stride)
     {
@@ -422,4 +440,71 @@ template <class Batch> inline BatchResult solve_lse_batch(Batch &b, Index nObj, 
     return r;
 }
 } // namespace internal
+// ---------------------------------------------------------------------------------------------------------------
+// Host-resident inputs, pipelined: the batch is split into `chunks` sub-batches, each with its own handle (its own CUDA
+// stream, asynchronous-copies mode: lexls_b200_set_async_copies) and its own host thread.  The host->device copies of one
+// chunk overlap the solve and the result read of the previous ones; the copy phases are serialised (the host link is the
+// shared resource) and each chunk waits ONCE, for its copies alone (lexls_b200_wait_copies) — the device-side repacks are
+// launched by the chunk's solve.  BatchT = LexLSEBatch or LexLSIBatch.  The caller's input buffers must stay valid until
+// solve() returns; pinned memory gives the full link rate.
+//
+//   PipelinedBatch<LexLSEBatch> pb(batch, 4, [&](uint64_t count) { return new LexLSEBatch(nVar, nObj, ObjDim, count); });
+//   pb.solve([&](LexLSEBatch &c, uint64_t first, uint64_t) {                       // set* calls of problems [first, first + count)
+//       for (Index k = 0; k < nObj; k++) c.setDataPacked(k, level[k] + first * stride[k], ObjDim[k], stride[k]); },
+//            x_out, nVar);
+// ---------------------------------------------------------------------------------------------------------------
+template <class BatchT> class PipelinedBatch
+{
+public:
+    template <class Make> PipelinedBatch(uint64_t batch, int chunks, Make make)
+    {
+        if (chunks < 1) chunks = 1;
+        if (static_cast<uint64_t>(chunks) > batch) chunks = static_cast<int>(batch);
+        for (int c = 0; c < chunks; c++)
+        {
+            const uint64_t lo = batch * c / chunks, hi = batch * (c + 1) / chunks;
+            first_.push_back(lo);
+            part_.push_back(std::unique_ptr<BatchT>(make(hi - lo)));
+            internal::lexls_b200_check(lexls_b200_set_async_copies(part_.back()->handle(), 1));
+        }
+    }
+    size_t chunks() const { return part_.size(); }
+    BatchT &chunk(size_t c) { return *part_[c]; }
+    uint64_t first(size_t c) const { return first_[c]; }
+
+    // feed(chunk, first, count) issues the host set* calls of the chunk's problems; x_out receives [batch][nVar]
+    template <class Feed> void solve(Feed feed, RealScalar *x_out, Index nVar)
+    {
+        std::vector<std::string> errors(part_.size());
+        std::vector<std::thread> workers;
+        for (size_t c = 0; c < part_.size(); c++)
+            workers.push_back(std::thread([this, c, &feed, x_out, nVar, &errors]() {
+                try
+                {
+                    BatchT &b = *part_[c];
+                    {
+                        std::lock_guard<std::mutex> link(copy_phase_);
+                        feed(b, first_[c], b.size());
+                        internal::lexls_b200_check(lexls_b200_wait_copies(b.handle()));
+                    }
+                    internal::lexls_b200_check(lexls_b200_solve_batch(b.handle()));
+                    internal::lexls_b200_check(lexls_b200_get_x(b.handle(), x_out + first_[c] * nVar)); // synchronises; reports bad inputs
+                }
+                catch (std::exception &e)
+                {
+                    errors[c] = e.what();
+                    if (errors[c].empty()) errors[c] = "error";
+                }
+            }));
+        for (size_t c = 0; c < workers.size(); c++) workers[c].join();
+        for (size_t c = 0; c < errors.size(); c++)
+            if (!errors[c].empty()) throw Exception(errors[c].c_str());
+    }
+
+private:
+    std::vector<uint64_t> first_;
+    std::vector<std::unique_ptr<BatchT> > part_;
+    std::mutex copy_phase_;
+};
+
 } // namespace LexLS

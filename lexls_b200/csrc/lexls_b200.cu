@@ -930,6 +930,13 @@ static int check_pending_flag(lexls_b200_batch *h)
     cudaMemsetAsync(h->flag, 0, sizeof(int), h->stream);
     return flag_error(h, flag);
 }
+// the source is a temporary of the library: its copy must have left it in every copy mode
+static int wait_copy_of_temporary(lexls_b200_batch *h)
+{
+    CK(cudaEventRecord(h->ev_copy, h->stream));
+    CK(cudaEventSynchronize(h->ev_copy));
+    return 0;
+}
 // host inputs: returns once the caller's buffer has been consumed (copied into the staging buffer)
 static int wait_copy(lexls_b200_batch *h)
 {
@@ -1153,7 +1160,8 @@ static int set_guess_impl(lexls_b200_batch *h, uint32_t level, const uint8_t *ty
         if (h->guess && h->sh.dim[level])
         {
             std::vector<uint8_t> z((size_t)h->sh.dim[level] * h->batch, 0);
-            return scatter_level<unsigned char>(h, &h->guess, level, z.data(), false);
+            if (int rc = scatter_level<unsigned char>(h, &h->guess, level, z.data(), false)) return rc;
+            return wait_copy_of_temporary(h);
         }
         return 0;
     }
@@ -1691,7 +1699,7 @@ int lexls_b200_set_active_guess_ordered(lexls_b200_batch_t *h, uint32_t count, c
         packed.swap(wide);
     }
     CK(cudaMemcpyAsync(h->glist, packed.data(), sizeof(unsigned) * packed.size(), cudaMemcpyHostToDevice, h->stream));
-    if (int rc = wait_copy(h)) return rc;
+    if (int rc = wait_copy_of_temporary(h)) return rc;
     h->have_glist = true;
     return 0;
 }

@@ -134,6 +134,43 @@ int main()
                 if (use == ndev) break;
             }
         }
+        // host-resident inputs pipelined over chunk handles (asynchronous copies, deferred repacks): the same bits
+        {
+            std::vector<std::vector<double> > lvl(Pe);
+            std::vector<uint64_t> stride(Pe);
+            for (Index k = 0; k < Pe; k++)
+            {
+                stride[k] = uint64_t(de[k]) * (ne + 1);
+                lvl[k].resize(B * stride[k]);
+                for (uint64_t q = 0; q < B; q++) std::copy(eq[q][k].data(), eq[q][k].data() + stride[k], lvl[k].begin() + q * stride[k]);
+            }
+            PipelinedBatch<LexLSEBatch> pb(B, 3, [&](uint64_t count) { return new LexLSEBatch(ne, Pe, de, count); });
+            std::vector<double> xp(B * ne);
+            for (int round = 0; round < 3; round++) // the staging arena grows during the first rounds
+            {
+                std::fill(xp.begin(), xp.end(), 0.0);
+                pb.solve([&](LexLSEBatch &c, uint64_t first, uint64_t) {
+                    for (Index k = 0; k < Pe; k++) c.setDataPacked(k, lvl[k].data() + first * stride[k], de[k], stride[k]);
+                }, xp.data(), ne);
+                for (uint64_t q = 0; q < B; q++)
+                    for (Index j = 0; j < ne; j++)
+                        if (xp[q * ne + j] != re.x[q](j)) { std::printf("FAIL pipelined LexLSE x of problem %u (round %d)\n", unsigned(q), round); return 1; }
+            }
+            PipelinedBatch<LexLSIBatch> pi(B, 4, [&](uint64_t count) { return new LexLSIBatch(n, P, dims, types, count); });
+            std::vector<double> xi(B * n);
+            pi.solve([&](LexLSIBatch &c, uint64_t first, uint64_t count) {
+                std::vector<dMatrixType> level(count);
+                for (Index k = 0; k < P; k++)
+                {
+                    for (uint64_t q = 0; q < count; q++) level[q] = data[first + q][k];
+                    if (k == 0) c.setData(0, var_index, level); else c.setData(k, level);
+                }
+            }, xi.data(), n);
+            for (uint64_t q = 0; q < B; q++)
+                for (Index j = 0; j < n; j++)
+                    if (xi[q * n + j] != r.x[q](j)) { std::printf("FAIL pipelined LexLSI x of problem %u\n", unsigned(q)); return 1; }
+            std::printf("PipelinedBatch ok\n");
+        }
         // the handle classes: ranks, packed data, fixed variables, residuals
         {
             LexLSEBatch b(ne, Pe, de, B);
