@@ -626,3 +626,27 @@ def test_least_norm_solution_matches_the_oracle_and_pinv(oracle, monkeypatch, va
                 A = np.concatenate([d[p].T[:, :n] for d in data])
                 b = np.concatenate([d[p].T[:, n] for d in data])
                 assert np.abs(x_ln[p] - np.linalg.pinv(A) @ b).max() < 1e-9
+
+
+# ---- reflector application: one thread per column while more columns are open than thread pairs ------------------------------
+@pytest.mark.parametrize("warps,n,dims", [(4, 80, [30, 25, 30]), (8, 150, [20, 30, 25]), (4, 70, [10, 70])])
+def test_wide_shapes_on_the_multi_warp_kernels_match_the_oracle(oracle, monkeypatch, warps, n, dims):
+    """Shapes with more open columns than half the threads of a group (qr_level_smem switches between one thread and a thread
+    pair per column): bit-identical x, ranks and factorization, rank-deficient problems included."""
+    monkeypatch.setenv("LEXLS_B200_WARPS", str(warps))
+    monkeypatch.setenv("LEXLS_B200_NO_AUTO_LODGLOBAL", "1")
+    rng = np.random.default_rng(warps * 1000 + n)
+    B = 6
+    data = [np.ascontiguousarray(rng.standard_normal((B, n + 1, m))) for m in dims]
+    data[0][::2, 3, :] = data[0][::2, 1, :]  # duplicated column: rank deficiency and pivot ties in half of the problems
+    ref = oracle.lse_solve_batch(n, dims, data, threads=0, want_factors=True)
+    import lexls_b200 as lx
+    with lx.LexLSEBatch(n, dims, batch=B) as s:
+        s.request_outputs(lexqr=True)
+        for k, d in enumerate(data):
+            s.setData(k, d)
+        s.solve()
+        assert s.kernel_info()["name"] == "lse_w%d" % warps
+        q, _ = s.get_lexqr()
+        assert np.array_equal(s.get_x(), ref["x"]) and np.array_equal(s.get_ranks(), ref["ranks"])
+        assert np.array_equal(q, ref["lexqr"])
