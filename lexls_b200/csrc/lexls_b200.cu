@@ -68,6 +68,7 @@ struct lexls_b200_batch
     double *rec = nullptr, *obj = nullptr, *sb = nullptr, *fval = nullptr, *x0 = nullptr, *v0 = nullptr;
     unsigned *sbidx = nullptr, *fidx = nullptr;
     unsigned char *ftype = nullptr, *guess = nullptr;
+    unsigned char *rownz = nullptr; // LSI: [B][M] 1 = the row of A is not all zero (set_data)
     uint64_t rec_stride = 0, obj_stride = 0, sbidx_stride = 0;
     bool have_x0 = false, have_guess = false;
     std::vector<char> have_v0;
@@ -227,6 +228,28 @@ __global__ void repack_level_kernel(double *dst, unsigned long long dstride, int
             const double lb = src[p * sstride + (unsigned long long)lbcol * sld + i];
             if (lb > val) atomicOr(flag, bit);
         }
+    }
+}
+
+// LexLSI: nz[p * M + roff + i] = (squared norm of row i of the level's A > 0): the "don't activate 0 * x = b" test of setData
+// (lexlsi.h:373-377) belongs to set-up, not to the solve; same (S) chain over the columns as the oracle
+__global__ void row_nonzero_kernel(const double *obj, unsigned long long ostride, int ldo, int roff, int m, int n, unsigned long long batch,
+                                   unsigned char *nz, int M)
+{
+    const unsigned long long tot = (unsigned long long)m * batch;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < tot;
+         e += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long p = e / m;
+        const int i                = (int)(e - p * m);
+        const double *row          = obj + p * ostride + roff + i;
+        double s                   = 0.0;
+        for (int col = 0; col < n; col++)
+        {
+            const double a = row[(unsigned long long)ldo * col];
+            s              = fma(a, a, s);
+        }
+        nz[p * M + roff + i] = s > 0 ? 1 : 0;
     }
 }
 
@@ -798,6 +821,8 @@ int lexls_b200_create_batch(int kind, uint32_t nVar, uint32_t nObj, const uint32
     {
         CKB(guarded_malloc(h, (void **)&h->obj, sizeof(double) * h->obj_stride * B));
         CKB(cudaMemsetAsync(h->obj, 0, sizeof(double) * h->obj_stride * B, h->stream));
+        CKB(guarded_malloc(h, (void **)&h->rownz, (size_t)std::max(s.M, 1) * B));
+        CKB(cudaMemsetAsync(h->rownz, 0, (size_t)std::max(s.M, 1) * B, h->stream));
         if (s.m0)
         {
             CKB(guarded_malloc(h, (void **)&h->sb, sizeof(double) * 2 * s.m0 * B));
@@ -835,7 +860,7 @@ int lexls_b200_destroy(lexls_b200_batch_t *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    void *ptrs[] = {h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
+    void *ptrs[] = {h->rownz, h->rec, h->obj, h->sb, h->fval, h->x0, h->v0, h->sbidx, h->fidx, h->ftype, h->guess, h->x, h->v, h->viol,
                     h->lod_scratch, h->act, h->order, h->counters, h->ranks, h->colperm, h->status, h->flag, h->queue, h->stage,
                     h->lexqr, h->hhout, h->lambda, h->wslog, h->wslog_count, h->xstar, h->lexdata, h->lexqr_star, h->hh_star, h->glist, h->wsl, h->reg_scratch, h->xln, h->ln_scratch, h->vec_scratch};
     for (void *p : ptrs)
@@ -979,8 +1004,12 @@ static int set_data_impl(lexls_b200_batch *h, uint32_t level, const double *data
     const unsigned long long work = (unsigned long long)m * cols * h->batch;
     return run_or_defer(h, [=]() -> int {
         if (lsi)
+        {
             repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->obj, h->obj_stride, h->sh.ldo, h->sh.goff[g], src, stride,
                                                                          (int)ld, m, cols, h->batch, h->sh.n, h->sh.n + 1, h->flag);
+            row_nonzero_kernel<<<blocks_for((unsigned long long)m * h->batch), 256, 0, h->stream>>>(h->obj, h->obj_stride, h->sh.ldo, h->sh.goff[g], m,
+                                                                                                  h->sh.n, h->batch, h->rownz, h->sh.M);
+        }
         else
             repack_level_kernel<<<blocks_for(work), 256, 0, h->stream>>>(h->rec, h->rec_stride, h->sh.ld, h->sh.goff[g], src, stride,
                                                                          (int)ld, m, cols, h->batch, -1, -1, h->flag);
@@ -1249,6 +1278,7 @@ int lexls_b200_solve_batch(lexls_b200_batch_t *h)
     Buffers b{};
     b.rec          = h->rec;
     b.obj          = h->obj;
+    b.rownz        = h->rownz;
     b.sb           = h->sb;
     b.sbidx        = h->sbidx;
     b.sbidx_stride = h->sbidx_stride;

@@ -102,6 +102,7 @@ struct Buffers
     // inputs
     const double *rec;      // LSE: [B][rec_stride] smem image of [A|b], column-major ld = shape.ld
     double *obj;            // LSI: [B][obj_stride] stacked general levels [M x (n+2)] column-major ld = ldo (bounds may be relaxed)
+    const unsigned char *rownz; // LSI: [B][M] 1 = the row of A is not all zero (row_nonzero_kernel at set_data, lexlsi.h:373-377)
     double *sb;             // LSI: [B][2*m0] lb | ub of the simple-bounds level
     const unsigned *sbidx;  // LSI: [B or 1][m0] variable indices
     unsigned long long sbidx_stride;
@@ -2594,23 +2595,8 @@ __global__ void __launch_bounds__(32 * W, (LG && W == 8) ? 2 : ((!LG && !DS && W
                 {
                     const double bl = ov.lb(k, i), bu = ov.ub(k, i);
                     bool eq = fabs(bl - bu) < 1e-15; // isEqual, utility.h:48-51
-                    if (eq && !(sh.off && k == 0))
-                    {
-                        // don't activate 0*x = b rows, lexlsi.h:377
-                        const int r = sh.goff[k - sh.off] + i;
-                        double s    = 0.0;
-                        int col     = 0;
-                        for (; col + 8 <= n; col += 8)
-                        {
-                            double t8[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) t8[u] = ov.A(r, col + u);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) s = fma(t8[u], t8[u], s);
-                        }
-                        for (; col < n; col++) s = fma(ov.A(r, col), ov.A(r, col), s);
-                        eq = s > 0;
-                    }
+                    // don't activate 0*x = b rows, lexlsi.h:377: the row norms were tested when the data was set
+                    if (eq && !(sh.off && k == 0)) eq = bf.rownz[p * sh.M + sh.goff[k - sh.off] + i] != 0;
                     eqflag[o + i] = eq;
                     gs[o + i]     = bf.guess ? bf.guess[p * sh.Mall + o + i] : 0;
                 }
