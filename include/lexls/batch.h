@@ -460,9 +460,24 @@ public:
     {
         if (chunks < 1) chunks = 1;
         if (static_cast<uint64_t>(chunks) > batch) chunks = static_cast<int>(batch);
+        // equal chunks, but the last two are a half and a quarter: what remains after the last copy is the last chunk's solve
+        std::vector<double> w(chunks, 1.0);
+        if (chunks >= 3 && batch >= 8192) // smaller batches: the small chunks would not fill the GPU
+        {
+            w[chunks - 2] = 0.5;
+            w[chunks - 1] = 0.25;
+        }
+        double tot = 0.0, acc = 0.0;
+        for (int c = 0; c < chunks; c++) tot += w[c];
+        std::vector<uint64_t> cut(chunks + 1, 0);
         for (int c = 0; c < chunks; c++)
         {
-            const uint64_t lo = batch * c / chunks, hi = batch * (c + 1) / chunks;
+            acc += w[c];
+            cut[c + 1] = (c + 1 == chunks) ? batch : static_cast<uint64_t>(batch * (acc / tot));
+        }
+        for (int c = 0; c < chunks; c++)
+        {
+            const uint64_t lo = cut[c], hi = cut[c + 1];
             first_.push_back(lo);
             part_.push_back(std::unique_ptr<BatchT>(make(hi - lo)));
             internal::lexls_b200_check(lexls_b200_set_async_copies(part_.back()->handle(), 1));

@@ -50,3 +50,14 @@ def test_two_rank_gather_gloo(tmp_path, oracle):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(os.path.join(str(tmp_path), "ok")).read() == "1"
+
+
+def test_tapered_ranges_cover_the_batch_without_empty_chunks():
+    from lexls_b200.shard import tapered_ranges
+    for batch in (1, 2, 3, 15, 63, 64, 65, 1000, 16384, 65536):
+        for chunks in (1, 2, 3, 4, 5, 8):
+            r = tapered_ranges(batch, chunks)
+            assert r[0][0] == 0 and r[-1][1] == batch
+            assert all(hi > lo for lo, hi in r) and all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+            if chunks >= 3 and batch >= 8192:
+                assert (r[-1][1] - r[-1][0]) * 3 < (r[0][1] - r[0][0])  # the last chunk is the small one
