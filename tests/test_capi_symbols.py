@@ -50,3 +50,13 @@ def test_product_does_not_reference_the_oracle():
                             if re.search(r"(import oracle|from oracle|liblexls_oracle|#include.*oracle)", s) and not s.startswith(("//", "#", "*")):
                                 bad.append((f, s))
     assert not bad, bad
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/lexls_b200.h is the FFI boundary: it must compile as C (no C++ types, no torch types)."""
+    import subprocess
+    src = tmp_path / "hc.c"
+    src.write_text('#include "lexls_b200.h"\nint main(void) { lexls_b200_params_t p; lexls_b200_batch_t *h = 0; (void)p; (void)h; return 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)],
+                   check=True, capture_output=True, text=True)
